@@ -1,0 +1,155 @@
+"""
+ctypes binding of libghn3_b200.so (the C ABI declared in include/ghn3_b200.h).
+
+There is no fallback: if the library is missing it is built with nvcc (ghn3_b200.build); if that fails, or a call
+returns a non-zero status, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libghn3_b200.so')
+
+BF16, TF32, F32 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+SCATTER_CHUNK = 4096
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class SpdArgs(C.Structure):
+    _fields_ = [('n_graphs', i32), ('cutoff', i32), ('node_off', vp), ('edge_off', vp), ('mat_off', vp),
+                ('edge_src', vp), ('edge_dst', vp), ('max_nodes', i32), ('total_nodes', i32), ('total_edges', i32),
+                ('bits_total', i64), ('mat_total', i64), ('adj_bits', vp), ('bits_off', vp), ('spd', vp)]
+
+
+class DeriveArgs(C.Structure):
+    _fields_ = [('n_graphs', i32), ('vmax', i32), ('node_off', vp), ('mat_off', vp), ('max_nodes', i32),
+                ('total_nodes', i32), ('spd', vp), ('pair', vp), ('deg_in', vp), ('deg_out', vp), ('dist0', vp)]
+
+
+class NodeFeaturesArgs(C.Structure):
+    _fields_ = [('total_nodes', i32), ('hid', i32), ('op', vp), ('shape_idx', vp), ('deg_in', vp), ('deg_out', vp),
+                ('dist0', vp), ('embed_op', vp), ('embed_ch', vp), ('embed_sp', vp), ('cent_in', vp),
+                ('cent_out', vp), ('dist_embed', vp), ('x', vp)]
+
+
+class EdgeLutArgs(C.Structure):
+    _fields_ = [('hid', i32), ('heads', i32), ('vmax', i32), ('edge_embed', vp), ('w1', vp), ('b1', vp), ('w2', vp),
+                ('b2', vp), ('workspace', vp), ('lut', vp)]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [('rows', i32), ('hid', i32), ('x', vp), ('gamma', vp), ('beta', vp), ('out', vp), ('out_dtype', i32),
+                ('dst_row', vp), ('out_f32', vp)]
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [('a_row0', i32), ('b_row0', i32), ('m', i32), ('n', i32), ('d_off', i64), ('ldd', i32),
+                ('bias_off', i32)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('a', vp), ('a_rows', i64), ('lda', i64), ('b', vp), ('b_rows', i64), ('ldb', i64), ('k', i32),
+                ('in_dtype', i32), ('d', vp), ('out_dtype', i32), ('bias', vp), ('act', i32), ('accumulate', i32),
+                ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32)]
+
+
+class GemmSimtArgs(C.Structure):
+    _fields_ = [('a', vp), ('sam', i64), ('sak', i64), ('b', vp), ('sbn', i64), ('sbk', i64), ('bias', vp),
+                ('d', vp), ('sdm', i64), ('sdn', i64), ('m', i32), ('n', i32), ('k', i32), ('relu_a', i32),
+                ('act', i32), ('batch', i32), ('a_bs', i64), ('d_bs', i64)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [('n_graphs', i32), ('hid', i32), ('heads', i32), ('max_nodes', i32), ('lut_size', i32),
+                ('node_off', vp), ('mat_off', vp), ('qkv', vp), ('dtype', i32), ('pair', vp), ('lut', vp),
+                ('out', vp)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [('ln1_w', vp), ('ln1_b', vp), ('w_qkv', vp), ('w_out', vp), ('b_out', vp), ('ln2_w', vp),
+                ('ln2_b', vp), ('w_ff1', vp), ('b_ff1', vp), ('w_ff2', vp), ('b_ff2', vp)]
+
+
+class GraphormerArgs(C.Structure):
+    _fields_ = [('hid', i32), ('heads', i32), ('layers', i32), ('dtype', i32), ('layers_host', C.POINTER(LayerWeights)),
+                ('ln_w', vp), ('ln_b', vp),
+                ('n_graphs', i32), ('total_nodes', i32), ('max_nodes', i32), ('lut_size', i32),
+                ('node_off', vp), ('mat_off', vp), ('pair', vp), ('lut', vp), ('x', vp),
+                ('h', vp), ('qkv', vp), ('ff', vp),
+                ('dec_in', vp), ('dec_dtype', i32), ('dst_row', vp), ('emb_f32', vp)]
+
+
+class ScatterDesc(C.Structure):
+    _fields_ = [('dst', vp), ('src', vp), ('numel', i64), ('chunk0', i64), ('t1', i32), ('t2', i32), ('t3', i32),
+                ('so', i32), ('si', i32), ('ld', i32), ('ca', i32), ('ra', i32), ('kh_src', i32), ('kw_src', i32),
+                ('cy', i32), ('cx', i32), ('scale', f32), ('mode', i32)]
+
+
+class ScatterArgs(C.Structure):
+    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64)]
+
+
+class SumsqArgs(C.Structure):
+    _fields_ = [('ptrs', vp), ('numels', vp), ('n', i32), ('out', vp)]
+
+
+assert C.sizeof(ScatterDesc) == 88 and C.sizeof(GemmProblem) == 32
+
+SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
+           'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
+           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32']
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Loads (building first if necessary) the CUDA library. Raises if it cannot be had -- no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError('ghn3_b200: %s is missing; run `python -m ghn3_b200.build`' % LIB_PATH)
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        if not hasattr(lib, s):
+            raise RuntimeError('ghn3_b200: %s does not export %s' % (LIB_PATH, s))
+    lib.ghn3_last_error.restype = C.c_char_p
+    lib.ghn3_launch_count.restype = C.c_int64
+    for s in SYMBOLS[3:14]:
+        getattr(lib, s).restype = C.c_int
+        getattr(lib, s).argtypes = [C.c_void_p, C.c_void_p]
+    lib.ghn3_convert_f32.restype = C.c_int
+    lib.ghn3_convert_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ghn3_last_error().decode(errors='replace')
+        raise RuntimeError('ghn3_b200: %s failed (status %d): %s' % (what, rc, msg))
+
+
+def call(name, args, stream):
+    """Invokes int ghn3_<name>(const Args*, stream) and raises on a non-zero status."""
+    lib = load()
+    check(getattr(lib, 'ghn3_' + name)(C.byref(args), C.c_void_p(stream)), 'ghn3_' + name)
+
+
+def launch_count():
+    return int(load().ghn3_launch_count())
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,107 @@
+// C-ABI plumbing: error state, launch counter, and the composite Graphormer-stack entry point.
+#include <atomic>
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace ghn3 {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream);
+int attention_impl(const ghn3_attention_args* a, cudaStream_t stream);
+int layernorm_impl(const ghn3_layernorm_args* a, cudaStream_t stream);
+
+static ghn3_gemm_args linear(const void* x, int64_t rows, int k, const void* w, int n, const float* bias, void* out,
+                             int in_dtype, int out_dtype, int act, int accumulate) {
+  ghn3_gemm_args g = {};
+  g.a = x; g.a_rows = rows; g.lda = k;
+  g.b = w; g.b_rows = n; g.ldb = k;
+  g.k = k;
+  g.in_dtype = in_dtype;
+  g.d = out; g.out_dtype = out_dtype;
+  g.bias = bias;
+  g.act = act;
+  g.accumulate = accumulate;
+  g.single.a_row0 = 0; g.single.b_row0 = 0;
+  g.single.m = (int32_t)rows; g.single.n = n;
+  g.single.d_off = 0; g.single.ldd = n;
+  g.single.bias_off = bias ? 0 : -1;
+  return g;
+}
+
+int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
+  GHN3_REQUIRE(a != nullptr && a->layers_host != nullptr, "ghn3_graphormer_stack: null args");
+  GHN3_REQUIRE(a->dtype == GHN3_BF16 || a->dtype == GHN3_TF32, "ghn3_graphormer_stack: dtype must be BF16 or TF32");
+  GHN3_REQUIRE(a->hid % 16 == 0, "ghn3_graphormer_stack: hid must be a multiple of 16");
+  if (a->total_nodes <= 0) return GHN3_OK;
+  const int C = a->hid, M = a->total_nodes, dt = a->dtype;
+  int rc;
+  for (int l = 0; l < a->layers; ++l) {
+    const ghn3_layer_weights& w = a->layers_host[l];
+    ghn3_layernorm_args ln = {};
+    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = w.ln1_w; ln.beta = w.ln1_b; ln.out = a->h; ln.out_dtype = dt;
+    if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+
+    ghn3_gemm_args qkv = linear(a->h, M, C, w.w_qkv, 3 * C, nullptr, a->qkv, dt, dt, GHN3_ACT_NONE, 0);
+    if ((rc = gemm_impl(&qkv, stream)) != GHN3_OK) return rc;
+
+    ghn3_attention_args at = {};
+    at.n_graphs = a->n_graphs; at.hid = C; at.heads = a->heads; at.max_nodes = a->max_nodes;
+    at.lut_size = a->lut_size; at.node_off = a->node_off; at.mat_off = a->mat_off;
+    at.qkv = a->qkv; at.dtype = dt; at.pair = a->pair; at.lut = a->lut; at.out = a->h;
+    if ((rc = attention_impl(&at, stream)) != GHN3_OK) return rc;
+
+    ghn3_gemm_args proj = linear(a->h, M, C, w.w_out, C, w.b_out, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1);
+    if ((rc = gemm_impl(&proj, stream)) != GHN3_OK) return rc;
+
+    ln.gamma = w.ln2_w; ln.beta = w.ln2_b;
+    if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+
+    ghn3_gemm_args ff1 = linear(a->h, M, C, w.w_ff1, 4 * C, w.b_ff1, a->ff, dt, dt, GHN3_ACT_GELU, 0);
+    if ((rc = gemm_impl(&ff1, stream)) != GHN3_OK) return rc;
+
+    ghn3_gemm_args ff2 = linear(a->ff, M, 4 * C, w.w_ff2, C, w.b_ff2, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1);
+    if ((rc = gemm_impl(&ff2, stream)) != GHN3_OK) return rc;
+  }
+  if (a->ln_w != nullptr) {
+    ghn3_layernorm_args ln = {};
+    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = a->ln_w; ln.beta = a->ln_b;
+    ln.out = a->dec_in; ln.out_dtype = a->dec_dtype; ln.dst_row = a->dst_row; ln.out_f32 = a->emb_f32;
+    if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+  } else {
+    set_error("ghn3_graphormer_stack: layernorm=False is not supported by the CUDA path");
+    return GHN3_ERR_UNSUPPORTED;
+  }
+  return GHN3_OK;
+}
+
+}  // namespace ghn3
+
+extern "C" const char* ghn3_last_error(void) { return ghn3::g_error; }
+extern "C" int ghn3_abi_version(void) { return 1; }
+extern "C" int64_t ghn3_launch_count(void) { return ghn3::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream) {
+  return ghn3::graphormer_impl(args, (cudaStream_t)stream);
+}

@@ -1,0 +1,75 @@
+// Shared helpers for the ghn3_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ghn3_b200.h"
+
+namespace ghn3 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define GHN3_REQUIRE(cond, ...)                \
+  do {                                         \
+    if (!(cond)) {                             \
+      ghn3::set_error(__VA_ARGS__);            \
+      return GHN3_ERR_BAD_ARG;                 \
+    }                                          \
+  } while (0)
+
+#define GHN3_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t err__ = (expr);                                                              \
+    if (err__ != cudaSuccess) {                                                              \
+      ghn3::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return GHN3_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define GHN3_LAUNCH_CHECK(name)                                                              \
+  do {                                                                                       \
+    cudaError_t err__ = cudaGetLastError();                                                  \
+    if (err__ != cudaSuccess) {                                                              \
+      ghn3::set_error("launch of %s failed: %s", name, cudaGetErrorString(err__));           \
+      return GHN3_ERR_CUDA;                                                                  \
+    }                                                                                        \
+    ghn3::count_launch();                                                                    \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// fp32 -> tf32 with round-to-nearest (ties away), result kept in an fp32 container.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// Typed loads/stores used by kernels templated on the activation storage type.
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+int num_sms();
+
+}  // namespace ghn3

@@ -1,0 +1,337 @@
+// LayerNorm, fused bias-aware attention, small strided SIMT GEMM and dtype conversion (sm_100a).
+//   ghn3_layernorm   reference ghn3/graphormer.py:239,241 and ghn3/nn.py:262-263
+//   ghn3_attention   reference ghn3/graphormer.py:121-140 (QK^T * d^-1/2 + edge bias, softmax, PV), flash-style:
+//                    no (B,H,N,N) logits and no (B,N,N,H) bias tensor are ever materialised
+//   ghn3_gemm_simt   classification heads (ghn3/nn.py:757-758, 294) whose operands are transposed views
+#include "common.cuh"
+
+namespace ghn3 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (C <= 1024), two-pass mean / variance in fp32
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const ghn3_layernorm_args a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  const int C = a.hid, C4 = C >> 2;
+  const float4* x4 = (const float4*)(a.x + (int64_t)row * C);
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < C4) {
+      v[i] = x4[f];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < C4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+  const int orow = a.dst_row ? a.dst_row[row] : row;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < C4) {
+      const float4 g = ((const float4*)a.gamma)[f];
+      const float4 b = ((const float4*)a.beta)[f];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (a.out_f32) ((float4*)(a.out_f32 + (int64_t)row * C))[f] = y;
+      if (orow >= 0 && a.out) {
+        if (a.out_dtype == GHN3_BF16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+          uint2 pk;
+          pk.x = *(uint32_t*)&lo;
+          pk.y = *(uint32_t*)&hi;
+          ((uint2*)((__nv_bfloat16*)a.out + (int64_t)orow * C))[f] = pk;
+        } else {
+          if (a.out_dtype == GHN3_TF32) {
+            y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w);
+          }
+          ((float4*)((float*)a.out + (int64_t)orow * C))[f] = y;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Attention. CTA = (graph, head, 16 queries); 8 warps, 2 queries per warp. Keys are processed in tiles of KT = 256
+// staged in shared memory as fp32 (rows padded to D+1 words: conflict-free when lanes walk over keys). Lane l
+// scores keys l, l+32, ...; the tile maximum and the normaliser are combined with warp shuffles; every lane keeps
+// a partial output over its own keys which is reduced across the warp once at the end.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAttnKT = 256;
+constexpr int kAttnQPerWarp = 2;
+constexpr int kAttnWarps = 8;
+constexpr int kAttnQT = kAttnQPerWarp * kAttnWarps;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_attention_args a) {
+  extern __shared__ float attn_smem[];
+  constexpr int DP = D + 1;
+  float* sK = attn_smem;                 // [KT][DP]
+  float* sV = sK + kAttnKT * DP;         // [KT][DP]
+  float* sLut = sV + kAttnKT * DP;       // [lut_size]
+
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int n0 = a.node_off[g];
+  const int n = a.node_off[g + 1] - n0;
+  const int q0 = blockIdx.x * kAttnQT;
+  if (q0 >= n) return;
+  const int ld = (n + 15) & ~15;
+  const int C = a.hid, C3 = 3 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qkv = (const T*)a.qkv + (int64_t)n0 * C3;
+  const uint16_t* pair = a.pair + a.mat_off[g];
+  const float scale_log2 = rsqrtf((float)D) * 1.44269504088896340736f;
+  constexpr float kLog2e = 1.44269504088896340736f;
+
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i] * kLog2e;
+
+  float q[kAttnQPerWarp][D], acc[kAttnQPerWarp][D], m[kAttnQPerWarp], l[kAttnQPerWarp];
+  int qi[kAttnQPerWarp];
+#pragma unroll
+  for (int t = 0; t < kAttnQPerWarp; ++t) {
+    qi[t] = q0 + warp * kAttnQPerWarp + t;
+    const bool ok = qi[t] < n;
+    const T* qp = qkv + (int64_t)(ok ? qi[t] : 0) * C3 + h * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      q[t][d] = ok ? to_float(qp[d]) * scale_log2 : 0.f;
+      acc[t][d] = 0.f;
+    }
+    m[t] = -INFINITY;
+    l[t] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < n; k0 += kAttnKT) {
+    const int kt = min(kAttnKT, n - k0);
+    __syncthreads();   // previous tile fully consumed (also orders the LUT fill on the first iteration)
+    for (int idx = threadIdx.x; idx < kt * D; idx += blockDim.x) {
+      const int j = idx / D, d = idx - j * D;
+      const T* rowp = qkv + (int64_t)(k0 + j) * C3 + h * D + d;
+      sK[j * DP + d] = to_float(rowp[C]);
+      sV[j * DP + d] = to_float(rowp[2 * C]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kAttnQPerWarp; ++t) {
+      if (qi[t] >= n) continue;   // warp-uniform
+      const uint16_t* prow = pair + (int64_t)qi[t] * ld + k0;
+      float s[kAttnKT / 32];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < kAttnKT / 32; ++r) {
+        const int j = lane + 32 * r;
+        float dot = -INFINITY;
+        if (j < kt) {
+          dot = sLut[prow[j]];
+          const float* kp = sK + j * DP;
+#pragma unroll
+          for (int d = 0; d < D; ++d) dot = fmaf(q[t][d], kp[d], dot);
+        }
+        s[r] = dot;
+        tmax = fmaxf(tmax, dot);
+      }
+      tmax = warp_max(tmax);
+      const float m_new = fmaxf(m[t], tmax);
+      const float corr = exp2f(m[t] - m_new);
+      m[t] = m_new;
+      l[t] *= corr;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[t][d] *= corr;
+#pragma unroll
+      for (int r = 0; r < kAttnKT / 32; ++r) {
+        const int j = lane + 32 * r;
+        if (j < kt) {
+          const float p = exp2f(s[r] - m_new);
+          l[t] += p;
+          const float* vp = sV + j * DP;
+#pragma unroll
+          for (int d = 0; d < D; ++d) acc[t][d] = fmaf(p, vp[d], acc[t][d]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int t = 0; t < kAttnQPerWarp; ++t) {
+    if (qi[t] >= n) continue;
+    const float inv = 1.f / warp_sum(l[t]);
+    float mine = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float tot = warp_sum(acc[t][d]);
+      if (lane == d) mine = tot * inv;
+    }
+    if (lane < D) {
+      T* op = (T*)a.out + (int64_t)(n0 + qi[t]) * C + h * D + lane;
+      if (sizeof(T) == 4 && a.dtype == GHN3_TF32) mine = round_tf32(mine);
+      *op = from_float<T>(mine);
+    }
+  }
+}
+
+template <typename T, int D>
+static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
+  const int smem = (2 * kAttnKT * (D + 1) + a->lut_size) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    GHN3_CUDA(cudaFuncSetAttribute(attention_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) {
+    set_error("ghn3_attention: lut too large for shared memory");
+    return GHN3_ERR_UNSUPPORTED;
+  }
+  const dim3 grid((unsigned)ceil_div(a->max_nodes, kAttnQT), (unsigned)a->heads, (unsigned)a->n_graphs);
+  attention_kernel<T, D><<<grid, kAttnWarps * 32, smem, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("attention_kernel");
+  return GHN3_OK;
+}
+
+int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
+  GHN3_REQUIRE(a != nullptr, "ghn3_attention: null args");
+  GHN3_REQUIRE(a->heads > 0 && a->hid % a->heads == 0, "ghn3_attention: hid must be divisible by heads");
+  GHN3_REQUIRE(a->dtype == GHN3_BF16 || a->dtype == GHN3_TF32, "ghn3_attention: dtype must be BF16 or TF32");
+  if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
+  const int D = a->hid / a->heads;
+  const bool bf = a->dtype == GHN3_BF16;
+#define GHN3_ATTN_CASE(DV)                                                     \
+  if (D == DV) return bf ? launch_attention<__nv_bfloat16, DV>(a, stream) : launch_attention<float, DV>(a, stream);
+  GHN3_ATTN_CASE(4)
+  GHN3_ATTN_CASE(8)
+  GHN3_ATTN_CASE(16)
+  GHN3_ATTN_CASE(24)
+  GHN3_ATTN_CASE(32)
+#undef GHN3_ATTN_CASE
+  set_error("ghn3_attention: head dim %d is not supported (4, 8, 16, 24, 32)", D);
+  return GHN3_ERR_UNSUPPORTED;
+}
+
+int layernorm_impl(const ghn3_layernorm_args* a, cudaStream_t stream) {
+  GHN3_REQUIRE(a != nullptr, "ghn3_layernorm: null args");
+  GHN3_REQUIRE(a->hid > 0 && a->hid % 4 == 0 && a->hid <= 1024, "ghn3_layernorm: hid must be a multiple of 4, <= 1024");
+  GHN3_REQUIRE(a->out_dtype >= GHN3_BF16 && a->out_dtype <= GHN3_F32, "ghn3_layernorm: bad out_dtype");
+  if (a->rows <= 0) return GHN3_OK;
+  layernorm_kernel<<<(unsigned)ceil_div(a->rows, 8), 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("layernorm_kernel");
+  return GHN3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Strided fp32 GEMM on CUDA cores: 64 x 64 tile, 256 threads, 4 x 4 outputs per thread, K step 16
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const ghn3_gemm_simt_args a) {
+  __shared__ float sA[16][65];
+  __shared__ float sB[16][65];
+  const int bz = blockIdx.z;
+  const float* A = a.a + (int64_t)bz * a.a_bs;
+  float* Dp = a.d + (int64_t)bz * a.d_bs;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < a.k; k0 += 16) {
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+      const int kk = idx & 15, r = idx >> 4;
+      const int k = k0 + kk;
+      float va = 0.f, vb = 0.f;
+      if (k < a.k) {
+        if (m0 + r < a.m) {
+          va = A[(int64_t)(m0 + r) * a.sam + (int64_t)k * a.sak];
+          if (a.relu_a) va = fmaxf(va, 0.f);
+        }
+        if (n0 + r < a.n) vb = a.b[(int64_t)(n0 + r) * a.sbn + (int64_t)k * a.sbk];
+      }
+      sA[kk][r] = va;
+      sB[kk][r] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float ra[4], rb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ra[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rb[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ra[i], rb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.n) continue;
+      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      if (a.act == GHN3_ACT_RELU) v = fmaxf(v, 0.f);
+      Dp[(int64_t)m * a.sdm + (int64_t)n * a.sdn] = v;
+    }
+  }
+}
+
+__global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t n, int dst_dtype) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = src[i];
+    if (dst_dtype == GHN3_BF16) ((__nv_bfloat16*)dst)[i] = __float2bfloat16_rn(v);
+    else ((float*)dst)[i] = dst_dtype == GHN3_TF32 ? round_tf32(v) : v;
+  }
+}
+
+}  // namespace ghn3
+
+using namespace ghn3;
+
+extern "C" int ghn3_layernorm(const ghn3_layernorm_args* a, ghn3_stream_t stream) {
+  return layernorm_impl(a, (cudaStream_t)stream);
+}
+
+extern "C" int ghn3_attention(const ghn3_attention_args* a, ghn3_stream_t stream) {
+  return attention_impl(a, (cudaStream_t)stream);
+}
+
+extern "C" int ghn3_gemm_simt(const ghn3_gemm_simt_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_gemm_simt: null args");
+  if (a->m <= 0 || a->n <= 0) return GHN3_OK;
+  const int batch = a->batch <= 0 ? 1 : a->batch;
+  const dim3 grid((unsigned)ceil_div(a->n, 64), (unsigned)ceil_div(a->m, 64), (unsigned)batch);
+  gemm_simt_kernel<<<grid, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("gemm_simt_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(dst_dtype >= GHN3_BF16 && dst_dtype <= GHN3_F32, "ghn3_convert_f32: bad dtype");
+  if (n <= 0) return GHN3_OK;
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 16);
+  convert_kernel<<<blocks, 256, 0, stream>>>(src, dst, n, dst_dtype);
+  GHN3_LAUNCH_CHECK("convert_kernel");
+  return GHN3_OK;
+}

@@ -1,0 +1,433 @@
+// D = epilogue(A . B^T + bias) on the 5th-generation tensor cores (tcgen05.mma), sm_100a.
+//
+// Replaces every nn.Linear on the GHN-3 hot path (reference ghn3/graphormer.py:38-44,121,141 and
+// ghn3/nn.py:738,748,758,289-294). See include/ghn3_b200.h (ghn3_gemm) for the contract.
+//
+// Structure (one 128 x BN output tile per CTA, 6 warps):
+//   warp 0 / one lane : TMA producer  -- cp.async.bulk.tensor 2D boxes of 128 bytes x rows, SWIZZLE_128B, into a
+//                                        kStages-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1 / one lane : MMA issuer    -- tcgen05.mma.cta_group::1 (kind::f16 for bf16, kind::tf32 for fp32 storage),
+//                                        128 x BN fp32 accumulator in TMEM; tcgen05.commit frees ring slots
+//   warps 2..5        : epilogue      -- tcgen05.ld 32 lanes x 32 columns, bias / ReLU / GELU / residual, stores
+// Two CTAs are resident per SM (3 stages x 32 KB each, 2 x 128 TMEM columns) so one CTA's epilogue overlaps the
+// other's main loop. Rows/columns outside a problem are loaded (TMA zero-fills outside the tensor) and masked at
+// the store; every output element depends only on its own A row and B row, so neighbours' data never leaks in.
+#include "common.cuh"
+
+namespace ghn3 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ghn3 gemm: mbarrier timeout (block %d, thread %d, bar %u, parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// 32 TMEM lanes (one per thread of the warp) x 32 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes with SWIZZLE_128B
+// (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), LBO in [16,30) (unused for swizzled K-major, 1),
+// SBO in [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A and B K-major.
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int m, int n) {
+  const uint32_t fmt = tf32 ? 2u : 1u;   // F16F32Format: BF16 = 1, TF32 = 2
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmKernelArgs {
+  ghn3_gemm_problem single;
+  const ghn3_gemm_problem* problems;
+  const int4* tiles;
+  void* d;
+  const float* bias;
+  int32_t k;
+  int32_t out_dtype;
+  int32_t act;
+  int32_t accumulate;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == GHN3_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == GHN3_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;   // bytes of K per ring stage row = one swizzle span
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+
+template <int BN>
+constexpr int gemm_smem_bytes() {
+  return kStages * (kBlockM + BN) * kRowBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+template <bool kTf32, int BN>
+__global__ void __launch_bounds__(kThreads, (BN <= 128) ? 2 : 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmKernelArgs args) {
+  constexpr int EB = kTf32 ? 4 : 2;
+  constexpr int BK = kRowBytes / EB;         // elements of K per stage
+  constexpr int kMmaPerStage = 4;            // 128 B / 32 B per tcgen05.mma (UMMA_K = 16 bf16 / 8 tf32)
+  constexpr uint32_t A_BYTES = kBlockM * kRowBytes;
+  constexpr uint32_t B_BYTES = BN * kRowBytes;
+  constexpr uint32_t kIdesc = make_idesc(kTf32, kBlockM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + kStages * A_BYTES;
+  const uint32_t bar_base = sB + kStages * B_BYTES;          // 8-byte aligned
+  const uint32_t full_bar = bar_base;                         // kStages barriers
+  const uint32_t empty_bar = bar_base + 8 * kStages;
+  const uint32_t tmem_full_bar = bar_base + 16 * kStages;
+  const uint32_t tmem_slot = bar_base + 16 * kStages + 8;
+  uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  ghn3_gemm_problem p;
+  int mt, nt;
+  if (args.tiles != nullptr) {
+    const int4 t = args.tiles[blockIdx.x];
+    p = args.problems[t.x];
+    mt = t.y;
+    nt = t.z;
+  } else {
+    p = args.single;
+    mt = blockIdx.y;
+    nt = blockIdx.x;
+  }
+  const int num_kb = (args.k + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int a_row = p.a_row0 + mt * kBlockM;
+      const int b_row = p.b_row0 + nt * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + B_BYTES);
+        tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, kb * BK, a_row);
+        tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, b_row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint64_t da = make_smem_desc(sA + s * A_BYTES);
+        const uint64_t db = make_smem_desc(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < kMmaPerStage; ++k) {
+          // advancing K inside the 128B swizzle span: +32 bytes = +2 in the (addr >> 4) field
+          umma<kTf32>(tmem_base, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tcgen05_commit(empty_bar + 8 * s);       // slot reusable once these MMAs have read it
+      }
+      tcgen05_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = mt * kBlockM + row;
+    const bool row_ok = m < p.m;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int64_t d_row = p.d_off + (int64_t)m * p.ldd;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int n0 = nt * BN + c0;
+      if (n0 >= p.n) break;                      // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int ncols = min(32, p.n - n0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (p.bias_off >= 0 && j < ncols) x += __ldg(args.bias + p.bias_off + n0 + j);
+          v[j] = apply_act(x, args.act);
+        }
+        if (args.out_dtype == GHN3_BF16) {
+          __nv_bfloat16* dptr = (__nv_bfloat16*)args.d + d_row + n0;
+          if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j + 0], v[j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
+              *(uint4*)(dptr + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) dptr[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* dptr = (float*)args.d + d_row + n0;
+          const bool tf = args.out_dtype == GHN3_TF32;
+          if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (args.accumulate) {
+                const float4 old = *(const float4*)(dptr + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              *(float4*)(dptr + j) = o;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) {
+              float o = v[j];
+              if (args.accumulate) o += dptr[j];
+              dptr[j] = tf ? round_tf32(o) : o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      return nullptr;
+    }
+    fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, bool tf32,
+                            int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return GHN3_ERR_CUDA;
+  }
+  const int eb = tf32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * eb)};
+  cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / eb), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld k=%lld ld=%lld)", (int)r, (long long)rows,
+              (long long)k, (long long)ld);
+    return GHN3_ERR_CUDA;
+  }
+  return GHN3_OK;
+}
+
+template <bool kTf32, int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelArgs& ka, dim3 grid,
+                       cudaStream_t stream) {
+  constexpr int smem = gemm_smem_bytes<BN>();
+  static bool configured = false;
+  if (!configured) {
+    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kTf32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  gemm_tcgen05_kernel<kTf32, BN><<<grid, kThreads, smem, stream>>>(ma, mb, ka);
+  GHN3_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return GHN3_OK;
+}
+
+int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
+  GHN3_REQUIRE(a != nullptr, "ghn3_gemm: null args");
+  GHN3_REQUIRE(a->in_dtype == GHN3_BF16 || a->in_dtype == GHN3_TF32, "ghn3_gemm: in_dtype must be BF16 or TF32");
+  GHN3_REQUIRE(a->out_dtype >= GHN3_BF16 && a->out_dtype <= GHN3_F32, "ghn3_gemm: bad out_dtype");
+  const bool tf32 = a->in_dtype == GHN3_TF32;
+  const int eb = tf32 ? 4 : 2;
+  GHN3_REQUIRE(a->k > 0 && (a->lda * eb) % 16 == 0 && (a->ldb * eb) % 16 == 0,
+               "ghn3_gemm: K must be positive and row strides multiples of 16 bytes (lda=%lld ldb=%lld)",
+               (long long)a->lda, (long long)a->ldb);
+  GHN3_REQUIRE((((uintptr_t)a->a) & 15) == 0 && (((uintptr_t)a->b) & 15) == 0, "ghn3_gemm: A/B must be 16-byte aligned");
+  GHN3_REQUIRE(!a->accumulate || a->out_dtype != GHN3_BF16, "ghn3_gemm: accumulate needs an fp32 output");
+  const int bn = a->block_n == 0 ? 128 : a->block_n;
+  GHN3_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "ghn3_gemm: block_n must be 32/64/128/256");
+
+  dim3 grid;
+  if (a->problems != nullptr) {
+    GHN3_REQUIRE(a->tiles != nullptr && a->n_tiles >= 0, "ghn3_gemm: grouped launch needs a tile list");
+    if (a->n_tiles == 0) return GHN3_OK;
+    grid = dim3((unsigned)a->n_tiles, 1, 1);
+  } else {
+    if (a->single.m <= 0 || a->single.n <= 0) return GHN3_OK;
+    grid = dim3((unsigned)ceil_div(a->single.n, bn), (unsigned)ceil_div(a->single.m, kBlockM), 1);
+  }
+
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, a->a, a->a_rows, a->k, a->lda, tf32, kBlockM);
+  if (rc != GHN3_OK) return rc;
+  rc = make_operand_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, bn);
+  if (rc != GHN3_OK) return rc;
+
+  GemmKernelArgs ka;
+  ka.single = a->single;
+  ka.problems = a->problems;
+  ka.tiles = (const int4*)a->tiles;
+  ka.d = a->d;
+  ka.bias = a->bias;
+  ka.k = a->k;
+  ka.out_dtype = a->out_dtype;
+  ka.act = a->act;
+  ka.accumulate = a->accumulate;
+
+#define GHN3_GEMM_CASE(TF, BNV) \
+  if (tf32 == TF && bn == BNV) return launch_gemm<TF, BNV>(ma, mb, ka, grid, stream);
+  GHN3_GEMM_CASE(false, 32)
+  GHN3_GEMM_CASE(false, 64)
+  GHN3_GEMM_CASE(false, 128)
+  GHN3_GEMM_CASE(false, 256)
+  GHN3_GEMM_CASE(true, 32)
+  GHN3_GEMM_CASE(true, 64)
+  GHN3_GEMM_CASE(true, 128)
+  GHN3_GEMM_CASE(true, 256)
+#undef GHN3_GEMM_CASE
+  set_error("ghn3_gemm: unsupported configuration");
+  return GHN3_ERR_UNSUPPORTED;
+}
+
+}  // namespace ghn3
+
+extern "C" int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream) {
+  return ghn3::gemm_impl(args, (cudaStream_t)stream);
+}

@@ -1,0 +1,314 @@
+/*
+ * ghn3_b200 -- C ABI of the B200-native GHN-3 parameter-prediction hot path.
+ *
+ * The reference (SamsungSAILMontreal/ghn3) is pure Python/PyTorch and has no FFI layer: its boundary is the Python
+ * API (`GHN3.forward`, ghn3/nn.py:186) and the checkpoint layout. This header is the boundary UNDER that API: each
+ * entry point replaces one group of ATen calls of the reference (cited per function, paths relative to the
+ * reference root). The Python host (ghn3_b200/nn.py) binds these symbols with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions:
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - the caller (PyTorch) owns all memory; the library never allocates device memory, never frees, never retains
+ *    pointers after a call returns; target parameters are written in place;
+ *  - all work is enqueued on the caller's stream; no internal synchronisation; re-entrant;
+ *  - return 0 on success or a negative ghn3_status; ghn3_last_error() returns a per-thread message;
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with GHN3_ERR_CUDA.
+ */
+#ifndef GHN3_B200_H_
+#define GHN3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ghn3_stream_t; /* a cudaStream_t */
+
+enum ghn3_status {
+  GHN3_OK = 0,
+  GHN3_ERR_BAD_ARG = -1,
+  GHN3_ERR_UNSUPPORTED = -2,
+  GHN3_ERR_CUDA = -3
+};
+
+enum ghn3_dtype {
+  GHN3_BF16 = 0,      /* bfloat16 storage, kind::f16 tensor-core path */
+  GHN3_TF32 = 1,      /* fp32 storage with values rounded to tf32 (cvt.rna), kind::tf32 tensor-core path */
+  GHN3_F32 = 2        /* plain fp32 (outputs only) */
+};
+
+enum ghn3_act { GHN3_ACT_NONE = 0, GHN3_ACT_RELU = 1, GHN3_ACT_GELU = 2 };
+
+const char* ghn3_last_error(void);
+int ghn3_abi_version(void);
+/* Number of kernels this library has launched since load (all streams); backs bench.py's "gpu_launches". */
+int64_t ghn3_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (2) Shortest-path "virtual edges" and structural indices  -- replaces networkx all_pairs_shortest_path_length in
+ * ghn3/graph.py:755-798 and the index arithmetic of ghn3/graphormer.py:229-237. Integer, bit-exact.
+ *
+ * A batch holds n_graphs graphs packed back to back. Graph g has n_g = node_off[g+1]-node_off[g] nodes, its 1-hop
+ * edges are edge_src/dst[edge_off[g] .. edge_off[g+1]) with LOCAL node ids, and its N x N matrices live at byte /
+ * element offset mat_off[g] with leading dimension ld_g = round_up(n_g, 16).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_graphs;
+  int32_t cutoff;            /* ve_cutoff, 1..254 (reference: 50) */
+  const int32_t* node_off;   /* [n_graphs+1] */
+  const int32_t* edge_off;   /* [n_graphs+1] */
+  const int64_t* mat_off;    /* [n_graphs+1], multiples of 16 */
+  const int32_t* edge_src;   /* [total_edges] */
+  const int32_t* edge_dst;   /* [total_edges] */
+  int32_t max_nodes;         /* max n_g over the batch (host copy, sizes the launch) */
+  int32_t total_nodes;
+  int32_t total_edges;
+  int64_t bits_total;        /* uint32 words in adj_bits = bits_off[n_graphs] */
+  int64_t mat_total;         /* bytes in spd = mat_off[n_graphs] */
+  uint32_t* adj_bits;        /* workspace: sum_g n_g * words_g uint32, words_g = ceil(n_g/32); offset = bits_off[g] */
+  const int64_t* bits_off;   /* [n_graphs+1] in uint32 units */
+  uint8_t* spd;              /* out: SPD matrices, uint8 */
+} ghn3_spd_args;
+
+/* edges -> uint8 shortest path distances (0 = none / self / beyond cutoff). */
+int ghn3_spd_bfs(const ghn3_spd_args* args, ghn3_stream_t stream);
+
+typedef struct {
+  int32_t n_graphs;
+  int32_t vmax;              /* largest SPD value that may occur (= cutoff) */
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  int32_t max_nodes;
+  int32_t total_nodes;
+  const uint8_t* spd;        /* in  */
+  uint16_t* pair;            /* out: pair[i][j] = spd[i][j] * (vmax+1) + spd[j][i]  (same offsets / ld, in elements) */
+  int32_t* deg_in;           /* out [total_nodes]: min(#{i: spd[i][j]==1}, 100)     graphormer.py:229-230 */
+  int32_t* deg_out;          /* out [total_nodes]: min(#{j: spd[i][j]==1}, 100)     graphormer.py:231 */
+  int32_t* dist0;            /* out [total_nodes]: min(spd[0][j], 1000)             graphormer.py:232 */
+} ghn3_derive_args;
+
+int ghn3_graph_derive(const ghn3_derive_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (1) Node features -- replaces embed + ppuda ShapeEncoder.forward (ghn3/nn.py:248-249) and the three structural
+ * embedding adds of ghn3/graphormer.py:230-232. fp32, same order of additions as the reference (bit-exact).
+ *   x[n] = (((E_op[op] + cat(E_ch[s0], E_ch[s1], E_sp[s2], E_sp[s3])) + E_in[deg_in]) + E_out[deg_out]) + E_dist[dist0]
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t total_nodes;
+  int32_t hid;                 /* C, multiple of 16 */
+  const int32_t* op;           /* [total_nodes] primitive id */
+  const int32_t* shape_idx;    /* [total_nodes][4] rows of embed_channel (x2) and embed_spatial (x2) */
+  const int32_t* deg_in;
+  const int32_t* deg_out;
+  const int32_t* dist0;
+  const float* embed_op;       /* [15][C] */
+  const float* embed_ch;       /* [n_ch+1][C/4] */
+  const float* embed_sp;       /* [n_sp+1][C/4] */
+  const float* cent_in;        /* [101][C] */
+  const float* cent_out;       /* [101][C] */
+  const float* dist_embed;     /* [1001][C] */
+  float* x;                    /* out [total_nodes][C] */
+} ghn3_node_features_args;
+
+int ghn3_node_features(const ghn3_node_features_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (3b) Edge-bias look-up table -- replaces EdgeEmbedding + proj_e over the materialised (B,N,N,2C) tensor
+ * (ghn3/graphormer.py:114-117) by evaluating the same MLP on the (vmax+1)^2 grid of (A_ij, A_ji) values.
+ *   lut[h][a*(vmax+1)+b] = W2[h] . relu(W1 . [E[a+2]; E[b+2]] + b1) + b2[h]
+ * workspace: 2*(vmax+1)*C floats.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t hid, heads, vmax;
+  const float* edge_embed;   /* [257][C] */
+  const float* w1;           /* [C][2C] */
+  const float* b1;           /* [C] */
+  const float* w2;           /* [H][C] */
+  const float* b2;           /* [H] */
+  float* workspace;
+  float* lut;                /* out [H][(vmax+1)^2] */
+} ghn3_edge_lut_args;
+
+int ghn3_edge_lut(const ghn3_edge_lut_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm over rows (eps 1e-5) -- ghn3/graphormer.py:239,241 and ghn3/nn.py:262-263. fp32 math; the output is
+ * written in the GEMM input dtype. Optional row scatter: out row = dst_row[r] (skip if < 0); optional fp32 copy.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows, hid;
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  void* out;                 /* [*, C] in out_dtype (GHN3_BF16 / GHN3_TF32 / GHN3_F32) */
+  int32_t out_dtype;
+  const int32_t* dst_row;    /* optional [rows] */
+  float* out_f32;            /* optional [rows][C] un-permuted fp32 copy (return_embeddings) */
+} ghn3_layernorm_args;
+
+int ghn3_layernorm(const ghn3_layernorm_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (3a)/(4a) Tensor-core GEMM  D = epilogue(A . B^T + bias)  -- replaces every nn.Linear of the Graphormer stack
+ * (ghn3/graphormer.py:38-44,121,141) and of the decoders (ghn3/nn.py:738,748,758,289-294).
+ * A [a_rows][K] and B [b_rows][K] are K-major (row-major with leading dims lda / ldb), both in `in_dtype`.
+ * tcgen05.mma (kind::f16 or kind::tf32), accumulators in TMEM, operands staged by TMA with 128B swizzle.
+ * A launch runs either ONE problem (`problems == NULL`, described by `single`) or a GROUP of problems that share
+ * A, B, K and the epilogue: `tiles[t] = {problem, m_tile, n_tile, 0}` with 128 x block_n tiles.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t a_row0;     /* first row of A used by the problem */
+  int32_t b_row0;     /* first row of B (output feature) used by the problem */
+  int32_t m, n;       /* extent */
+  int64_t d_off;      /* element offset of D[0][0] in the output buffer */
+  int32_t ldd;        /* leading dimension of D, elements */
+  int32_t bias_off;   /* element offset into bias for column 0, or -1 for no bias */
+} ghn3_gemm_problem;
+
+typedef struct {
+  const void* a; int64_t a_rows; int64_t lda;
+  const void* b; int64_t b_rows; int64_t ldb;
+  int32_t k;
+  int32_t in_dtype;          /* GHN3_BF16 | GHN3_TF32 */
+  void* d;
+  int32_t out_dtype;         /* GHN3_BF16 | GHN3_TF32 | GHN3_F32 */
+  const float* bias;
+  int32_t act;               /* ghn3_act, applied after the bias */
+  int32_t accumulate;        /* 1: D (fp32) += result   (residual update in place, graphormer.py:240-241) */
+  ghn3_gemm_problem single;
+  const ghn3_gemm_problem* problems;   /* device, or NULL */
+  const int32_t* tiles;                /* device int32[n_tiles][4], or NULL */
+  int32_t n_tiles;
+  int32_t block_n;           /* 0 = default (128); 32/64/128/256 */
+} ghn3_gemm_args;
+
+int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);
+
+/* Small strided fp32 GEMM on CUDA cores for shapes that are too small or too oddly laid out for TMA:
+ *   D[m][n] = act(bias[n] + sum_k f(A[m*sam + k*sak]) * B[n*sbn + k*sbk]),  f = relu if relu_a else identity.
+ * Used for the classification heads (ghn3/nn.py:757-758, 294). */
+typedef struct {
+  const float* a; int64_t sam, sak;
+  const float* b; int64_t sbn, sbk;
+  const float* bias;
+  float* d; int64_t sdm, sdn;
+  int32_t m, n, k;
+  int32_t relu_a;
+  int32_t act;
+  int32_t batch; int64_t a_bs, d_bs;   /* optional batch over A and D (B and bias shared) */
+} ghn3_gemm_simt_args;
+
+int ghn3_gemm_simt(const ghn3_gemm_simt_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (3b) Fused multi-head attention with the SPD/edge bias -- replaces ghn3/graphormer.py:121-140
+ * (QK^T * d^-1/2 + bias, softmax, PV) without materialising (B,H,N,N) or (B,N,N,H).
+ * Graphs are packed (no padding => no mask); logit(i,j,h) += lut[h][pair[i][j]].
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_graphs, hid, heads, max_nodes;
+  int32_t lut_size;          /* (vmax+1)^2 */
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  const void* qkv;           /* [total_nodes][3C] in dtype: q | k | v, head-major inside each */
+  int32_t dtype;             /* GHN3_BF16 | GHN3_TF32 (fp32 storage) */
+  const uint16_t* pair;
+  const float* lut;          /* [H][lut_size] */
+  void* out;                 /* [total_nodes][C] in dtype */
+} ghn3_attention_args;
+
+int ghn3_attention(const ghn3_attention_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * The whole Graphormer stack on packed node features (ghn3/nn.py:258-263, graphormer.py:208-248): per layer
+ * LN1 -> QKV GEMM -> attention -> out-proj GEMM (+residual) -> LN2 -> FFN1 GEMM (+GELU) -> FFN2 GEMM (+residual),
+ * then the final LayerNorm with row scatter into the decoder input buffers. One call enqueues 7*L+1 kernels.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* w_qkv;                       /* [3C][C] */
+  const void* w_out; const float* b_out;   /* [C][C] */
+  const float* ln2_w; const float* ln2_b;
+  const void* w_ff1; const float* b_ff1;   /* [4C][C] */
+  const void* w_ff2; const float* b_ff2;   /* [C][4C] */
+} ghn3_layer_weights;
+
+typedef struct {
+  int32_t hid, heads, layers, dtype;
+  const ghn3_layer_weights* layers_host;   /* HOST array [layers] of device pointers */
+  const float* ln_w; const float* ln_b;    /* final LayerNorm, may be NULL (layernorm=False) */
+  /* batch */
+  int32_t n_graphs, total_nodes, max_nodes, lut_size;
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  const uint16_t* pair;
+  const float* lut;
+  float* x;                  /* in/out [total_nodes][C] fp32 residual stream */
+  /* workspace, all [total_nodes][*] in dtype */
+  void* h;                   /* [total_nodes][C]   LN output / attention output */
+  void* qkv;                 /* [total_nodes][3C] */
+  void* ff;                  /* [total_nodes][4C] */
+  /* final LN outputs */
+  void* dec_in; int32_t dec_dtype;         /* rows scattered by dst_row */
+  const int32_t* dst_row;                  /* [total_nodes] or NULL (identity) */
+  float* emb_f32;                          /* optional [total_nodes][C] */
+} ghn3_graphormer_args;
+
+int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (4b) Tile / slice / normalise / scatter -- replaces _tile_params + _normalize + _set_params
+ * (ghn3/nn.py:422-506, 554-592, 508-552): every predicted tensor of a model is written straight into the target
+ * parameter storage by ONE launch driven by a descriptor table.
+ *
+ * Target element with (padded-to-4D) index (a, b, y, x), dims (t0, t1, t2, t3):
+ *   row = a*ra + (y+cy)*kw_src + (x+cx);   col = (a % so)*ca + (b % si);   v = src[row*ld + col]
+ *   mode 0: dst = v * scale      (fan-in normalisation, nn.py:583; scale = 1 for positional encodings)
+ *   mode 1: dst = 2*sigmoid(0.5 v)   (1-D weights, nn.py:588)
+ *   mode 2: dst = tanh(0.2 v)        (1-D biases,  nn.py:590)
+ *   mode 3: like mode 0 but (y, x) are bilinearly resampled from a kh_src x kw_src source window (nn.py:751-753)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* dst;
+  const float* src;
+  int64_t numel;
+  int64_t chunk0;        /* index of this tensor's first chunk (prefix sum of ceil(numel / GHN3_SCATTER_CHUNK)) */
+  int32_t t1, t2, t3;
+  int32_t so, si;
+  int32_t ld, ca, ra;
+  int32_t kh_src, kw_src, cy, cx;
+  float scale;
+  int32_t mode;
+} ghn3_scatter_desc;       /* 88 bytes */
+
+#define GHN3_SCATTER_CHUNK 4096
+
+typedef struct {
+  const ghn3_scatter_desc* descs;   /* device [n_descs] */
+  int32_t n_descs;
+  int64_t n_chunks;
+} ghn3_scatter_args;
+
+int ghn3_scatter(const ghn3_scatter_args* args, ghn3_stream_t stream);
+
+/* Sum of squares of a set of fp32 tensors (norm_check metric, ghn3/nn.py:783-797): out[0] += sum_i |t_i|^2. */
+typedef struct {
+  const float* const* ptrs;    /* device array of device pointers */
+  const int64_t* numels;       /* device */
+  int32_t n;
+  double* out;                 /* device, one double, zeroed by the call */
+} ghn3_sumsq_args;
+
+int ghn3_sumsq(const ghn3_sumsq_args* args, ghn3_stream_t stream);
+
+/* dtype conversion helpers used when a checkpoint is prepared for the device (one-time, not on the hot path). */
+int ghn3_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, ghn3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHN3_B200_H_ */
