@@ -1,0 +1,513 @@
+"""
+GHN-3 on B200: the reference's Python API (`from_pretrained`, `GHN3(...)`, `ghn(model)`; reference ghn3/nn.py:31-349)
+and state_dict layout over the C-ABI CUDA library. The modules below only HOLD parameters (same names and shapes
+as the reference, so checkpoints load unchanged); all arithmetic of the forward pass runs in our kernels:
+
+  graphs  --H2D-->  ghn3_spd_bfs / ghn3_graph_derive  ->  ghn3_node_features  ->  ghn3_graphormer_stack
+          ->  decoder GEMMs (ghn3_gemm grouped: fc, conv.0, conv.2 restricted to the needed weight rows)
+          ->  ghn3_gemm_simt (classification heads)  ->  ghn3_scatter straight into the target parameters
+
+There is no CPU path: the GHN must live on a CUDA device.
+"""
+import math
+import weakref
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .graph import Graph, GraphBatch
+from .plan import (BatchPlan, ModelPlan, SCATTER_CHUNK, SRC_CLSB, SRC_CLSW, SRC_D1, SRC_TOK, SRC_WOUT)
+from .weights import (EDGE_EMBED_ROWS, MAX_DEGREE, MAX_INPUT_DIST, N_PRIMITIVES, channel_bins, normalize_config,
+                      sinusoid_table, spatial_bins)
+
+DTYPES = {'bf16': ops.BF16, 'tf32': ops.TF32}
+
+
+def log(*a, **k):
+    print(*a, **k)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's attribute names (state_dict contract)
+# ----------------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError('parameter container: the computation runs in ghn3_b200 CUDA kernels')
+
+
+class ShapeEncoder(_Holder):
+    """ppuda ShapeEncoder parameters: embed_spatial [n_s+1, C/4], embed_channel [n_ch+1, C/4]."""
+
+    def __init__(self, hid, num_classes, max_shape):
+        super().__init__()
+        self.embed_spatial = nn.Embedding(len(spatial_bins(max_shape)) + 1, hid // 4)
+        self.embed_channel = nn.Embedding(len(channel_bins(num_classes)) + 1, hid // 4)
+
+
+class EdgeEmbedding(_Holder):
+    def __init__(self, hid, max_len):
+        super().__init__()
+        self.embed = nn.Embedding(max_len, hid)
+        self.embed.weight.data = sinusoid_table(max_len, hid)      # graphormer.py:55-65
+
+
+class Attention(_Holder):
+    def __init__(self, dim, heads, edge_dim):
+        super().__init__()
+        self.num_heads = heads
+        self.to_qkv = nn.Linear(dim, dim * 3, bias=False)                         # graphormer.py:89
+        self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Identity())           # graphormer.py:92
+        if edge_dim > 0:
+            self.edge_embed = EdgeEmbedding(dim, EDGE_EMBED_ROWS)                 # graphormer.py:96
+            self.proj_e = nn.Sequential(nn.Linear(edge_dim * dim, dim), nn.ReLU(), nn.Linear(dim, heads))
+
+
+class FeedForward(_Holder):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Identity(), nn.Linear(hidden, dim),
+                                 nn.Identity())                                    # graphormer.py:38-44
+
+
+class GraphormerLayer(_Holder):
+    def __init__(self, dim, num_heads, mlp_ratio=4, edge_dim=0, eps=1e-5, return_edges=False, **_):
+        super().__init__()
+        self.edge_dim = edge_dim
+        self.return_edges = return_edges
+        if edge_dim > 0:
+            self.max_degree = MAX_DEGREE
+            self.max_input_dist = MAX_INPUT_DIST
+        self.ln1 = nn.LayerNorm(dim, eps=eps)
+        self.attn = Attention(dim, num_heads, edge_dim)
+        self.ln2 = nn.LayerNorm(dim, eps=eps)
+        self.ff = FeedForward(dim, int(dim * mlp_ratio))
+
+
+class SequentialMultipleInOut(nn.Sequential):
+    pass
+
+
+class MLP(_Holder):
+    def __init__(self, in_features, hid):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(in_features, hid[0]), nn.ReLU(), nn.Linear(hid[0], hid[1]), nn.Identity())
+
+
+class ConvDecoder3(_Holder):
+    """Parameters of the reference's ConvDecoder3 (nn.py:716-733): fc.0, conv.0, conv.2, class_layer_predictor.1."""
+
+    def __init__(self, in_features, hid, out_shape, num_classes, is_ghn2=False):
+        super().__init__()
+        self.out_shape = out_shape
+        self.num_classes = num_classes
+        self.fc = nn.Sequential(nn.Linear(in_features, hid[0] * out_shape[2] * out_shape[3]), nn.ReLU())
+        self.conv = nn.Sequential(nn.Linear(hid[0], hid[1]), nn.ReLU(),
+                                  nn.Linear(hid[1], out_shape[0] * out_shape[1]), nn.Identity())
+        self.class_layer_predictor = nn.Sequential(nn.ReLU(), nn.Linear(out_shape[0], num_classes))
+
+
+class GHN(nn.Module):
+    """Base-class marker (the reference's Trainer detects a GHN by isinstance(model, ppuda GHN), trainer.py:134)."""
+
+
+class GHN3(GHN):
+    r"""
+    Transformer-based Graph HyperNetwork (GHN-3), B200-native. Constructor and forward signatures follow the
+    reference (ghn3/nn.py:140-193). Extra keyword: compute_dtype='bf16' | 'tf32' selects the tensor-core path.
+    """
+
+    def __init__(self, max_shape, num_classes, hid, heads=8, layers=3, is_ghn2=False, pretrained=False, **kwargs):
+        super().__init__()
+        if is_ghn2:
+            raise NotImplementedError('ghn3_b200 implements the GHN-3 (Graphormer) path only; GHN-2 checkpoints '
+                                      '(is_ghn2=True, GatedGNN on sparse edge lists) are out of scope')
+        kwargs.pop('act_layer', None)
+        kwargs.pop('hypernet', None)
+        kwargs.pop('decoder', None)
+        self.weight_norm = kwargs.pop('weight_norm', False)
+        self.ve = kwargs.pop('ve', False)
+        self.layernorm = kwargs.pop('layernorm', False)
+        self.debug_level = kwargs.pop('debug_level', 0)
+        self.compute_dtype = kwargs.pop('compute_dtype', 'bf16')
+        assert self.compute_dtype in DTYPES, self.compute_dtype
+        if kwargs:
+            raise TypeError('unexpected GHN3 arguments: %s' % sorted(kwargs))
+        cfg = normalize_config(dict(max_shape=max_shape, num_classes=num_classes, hid=hid, heads=heads, layers=layers,
+                                    layernorm=self.layernorm))
+        self.config = cfg
+        self.max_shape = cfg['max_shape']
+        self.num_classes = num_classes
+        self.hid, self.heads, self.layers = hid, heads, layers
+        self._is_ghn2 = False
+        ms = self.max_shape
+        if self.layernorm:
+            self.ln = nn.LayerNorm(hid)
+        self.embed = nn.Embedding(N_PRIMITIVES, hid)
+        self.shape_enc = ShapeEncoder(hid, num_classes, ms)
+        self.gnn = SequentialMultipleInOut(*[
+            GraphormerLayer(dim=hid, num_heads=heads, mlp_ratio=4, edge_dim=2 if layer == 0 else 0,
+                            return_edges=layer < layers - 1) for layer in range(layers)])
+        self.centrality_embed_in = nn.Embedding(MAX_DEGREE + 1, hid)
+        self.centrality_embed_out = nn.Embedding(MAX_DEGREE + 1, hid)
+        self.input_dist_embed = nn.Embedding(MAX_INPUT_DIST + 1, hid)
+        self.decoder = ConvDecoder3(hid, (hid * 4, hid * 8), ms, num_classes)
+        max_ch = max(ms[:2])
+        self.decoder_1d = MLP(hid, (hid * 2, 2 * max_ch))
+        self.bias_class = nn.Sequential(nn.ReLU(), nn.Linear(max_ch, num_classes))
+        # nn.py:165-172
+        for m in (self.decoder_1d.fc[-2], self.decoder.conv[-2], self.decoder.class_layer_predictor[-1]):
+            m.weight.data /= 5.0
+            m.bias.data *= 0
+        for m in self.modules():                      # nn.py:170,704-713 (applies to every nn.Embedding)
+            if isinstance(m, nn.Embedding):
+                nn.init.trunc_normal_(m.weight.data, std=m.weight.shape[1] ** (-0.5))
+        if not pretrained:
+            self.fix_embed_layers()
+        self._dev = None
+        self._plan_cache = OrderedDict()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def fix_embed_layers(self):
+        """nn.py:174-184: the three structural embeddings live under gnn.0 in released checkpoints."""
+        for name in ('centrality_embed_in', 'centrality_embed_out', 'input_dist_embed'):
+            if name in self._modules:
+                mod = self._modules.pop(name)
+                setattr(self.gnn[0], name, mod)
+
+    def is_dense(self):
+        return True
+
+    # ------------------------------------------------------------------------------------------------------------
+    # device-side weight cache
+    # ------------------------------------------------------------------------------------------------------------
+    def _weights_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()), self.compute_dtype
+
+    def _device_weights(self):
+        sig = self._weights_signature()
+        if self._dev is not None and self._dev['sig'] == sig:
+            return self._dev
+        dev = self.embed.weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError('ghn3_b200: the GHN must be on a CUDA device (got %s); there is no CPU path' % dev)
+        if not self.layernorm:
+            raise NotImplementedError('ghn3_b200: layernorm=False GHNs are not supported by the CUDA path')
+        self.fix_embed_layers()
+        dt = DTYPES[self.compute_dtype]
+        C, S = self.hid, self.max_shape[2]
+        f = lambda p: p.detach().contiguous().float()
+        cv = lambda p: ops.convert(f(p), dt)
+        g0 = self.gnn[0]
+        w = {'sig': sig, 'dtype': dt}
+        w['tables'] = {'embed_op': f(self.embed.weight), 'embed_ch': f(self.shape_enc.embed_channel.weight),
+                       'embed_sp': f(self.shape_enc.embed_spatial.weight),
+                       'cent_in': f(g0.centrality_embed_in.weight), 'cent_out': f(g0.centrality_embed_out.weight),
+                       'dist_embed': f(g0.input_dist_embed.weight)}
+        self._lut_cache = {}
+        w['lut_inputs'] = (f(g0.attn.edge_embed.embed.weight), f(g0.attn.proj_e[0].weight), f(g0.attn.proj_e[0].bias),
+                           f(g0.attn.proj_e[2].weight), f(g0.attn.proj_e[2].bias))
+        layers = (L.LayerWeights * self.layers)()
+        keep = []
+        for l, layer in enumerate(self.gnn):
+            t = dict(ln1_w=f(layer.ln1.weight), ln1_b=f(layer.ln1.bias), w_qkv=cv(layer.attn.to_qkv.weight),
+                     w_out=cv(layer.attn.to_out[0].weight), b_out=f(layer.attn.to_out[0].bias),
+                     ln2_w=f(layer.ln2.weight), ln2_b=f(layer.ln2.bias), w_ff1=cv(layer.ff.net[0].weight),
+                     b_ff1=f(layer.ff.net[0].bias), w_ff2=cv(layer.ff.net[3].weight), b_ff2=f(layer.ff.net[3].bias))
+            keep.append(t)
+            for k, v in t.items():
+                setattr(layers[l], k, v.data_ptr())
+        w['layers'], w['layers_keep'] = layers, keep
+        w['ln_w'], w['ln_b'] = f(self.ln.weight), f(self.ln.bias)
+        dec = self.decoder
+        # fc weight repacked position-major: [c*S*S + p][k] -> [p][c][k], so one decoder-grid position is one
+        # contiguous [4C, C] block and a crop window is a set of row ranges (nn.py:738-745)
+        fc_w = f(dec.fc[0].weight).view(4 * C, S * S, C).permute(1, 0, 2).contiguous().view(S * S * 4 * C, C)
+        w['fc_w'] = ops.convert(fc_w, dt)
+        del fc_w
+        w['fc_b'] = f(dec.fc[0].bias).view(4 * C, S * S).t().contiguous().view(-1)
+        w['c0_w'], w['c0_b'] = cv(dec.conv[0].weight), f(dec.conv[0].bias)
+        w['c2_w'], w['c2_b'] = cv(dec.conv[2].weight), f(dec.conv[2].bias)
+        w['cls_w'], w['cls_b'] = f(dec.class_layer_predictor[1].weight), f(dec.class_layer_predictor[1].bias)
+        w['d1_w0'], w['d1_b0'] = cv(self.decoder_1d.fc[0].weight), f(self.decoder_1d.fc[0].bias)
+        w['d1_w1'], w['d1_b1'] = cv(self.decoder_1d.fc[2].weight), f(self.decoder_1d.fc[2].bias)
+        w['bc_w'], w['bc_b'] = f(self.bias_class[1].weight), f(self.bias_class[1].bias)
+        self._dev = w
+        return w
+
+    def _lut(self, w, vmax):
+        if vmax not in self._lut_cache:
+            self._lut_cache[vmax] = ops.edge_lut(*w['lut_inputs'], vmax=vmax)
+        return self._lut_cache[vmax]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, nets_torch, graphs=None, return_embeddings=False, predict_class_layers=True,
+                bn_track_running_stats=True, keep_grads=False, reduce_graph=False):
+        r"""
+        Predict parameters for a list of >=1 networks (signature of the reference, nn.py:186-209).
+        The predicted tensors are written in place into the parameters of `nets_torch` on the GHN's device.
+        """
+        device = self.embed.weight.device
+        if device.type != 'cuda':
+            raise RuntimeError('ghn3_b200: the GHN must be on a CUDA device (got %s); there is no CPU path' % device)
+        if keep_grads or (keep_grads is None and self.training):
+            raise NotImplementedError('ghn3_b200: keep_grads=True (training the GHN through the predicted '
+                                      'parameters) is not implemented in the CUDA path yet')
+        is_lst = isinstance(nets_torch, (list, tuple))
+        nets = list(nets_torch) if is_lst else [nets_torch]
+
+        if graphs is None:
+            graphs = GraphBatch([Graph(net, ve_cutoff=50 if self.ve else 1) for net in nets], dense=True)
+        elif not isinstance(graphs, GraphBatch):
+            graphs = GraphBatch(list(graphs) if isinstance(graphs, (list, tuple)) else [graphs], dense=True)
+        if not graphs.on_device(device):
+            graphs.to_device(device)
+        assert len(graphs) == len(nets), 'number of graphs and networks must match'
+
+        w = self._device_weights()
+        bp = self._batch_plan(graphs, nets, predict_class_layers, reduce_graph)
+        emb = self._run(w, graphs.pack, bp, return_embeddings)
+
+        if bn_track_running_stats is None:
+            bn_track_running_stats = self.training
+        if not bn_track_running_stats:
+            def bn_set_train(module):                      # nn.py:333-342
+                if isinstance(module, nn.BatchNorm2d):
+                    module.track_running_stats = False
+                    module.training = True
+            for net in nets:
+                net.apply(bn_set_train)
+
+        if self.debug_level:
+            n_params = sum(sum(p.numel() for p in net.parameters()) for net in nets)
+            n_pred = sum(p.n_params for p in bp.plans)
+            log('number of parameter tensors predicted using GHN: {}, total parameters predicted: {} ({})'.format(
+                sum(p.n_tensors for p in bp.plans), n_pred,
+                'MATCHED!' if n_params == n_pred else 'ERROR! NOT MATCHED WITH {} ACTUAL PARAMS'.format(n_params)))
+
+        out = nets if is_lst or len(nets) > 1 else nets[0]
+        return (out, emb) if return_embeddings else out
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _batch_plan(self, graphs, nets, predict_class_layers, reduce_graph):
+        plans = []
+        for graph, net in zip(graphs.graphs, nets):
+            cache = net.__dict__.setdefault('_ghn3_b200_plans', {})
+            key = (id(graph), self.max_shape, self.num_classes, predict_class_layers)
+            plan = cache.get(key)
+            if plan is None or plan.graph_ref() is not graph:
+                plan = ModelPlan(graph, net, self.config, predict_class_layers)
+                plan.graph_ref = weakref.ref(graph)
+                if reduce_graph:
+                    plan.prune_unmatched()
+                cache.clear()
+                cache[key] = plan
+            plans.append(plan)
+        key = tuple(id(p) for p in plans)
+        bp = self._plan_cache.get(key)
+        if bp is None or any(a is not b for a, b in zip(bp.plans, plans)):
+            bp = BatchPlan(plans, self.config)
+            self._plan_cache[key] = bp
+            while len(self._plan_cache) > 64:
+                self._plan_cache.popitem(last=False)
+        return bp
+
+    def _static_device(self, bp, device):
+        """Uploads the per-plan static metadata once (op ids come from the graphs, see _run)."""
+        st = getattr(bp, 'dev', None)
+        if st is not None and st['device'] == device:
+            return st
+        blob = ops.HostBlob()
+        blob.add('shape_idx', bp.shape_idx.astype(np.int32))
+        blob.add('dst_row', bp.dst_row)
+        blob.add('fc_problems', bp.fc_problems.view(np.uint8))
+        blob.add('fc_tiles', bp.fc_tiles)
+        blob.add('c2_problems', bp.c2_problems.view(np.uint8))
+        blob.add('c2_tiles', bp.c2_tiles)
+        st = blob.upload(device)
+        st['device'] = device
+        st['bytes'] = blob.size
+        bp.dev = st
+        return st
+
+    def _run(self, w, pack, bp, return_embeddings):
+        device = self.embed.weight.device
+        dt = w['dtype']
+        tdt = ops.TORCH_DTYPE[dt]
+        C, H = self.hid, self.heads
+        ms0, ms1, S, _ = self.max_shape
+        ncls = self.num_classes
+        st = self._static_device(bp, device)
+        N = bp.total_nodes
+        assert N == pack.total_nodes
+        stream = L.current_stream()
+
+        # ---- node features ----
+        op = getattr(pack, 'op_dev', None)
+        if op is None:
+            raise RuntimeError('internal: graph pack has no op ids')
+        x = ops.node_features(op, st['shape_idx'], pack, w['tables'], C)
+
+        # ---- Graphormer stack + final LN scattered into the decoder input rows ----
+        n_dec = bp.n_conv + bp.n_1d
+        dec_in = torch.empty(max(n_dec, 1), C, dtype=tdt, device=device)
+        emb = torch.empty(N, C, dtype=torch.float32, device=device) if return_embeddings else None
+        h = torch.empty(N, C, dtype=tdt, device=device)
+        qkv = torch.empty(N, 3 * C, dtype=tdt, device=device)
+        ff = torch.empty(N, 4 * C, dtype=tdt, device=device)
+        lut = self._lut(w, pack.cutoff)
+        ga = L.GraphormerArgs(hid=C, heads=H, layers=self.layers, dtype=dt, layers_host=w['layers'],
+                              ln_w=L.ptr(w['ln_w']), ln_b=L.ptr(w['ln_b']), n_graphs=pack.n_graphs, total_nodes=N,
+                              max_nodes=pack.max_nodes, lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']),
+                              mat_off=L.ptr(pack.d['mat_off']), pair=L.ptr(pack.pair), lut=L.ptr(lut), x=L.ptr(x),
+                              h=L.ptr(h), qkv=L.ptr(qkv), ff=L.ptr(ff), dec_in=L.ptr(dec_in), dec_dtype=dt,
+                              dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(emb))
+        L.call('graphormer_stack', ga, stream)
+
+        bufs = {}
+        # ---- conv decoder: fc (cropped positions) -> conv.0 -> conv.2 (needed columns only) ----
+        R = bp.conv_total_rows
+        if R > 0:
+            h0 = torch.empty(R, 4 * C, dtype=tdt, device=device)
+            ops.gemm(dec_in, w['fc_w'], bias=w['fc_b'], act=ops.ACT_RELU, in_dtype=dt, out=h0, out_dtype=dt,
+                     problems=st['fc_problems'], tiles=st['fc_tiles'])
+            h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=dt)
+            wout = torch.empty(bp.wout_elems, dtype=torch.float32, device=device)
+            ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
+                     problems=st['c2_problems'], tiles=st['c2_tiles'])
+            bufs[SRC_WOUT] = wout
+            if bp.clsw_elems:
+                clsw = torch.empty(bp.clsw_elems, dtype=torch.float32, device=device)
+                for (woff, ld, ii, cnt, coff) in bp.cls_heads:
+                    # out[node][cls][b] = b_cls[cls] + sum_a W_cls[cls][a] * relu(wout[node][a*i'+b])  (nn.py:757-758)
+                    ops.gemm_simt(wout, 1, ii, w['cls_w'], ms0, 1, w['cls_b'], clsw, 1, ii, m=ii, n=ncls, k=ms0,
+                                  relu_a=True, batch=cnt, a_bs=ld, d_bs=ncls * ii, a_off=woff, d_off=coff)
+                bufs[SRC_CLSW] = clsw
+        # ---- 1-D decoder (+ classification bias head) ----
+        if bp.n_1d > 0:
+            d_in = dec_in[bp.n_conv:bp.n_conv + bp.n_1d]
+            hid1 = ops.gemm(d_in, w['d1_w0'], bias=w['d1_b0'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=dt)
+            d1 = ops.gemm(hid1, w['d1_w1'], bias=w['d1_b1'], in_dtype=dt, out_dtype=ops.F32)
+            bufs[SRC_D1] = d1
+            if bp.n_clsb:
+                mc = bp.max_ch
+                clsb = torch.empty(2 * bp.n_clsb, ncls, dtype=torch.float32, device=device)
+                ops.gemm_simt(d1, mc, 1, w['bc_w'], mc, 1, w['bc_b'], clsb, ncls, 1, m=2 * bp.n_clsb, n=ncls, k=mc,
+                              relu_a=True, a_off=(bp.n_1d - bp.n_clsb) * 2 * mc)
+                bufs[SRC_CLSB] = clsb
+        if bp.n_tok_elems:
+            # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
+            bufs[SRC_TOK] = torch.normal(mean=0.0, std=0.02, size=(bp.n_tok_elems,), device=device)
+
+        # ---- tile / normalise / scatter into the target parameters ----
+        self._scatter(bp, bufs, device)
+        self._last_buffers = bufs if self.debug_level else None
+        return emb
+
+    def _scatter(self, bp, bufs, device):
+        n = len(bp.desc_static)
+        if n == 0:
+            return
+        ptrs = np.empty(n, dtype=np.uint64)
+        for i, (module, attr, shape, view) in enumerate(bp.desc_targets):
+            p = getattr(module, attr)
+            if not isinstance(p, torch.Tensor):
+                raise RuntimeError('ghn3_b200: target %s.%s is not a tensor (light modules need keep_grads=True, '
+                                   'which the CUDA path does not support yet)' % (type(module).__name__, attr))
+            if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
+                # reference semantics (nn.py:548): param.data is replaced by a tensor on the GHN's device
+                p.data = torch.empty(tuple(p.shape), dtype=torch.float32, device=device)
+            ptrs[i] = p.data_ptr()
+        desc = bp.desc_static.copy()
+        base = np.zeros(8, dtype=np.uint64)
+        for k, v in bufs.items():
+            base[k] = v.data_ptr()
+        desc['dst'] = ptrs + bp.desc_dst_shift
+        desc['src'] = base[bp.desc_src_buf] + bp.desc_src_off * np.uint64(4)
+        if not self.weight_norm:
+            desc['mode'] = np.where(desc['mode'] == 3, 3, 0)
+            desc['scale'] = 1.0
+        dev_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(device)
+        ops.scatter(dev_desc, n, bp.n_chunks)
+        self._desc_keepalive = (dev_desc, bufs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def from_pretrained(ghn3_name='ghn3xlm16.pt', **kwargs):
+    """
+    Loads a GHN-3 checkpoint (reference nn.py:31-125): a local file holding {'state_dict', 'config'?} or a bare
+    state_dict; the GHN config is inferred from tensor names/shapes when absent. Hugging Face download is attempted
+    only if the file does not exist locally and huggingface_hub is importable.
+    """
+    import os
+    assert ghn3_name is not None, 'GHN ckpt must be specified.'
+    state_dict, ghn_config = None, None
+    if not os.path.exists(ghn3_name):
+        try:
+            import joblib
+            from huggingface_hub import hf_hub_download
+            state_dict = joblib.load(hf_hub_download(repo_id='SamsungSAILMontreal/ghn3', filename=ghn3_name))
+        except Exception as e:
+            raise FileNotFoundError('cannot load GHN checkpoint %s: not a local file and the hub download failed (%s)'
+                                    % (ghn3_name, e))
+    else:
+        state_dict = torch.load(ghn3_name, map_location='cpu', weights_only=False)
+        if 'config' in state_dict:
+            ghn_config = state_dict['config']
+        if 'state_dict' in state_dict:
+            state_dict = state_dict['state_dict']
+    if any(k.find('gnn.gru.') >= 0 for k in state_dict):
+        raise NotImplementedError('GHN-2 checkpoints are out of scope of ghn3_b200')
+    compute_dtype = kwargs.pop('compute_dtype', 'bf16')
+    if ghn_config is None:
+        num_classes = kwargs.pop('num_classes', 10)
+        layers = kwargs.pop('layers', 0)
+        hid = kwargs.pop('hid', 32)
+        layernorm = kwargs.pop('layernorm', False)
+        pretrained = kwargs.pop('pretrained', False)
+        max_shape = kwargs.pop('max_shape', 64)
+        for name, p in state_dict.items():
+            if name.find('class_layer_predictor') >= 0:
+                num_classes = len(p)
+                break
+        s = 16 if num_classes >= 1000 else 11
+        for name, p in state_dict.items():
+            if name.endswith('ln.weight'):
+                layernorm = True
+            elif name.endswith('embed.weight'):
+                hid = p.shape[-1]
+            elif name.endswith('decoder.conv.2.weight'):
+                max_shape = int(len(p) ** 0.5)
+            elif name.endswith('shape_enc.embed_spatial.weight'):
+                s = 11 if len(p) == 9 else 16
+            elif name.endswith('ln1.weight') and name.find('gnn.') >= 0:
+                layers += 1
+            elif name.find('centrality_embed_in') >= 0 > name.find('gnn.'):
+                pretrained = True
+        ghn_config = {'hid': hid,
+                      'max_shape': max_shape if isinstance(max_shape, tuple) else (max_shape, max_shape, s, s),
+                      'num_classes': num_classes, 'heads': 16 if hid > 64 else 8, 'layers': layers,
+                      'weight_norm': True, 've': True, 'layernorm': layernorm, 'pretrained': pretrained}
+    else:
+        ghn_config = dict(ghn_config)
+        ghn_config.pop('is_ghn2', None)
+    ghn = GHN3(**ghn_config, compute_dtype=compute_dtype, **kwargs)
+    ghn.load_state_dict(state_dict)
+    ghn.fix_embed_layers()
+    return ghn
+
+
+def param_norm(model):
+    """Total L2 norm of a model's parameters, computed on the device by ghn3_sumsq (the norm_check metric of
+    nn.py:783-797). Returns a 0-d float64 CUDA tensor (no host sync)."""
+    ps = [p.data for p in model.parameters() if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()]
+    dev = ps[0].device
+    meta = np.array([[p.data_ptr() for p in ps], [p.numel() for p in ps]], dtype=np.int64)
+    meta_dev = torch.from_numpy(meta).to(dev)
+    out = torch.empty(1, dtype=torch.float64, device=dev)
+    a = L.SumsqArgs(ptrs=meta_dev[0].data_ptr(), numels=meta_dev[1].data_ptr(), n=len(ps), out=out.data_ptr())
+    L.call('sumsq', a, L.current_stream())
+    return out.sqrt_()

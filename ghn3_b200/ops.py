@@ -55,7 +55,7 @@ class GraphPack:
     Layout per graph g: N_g x N_g matrices with leading dimension ld_g = round_up(N_g, 16) at offset mat_off[g].
     """
 
-    def __init__(self, n_nodes, edges=None, spd=None, cutoff=50, device='cuda'):
+    def __init__(self, n_nodes, edges=None, spd=None, cutoff=50, device='cuda', op=None):
         self.device = torch.device(device)
         self.n_nodes = [int(n) for n in n_nodes]
         self.n_graphs = len(self.n_nodes)
@@ -96,11 +96,14 @@ class GraphPack:
                 m[:, :n] = A
                 packed[self.mat_off[g]:self.mat_off[g + 1]] = m.reshape(-1)
             blob.add('spd', packed)
+        if op is not None:
+            blob.add('op', np.asarray(op, dtype=np.int32))
         self.h2d_bytes = blob.size
         v = blob.upload(self.device)
         self._blob = blob
         self.d = v
         self.spd = v.get('spd')
+        self.op_dev = v.get('op')
         self.pair = self.deg_in = self.deg_out = self.dist0 = None
 
     def build(self, stream=None):

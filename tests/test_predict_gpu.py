@@ -1,0 +1,127 @@
+"""End-to-end parity on the B200: ghn(model) through the CUDA path vs the CPU oracle on the same weights / graphs."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from ghn3_b200 import GHN3, Graph, GraphBatch, param_norm
+from ghn3_b200.weights import CONFIGS, procedural_state_dict
+from oracle import ghn3_oracle as O
+from tests import helpers as H
+
+DEV = 'cuda'
+# north_star tolerance: max relative error (max |a-b| / max |b| per tensor) <= 1e-3 (tf32), <= 2e-2 (bf16)
+TOL = {'tf32': 1e-3, 'bf16': 2e-2}
+
+
+def make_ghn(cfg_name, dtype):
+    cfg = CONFIGS[cfg_name]
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    return ghn.to(DEV).eval(), cfg
+
+
+def run_case(cfg_name, archs, dtype, check_logits=True):
+    ghn, cfg = make_ghn(cfg_name, dtype)
+    sd = procedural_state_dict(cfg, 0)
+    recs = [H.graph_records()[a] for a in archs]
+    models = [H.build_model(a).to(DEV) for a in archs]
+    graphs = [Graph.from_record(r) for r in recs]
+    with torch.no_grad():
+        out, emb = ghn(models if len(models) > 1 else models[0], graphs if len(graphs) > 1 else graphs[0],
+                       return_embeddings=True)
+    torch.cuda.synchronize()
+    out = out if isinstance(out, list) else [out]
+    off = 0
+    worst = {}
+    for arch, rec, model in zip(archs, recs, out):
+        ref_model = H.build_model(arch)
+        g = O.graph_from_record(rec)
+        ref_model, ref_emb, stats = O.predict(sd, cfg, ref_model, g)
+        e = H.max_rel_err(emb[off:off + rec['n']], ref_emb)
+        assert e < TOL[dtype], ('embeddings', arch, e)
+        off += rec['n']
+        ref_params = dict(ref_model.named_parameters())
+        w = 0.0
+        for name, p in model.named_parameters():
+            r = ref_params[name]
+            assert p.shape == r.shape
+            if name.endswith('pos_embedding'):          # row 0 is a fresh random class token (nn.py:446)
+                p, r = p[:, 1:], r[:, 1:]
+            err = H.max_rel_err(p, r)
+            w = max(w, err)
+            assert err < TOL[dtype], (arch, name, err)
+        worst[arch] = w
+        if check_logits:
+            torch.manual_seed(1)
+            sz = 299 if arch == 'inception_v3' else 224
+            x = torch.randn(2, 3, sz, sz)
+            with torch.no_grad():
+                model.eval(); ref_model.eval()
+                y = model(x.to(DEV)).float().cpu()
+                y_ref = ref_model(x)
+            if torch.isfinite(y_ref).all():
+                assert H.max_rel_err(y, y_ref) < 5 * TOL[dtype], (arch, 'logits', H.max_rel_err(y, y_ref))
+    print(cfg_name, dtype, worst)
+    return worst
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+@pytest.mark.parametrize('arch', ['resnet18', 'squeezenet1_1', 'mobilenet_v3_small', 'vit_b_32', 'swin_v2_t',
+                                  'convnext_tiny', 'alexnet', 'densenet121'])
+def test_tiny_single(arch, dtype):
+    run_case('ghn3tiny', [arch], dtype)
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+def test_tm8_resnet50(dtype):
+    run_case('ghn3tm8', ['resnet50'], dtype)
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+def test_batch_equals_per_graph_oracle(dtype):
+    """B > 1 with unequal sizes: every graph must equal its own B = 1 oracle prediction."""
+    run_case('ghn3tiny', ['resnet18', 'resnet34', 'squeezenet1_1', 'vit_b_32'], dtype, check_logits=False)
+
+
+def test_param_count_matched_and_norm():
+    ghn, cfg = make_ghn('ghn3tm8', 'tf32')
+    model = H.build_model('resnet50').to(DEV)
+    g = Graph.from_record(H.graph_records()['resnet50'])
+    with torch.no_grad():
+        ghn(model, g)
+    bp = list(ghn._plan_cache.values())[-1]
+    assert (bp.plans[0].n_tensors, bp.plans[0].n_params) == (161, 25557032)     # nn.py:384-392 "MATCHED!"
+    n = param_norm(model).item()
+    ref = torch.norm(torch.stack([p.norm() for p in model.parameters()]), 2).item()
+    assert abs(n - ref) / ref < 1e-5
+
+
+def test_accepts_dense_adj_and_device_batch():
+    """Graphs that already carry a dense SPD matrix (reference-style) and a GraphBatch already on the device."""
+    ghn, cfg = make_ghn('ghn3tiny', 'tf32')
+    rec = H.graph_records()['resnet18']
+    og = O.graph_from_record(rec)
+    g_dense = Graph(node_feat=torch.as_tensor(og['ops']).view(-1, 1), node_info=og['node_info'],
+                    A=torch.as_tensor(og['A']), dense=True)
+    m1, m2 = H.build_model('resnet18').to(DEV), H.build_model('resnet18').to(DEV)
+    with torch.no_grad():
+        ghn(m1, g_dense)
+        batch = GraphBatch([Graph.from_record(rec)], dense=True).to_device(DEV)
+        ghn(m2, batch)
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1, p2), n1
+
+
+def test_cpu_model_gets_device_params_and_no_cpu_fallback():
+    ghn, cfg = make_ghn('ghn3tiny', 'bf16')
+    model = H.build_model('resnet18')                  # parameters on the CPU
+    with torch.no_grad():
+        ghn(model, Graph.from_record(H.graph_records()['resnet18']))
+    assert all(p.is_cuda for p in model.parameters())  # nn.py:548 semantics: data replaced on the GHN's device
+    with pytest.raises(RuntimeError):
+        GHN3(**cfg, weight_norm=True, ve=True)(H.build_model('resnet18'),
+                                               Graph.from_record(H.graph_records()['resnet18']))
