@@ -345,11 +345,21 @@ class GHN3(GHN):
         assert N == pack.total_nodes
         stream = L.current_stream()
 
+        prof = getattr(self, '_profile', None)
+
+        def mark(name):
+            if prof is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                prof.append((name, ev))
+
+        mark('start')
         # ---- node features ----
         op = getattr(pack, 'op_dev', None)
         if op is None:
             raise RuntimeError('internal: graph pack has no op ids')
         x = ops.node_features(op, st['shape_idx'], pack, w['tables'], C)
+        mark('node_features')
 
         # ---- Graphormer stack + final LN scattered into the decoder input rows ----
         n_dec = bp.n_conv + bp.n_1d
@@ -366,6 +376,7 @@ class GHN3(GHN):
                               h=L.ptr(h), qkv=L.ptr(qkv), ff=L.ptr(ff), dec_in=L.ptr(dec_in), dec_dtype=dt,
                               dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(emb))
         L.call('graphormer_stack', ga, stream)
+        mark('graphormer')
 
         bufs = {}
         # ---- conv decoder: fc (cropped positions) -> conv.0 -> conv.2 (needed columns only) ----
@@ -374,10 +385,13 @@ class GHN3(GHN):
             h0 = torch.empty(R, 4 * C, dtype=tdt, device=device)
             ops.gemm(dec_in, w['fc_w'], bias=w['fc_b'], act=ops.ACT_RELU, in_dtype=dt, out=h0, out_dtype=dt,
                      problems=st['fc_problems'], tiles=st['fc_tiles'])
+            mark('dec_fc')
             h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=dt)
+            mark('dec_conv0')
             wout = torch.empty(bp.wout_elems, dtype=torch.float32, device=device)
             ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
                      problems=st['c2_problems'], tiles=st['c2_tiles'])
+            mark('dec_conv2')
             bufs[SRC_WOUT] = wout
             if bp.clsw_elems:
                 clsw = torch.empty(bp.clsw_elems, dtype=torch.float32, device=device)
@@ -402,8 +416,10 @@ class GHN3(GHN):
             # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
             bufs[SRC_TOK] = torch.normal(mean=0.0, std=0.02, size=(bp.n_tok_elems,), device=device)
 
+        mark('heads_1d')
         # ---- tile / normalise / scatter into the target parameters ----
         self._scatter(bp, bufs, device)
+        mark('scatter')
         self._last_buffers = bufs if self.debug_level else None
         return emb
 

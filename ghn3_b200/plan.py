@@ -447,7 +447,7 @@ class BatchPlan:
         self.desc_src_buf = np.array([s_[0] for s_ in srcs], dtype=np.int64)
         self.desc_src_off = np.array([s_[1] for s_ in srcs], dtype=np.uint64)
         # rows 1.. of a ViT pos_embedding start one row (D floats) after the parameter's base address
-        self.desc_dst_shift = np.array([tg[0].__getattribute__(tg[1]).shape[-1] * 4 if tg[3] == 'body' else 0
+        self.desc_dst_shift = np.array([getattr(tg[0], tg[1]).shape[-1] * 4 if tg[3] == 'body' else 0
                                         for tg in targets], dtype=np.uint64)
         chunks = (self.desc_static['numel'] + SCATTER_CHUNK - 1) // SCATTER_CHUNK
         self.desc_static['chunk0'] = np.concatenate([[0], np.cumsum(chunks)[:-1]]) if len(chunks) else []

@@ -50,6 +50,8 @@ def run_case(cfg_name, archs, dtype, check_logits=True):
             r = ref_params[name]
             assert p.shape == r.shape
             if name.endswith('pos_embedding'):          # row 0 is a fresh random class token (nn.py:446)
+                with torch.no_grad():
+                    p[:, 0] = r[:, 0].to(p.device)        # same token in both models for the logits check
                 p, r = p[:, 1:], r[:, 1:]
             err = H.max_rel_err(p, r)
             w = max(w, err)
@@ -125,3 +127,10 @@ def test_cpu_model_gets_device_params_and_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         GHN3(**cfg, weight_norm=True, ve=True)(H.build_model('resnet18'),
                                                Graph.from_record(H.graph_records()['resnet18']))
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+@pytest.mark.parametrize('arch', ['vit_b_16', 'convnext_base'])
+def test_xl_bench_models(arch, dtype):
+    """BASELINE.json config 2: ghn3xlm16 (random-init) on ViT-B/16 and ConvNeXt-Base."""
+    run_case('ghn3xlm16', [arch], dtype)
