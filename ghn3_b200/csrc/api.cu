@@ -33,7 +33,7 @@ int attention_impl(const ghn3_attention_args* a, cudaStream_t stream);
 int layernorm_impl(const ghn3_layernorm_args* a, cudaStream_t stream);
 
 static ghn3_gemm_args linear(const void* x, int64_t rows, int k, const void* w, int n, const float* bias, void* out,
-                             int in_dtype, int out_dtype, int act, int accumulate) {
+                             int in_dtype, int out_dtype, int act, int accumulate, int x3) {
   ghn3_gemm_args g = {};
   g.a = x; g.a_rows = rows; g.lda = k;
   g.b = w; g.b_rows = n; g.ldb = k;
@@ -43,6 +43,7 @@ static ghn3_gemm_args linear(const void* x, int64_t rows, int k, const void* w, 
   g.bias = bias;
   g.act = act;
   g.accumulate = accumulate;
+  g.tf32_x3 = x3;
   g.single.a_row0 = 0; g.single.b_row0 = 0;
   g.single.m = (int32_t)rows; g.single.n = n;
   g.single.d_off = 0; g.single.ldd = n;
@@ -56,32 +57,34 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a->hid % 16 == 0, "ghn3_graphormer_stack: hid must be a multiple of 16");
   if (a->total_nodes <= 0) return GHN3_OK;
   const int C = a->hid, M = a->total_nodes, dt = a->dtype;
+  const int x3 = (a->tf32_x3 != 0 && dt == GHN3_TF32) ? 1 : 0;
+  const int act_dt = x3 ? GHN3_F32 : dt;      // storage dtype tag of the activations produced between GEMMs
   int rc;
   for (int l = 0; l < a->layers; ++l) {
     const ghn3_layer_weights& w = a->layers_host[l];
     ghn3_layernorm_args ln = {};
-    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = w.ln1_w; ln.beta = w.ln1_b; ln.out = a->h; ln.out_dtype = dt;
+    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = w.ln1_w; ln.beta = w.ln1_b; ln.out = a->h; ln.out_dtype = act_dt;
     if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
 
-    ghn3_gemm_args qkv = linear(a->h, M, C, w.w_qkv, 3 * C, nullptr, a->qkv, dt, dt, GHN3_ACT_NONE, 0);
+    ghn3_gemm_args qkv = linear(a->h, M, C, w.w_qkv, 3 * C, nullptr, a->qkv, dt, act_dt, GHN3_ACT_NONE, 0, x3);
     if ((rc = gemm_impl(&qkv, stream)) != GHN3_OK) return rc;
 
     ghn3_attention_args at = {};
     at.n_graphs = a->n_graphs; at.hid = C; at.heads = a->heads; at.max_nodes = a->max_nodes;
     at.lut_size = a->lut_size; at.node_off = a->node_off; at.mat_off = a->mat_off;
-    at.qkv = a->qkv; at.dtype = dt; at.pair = a->pair; at.lut = a->lut; at.out = a->h;
+    at.qkv = a->qkv; at.dtype = act_dt; at.pair = a->pair; at.lut = a->lut; at.out = a->h;
     if ((rc = attention_impl(&at, stream)) != GHN3_OK) return rc;
 
-    ghn3_gemm_args proj = linear(a->h, M, C, w.w_out, C, w.b_out, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1);
+    ghn3_gemm_args proj = linear(a->h, M, C, w.w_out, C, w.b_out, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1, x3);
     if ((rc = gemm_impl(&proj, stream)) != GHN3_OK) return rc;
 
     ln.gamma = w.ln2_w; ln.beta = w.ln2_b;
     if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
 
-    ghn3_gemm_args ff1 = linear(a->h, M, C, w.w_ff1, 4 * C, w.b_ff1, a->ff, dt, dt, GHN3_ACT_GELU, 0);
+    ghn3_gemm_args ff1 = linear(a->h, M, C, w.w_ff1, 4 * C, w.b_ff1, a->ff, dt, act_dt, GHN3_ACT_GELU, 0, x3);
     if ((rc = gemm_impl(&ff1, stream)) != GHN3_OK) return rc;
 
-    ghn3_gemm_args ff2 = linear(a->ff, M, 4 * C, w.w_ff2, C, w.b_ff2, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1);
+    ghn3_gemm_args ff2 = linear(a->ff, M, 4 * C, w.w_ff2, C, w.b_ff2, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1, x3);
     if ((rc = gemm_impl(&ff2, stream)) != GHN3_OK) return rc;
   }
   if (a->ln_w != nullptr) {

@@ -121,11 +121,31 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_a
   for (int k0 = 0; k0 < n; k0 += kAttnKT) {
     const int kt = min(kAttnKT, n - k0);
     __syncthreads();   // previous tile fully consumed (also orders the LUT fill on the first iteration)
-    for (int idx = threadIdx.x; idx < kt * D; idx += blockDim.x) {
-      const int j = idx / D, d = idx - j * D;
-      const T* rowp = qkv + (int64_t)(k0 + j) * C3 + h * D + d;
-      sK[j * DP + d] = to_float(rowp[C]);
-      sV[j * DP + d] = to_float(rowp[2 * C]);
+    {
+      // 16-byte (8-byte for D*sizeof(T) == 8) vector loads of the K and V head slices, all independent
+      constexpr int ROW_BYTES = D * (int)sizeof(T);
+      constexpr int VB = (ROW_BYTES % 16 == 0) ? 16 : 8;
+      constexpr int VPR = ROW_BYTES / VB;
+      constexpr int EPV = VB / (int)sizeof(T);
+      const char* kbase = (const char*)(qkv + (int64_t)k0 * C3 + C + h * D);
+      const size_t row_stride = (size_t)C3 * sizeof(T), v_off = (size_t)C * sizeof(T);
+      for (int idx = threadIdx.x; idx < kt * VPR; idx += blockDim.x) {
+        const int j = idx / VPR, c = idx - j * VPR;
+        const char* src = kbase + (size_t)j * row_stride + c * VB;
+        union { uint4 u4; uint2 u2; T e[EPV]; } kv, vv;
+        if constexpr (VB == 16) {
+          kv.u4 = __ldg((const uint4*)src);
+          vv.u4 = __ldg((const uint4*)(src + v_off));
+        } else {
+          kv.u2 = __ldg((const uint2*)src);
+          vv.u2 = __ldg((const uint2*)(src + v_off));
+        }
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          sK[j * DP + c * EPV + e] = to_float(kv.e[e]);
+          sV[j * DP + c * EPV + e] = to_float(vv.e[e]);
+        }
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -207,7 +227,7 @@ static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
 int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_attention: null args");
   GHN3_REQUIRE(a->heads > 0 && a->hid % a->heads == 0, "ghn3_attention: hid must be divisible by heads");
-  GHN3_REQUIRE(a->dtype == GHN3_BF16 || a->dtype == GHN3_TF32, "ghn3_attention: dtype must be BF16 or TF32");
+  GHN3_REQUIRE(a->dtype >= GHN3_BF16 && a->dtype <= GHN3_F32, "ghn3_attention: bad dtype");
   if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
   const int D = a->hid / a->heads;
   const bool bf = a->dtype == GHN3_BF16;

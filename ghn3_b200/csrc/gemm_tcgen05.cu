@@ -130,7 +130,12 @@ struct GemmKernelArgs {
   int32_t out_dtype;
   int32_t act;
   int32_t accumulate;
+  int32_t k_splits;      // single-problem mode: blockIdx.z = K split; partial sums are added atomically (fp32)
 };
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == GHN3_ACT_RELU) return fmaxf(v, 0.f);
@@ -140,18 +145,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;   // bytes of K per ring stage row = one swizzle span
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
 
-template <int BN>
+// kX3: error-compensated tf32 ("3xTF32"): four extra warps split every fp32 tile in shared memory into
+// hi = tf32(x) and lo = x - hi; the MMA warp issues lo*hi + hi*lo + hi*hi per K step. ~fp32 accuracy from
+// kind::tf32 tensor-core instructions, no extra HBM traffic.
+template <bool kX3, int BN, int kStages>
 constexpr int gemm_smem_bytes() {
-  return kStages * (kBlockM + BN) * kRowBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return kStages * (kBlockM + BN) * kRowBytes * (kX3 ? 2 : 1) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
+template <bool kX3>
+constexpr int gemm_threads() { return kX3 ? 320 : 192; }
 
-template <bool kTf32, int BN>
-__global__ void __launch_bounds__(kThreads, (BN <= 128) ? 2 : 1)
+template <bool kTf32, bool kX3, int BN, int kStages>
+__global__ void __launch_bounds__(gemm_threads<kX3>(), (2 * gemm_smem_bytes<kX3, BN, kStages>() <= 227 * 1024) ? 2 : 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const GemmKernelArgs args) {
+  static_assert(!kX3 || kTf32, "the 3-term split is a tf32 mode");
   constexpr int EB = kTf32 ? 4 : 2;
   constexpr int BK = kRowBytes / EB;         // elements of K per stage
   constexpr int kMmaPerStage = 4;            // 128 B / 32 B per tcgen05.mma (UMMA_K = 16 bf16 / 8 tf32)
@@ -162,12 +171,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + kStages * A_BYTES;
-  const uint32_t bar_base = sB + kStages * B_BYTES;          // 8-byte aligned
-  const uint32_t full_bar = bar_base;                         // kStages barriers
+  const uint32_t sB = sA + kStages * A_BYTES;
+  const uint32_t sAlo = sB + kStages * B_BYTES;                     // only used when kX3
+  const uint32_t sBlo = sAlo + (kX3 ? kStages * A_BYTES : 0);
+  const uint32_t bar_base = sBlo + (kX3 ? kStages * B_BYTES : 0);   // 8-byte aligned
+  const uint32_t full_bar = bar_base;                                // kStages barriers each
   const uint32_t empty_bar = bar_base + 8 * kStages;
-  const uint32_t tmem_full_bar = bar_base + 16 * kStages;
-  const uint32_t tmem_slot = bar_base + 16 * kStages + 8;
+  const uint32_t split_bar = bar_base + 16 * kStages;
+  const uint32_t tmem_full_bar = bar_base + 24 * kStages;
+  const uint32_t tmem_slot = tmem_full_bar + 8;
   uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -175,6 +187,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   ghn3_gemm_problem p;
   int mt, nt;
+  int kb0 = 0, kb1 = (args.k + BK - 1) / BK;
+  bool first_split = true;
   if (args.tiles != nullptr) {
     const int4 t = args.tiles[blockIdx.x];
     p = args.problems[t.x];
@@ -184,8 +198,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     p = args.single;
     mt = blockIdx.y;
     nt = blockIdx.x;
+    if (args.k_splits > 1) {
+      const int per = (kb1 + args.k_splits - 1) / args.k_splits;
+      kb0 = blockIdx.z * per;
+      kb1 = min(kb1, kb0 + per);
+      first_split = blockIdx.z == 0;
+      if (kb0 >= kb1) return;               // uniform for the CTA, before any barrier / TMEM allocation
+    }
   }
-  const int num_kb = (args.k + BK - 1) / BK;
+  const int num_kb = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -193,6 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(split_bar + 8 * s, 128);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -208,39 +230,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       const int a_row = p.a_row0 + mt * kBlockM;
       const int b_row = p.b_row0 + nt * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + B_BYTES);
-        tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, kb * BK, a_row);
-        tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, b_row);
+        tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, (kb0 + i) * BK, a_row);
+        tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, (kb0 + i) * BK, b_row);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(full_bar + 8 * s, ph);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait((kX3 ? split_bar : full_bar) + 8 * s, ph);
         tcgen05_fence_after();
         const uint64_t da = make_smem_desc(sA + s * A_BYTES);
         const uint64_t db = make_smem_desc(sB + s * B_BYTES);
+        if constexpr (kX3) {
+          const uint64_t da_lo = make_smem_desc(sAlo + s * A_BYTES);
+          const uint64_t db_lo = make_smem_desc(sBlo + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < kMmaPerStage; ++k) {
-          // advancing K inside the 128B swizzle span: +32 bytes = +2 in the (addr >> 4) field
-          umma<kTf32>(tmem_base, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kMmaPerStage; ++k) {
+            umma<true>(tmem_base, da_lo + 2 * k, db + 2 * k, kIdesc, (i | k) != 0 ? 1u : 0u);
+            umma<true>(tmem_base, da + 2 * k, db_lo + 2 * k, kIdesc, 1u);
+            umma<true>(tmem_base, da + 2 * k, db + 2 * k, kIdesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kMmaPerStage; ++k) {
+            // advancing K inside the 128B swizzle span: +32 bytes = +2 in the (addr >> 4) field
+            umma<kTf32>(tmem_base, da + 2 * k, db + 2 * k, kIdesc, (i | k) != 0 ? 1u : 0u);
+          }
         }
         tcgen05_commit(empty_bar + 8 * s);       // slot reusable once these MMAs have read it
       }
       tcgen05_commit(tmem_full_bar);             // accumulator complete
     }
-  } else {
+  } else if (warp < 6) {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int m = mt * kBlockM + row;
     const bool row_ok = m < p.m;
+    const bool atomic = args.k_splits > 1 && args.tiles == nullptr;
+    const bool use_bias = p.bias_off >= 0 && first_split;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const int64_t d_row = p.d_off + (int64_t)m * p.ldd;
@@ -257,7 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[j]);
-          if (p.bias_off >= 0 && j < ncols) x += __ldg(args.bias + p.bias_off + n0 + j);
+          if (use_bias && j < ncols) x += __ldg(args.bias + p.bias_off + n0 + j);
           v[j] = apply_act(x, args.act);
         }
         if (args.out_dtype == GHN3_BF16) {
@@ -274,12 +309,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               *(uint4*)(dptr + j) = pk;
             }
           } else {
-            for (int j = 0; j < ncols; ++j) dptr[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dptr[j] = __float2bfloat16_rn(v[j]);
           }
         } else {
           float* dptr = (float*)args.d + d_row + n0;
           const bool tf = args.out_dtype == GHN3_TF32;
-          if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
+          if (atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(dptr + j, v[j]);
+          } else if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -291,13 +332,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               *(float4*)(dptr + j) = o;
             }
           } else {
-            for (int j = 0; j < ncols; ++j) {
-              float o = v[j];
-              if (args.accumulate) o += dptr[j];
-              dptr[j] = tf ? round_tf32(o) : o;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                float o = v[j];
+                if (args.accumulate) o += dptr[j];
+                dptr[j] = tf ? round_tf32(o) : o;
+              }
             }
           }
         }
+      }
+    }
+  } else {
+    // kX3 only: warps 6..9 split each landed fp32 tile into hi (in place) and lo (second buffer)
+    if constexpr (kX3) {
+      const int t = threadIdx.x - 192;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        float4* a_hi = (float4*)(smem_raw + (sA + s * A_BYTES - smem_u32(smem_raw)));
+        float4* a_lo = (float4*)(smem_raw + (sAlo + s * A_BYTES - smem_u32(smem_raw)));
+        float4* b_hi = (float4*)(smem_raw + (sB + s * B_BYTES - smem_u32(smem_raw)));
+        float4* b_lo = (float4*)(smem_raw + (sBlo + s * B_BYTES - smem_u32(smem_raw)));
+        auto split4 = [](float4* hi, float4* lo, int idx) {
+          float4 v = hi[idx], h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        };
+#pragma unroll 4
+        for (int idx = t; idx < (int)(A_BYTES / 16); idx += 128) split4(a_hi, a_lo, idx);
+#pragma unroll 4
+        for (int idx = t; idx < (int)(B_BYTES / 16); idx += 128) split4(b_hi, b_lo, idx);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        mbar_arrive(split_bar + 8 * s);
       }
     }
   }
@@ -356,16 +429,18 @@ static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, in
   return GHN3_OK;
 }
 
-template <bool kTf32, int BN>
+template <bool kTf32, bool kX3, int BN, int kStages>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelArgs& ka, dim3 grid,
                        cudaStream_t stream) {
-  constexpr int smem = gemm_smem_bytes<BN>();
+  constexpr int smem = gemm_smem_bytes<kX3, BN, kStages>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kTf32, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<kTf32, kX3, BN, kStages>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  gemm_tcgen05_kernel<kTf32, BN><<<grid, kThreads, smem, stream>>>(ma, mb, ka);
+  gemm_tcgen05_kernel<kTf32, kX3, BN, kStages><<<grid, gemm_threads<kX3>(), smem, stream>>>(ma, mb, ka);
   GHN3_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return GHN3_OK;
 }
@@ -375,24 +450,42 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a->in_dtype == GHN3_BF16 || a->in_dtype == GHN3_TF32, "ghn3_gemm: in_dtype must be BF16 or TF32");
   GHN3_REQUIRE(a->out_dtype >= GHN3_BF16 && a->out_dtype <= GHN3_F32, "ghn3_gemm: bad out_dtype");
   const bool tf32 = a->in_dtype == GHN3_TF32;
+  const bool x3 = a->tf32_x3 != 0;
+  GHN3_REQUIRE(!x3 || tf32, "ghn3_gemm: tf32_x3 needs in_dtype TF32 (fp32 storage)");
   const int eb = tf32 ? 4 : 2;
   GHN3_REQUIRE(a->k > 0 && (a->lda * eb) % 16 == 0 && (a->ldb * eb) % 16 == 0,
                "ghn3_gemm: K must be positive and row strides multiples of 16 bytes (lda=%lld ldb=%lld)",
                (long long)a->lda, (long long)a->ldb);
   GHN3_REQUIRE((((uintptr_t)a->a) & 15) == 0 && (((uintptr_t)a->b) & 15) == 0, "ghn3_gemm: A/B must be 16-byte aligned");
   GHN3_REQUIRE(!a->accumulate || a->out_dtype != GHN3_BF16, "ghn3_gemm: accumulate needs an fp32 output");
-  const int bn = a->block_n == 0 ? 128 : a->block_n;
-  GHN3_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "ghn3_gemm: block_n must be 32/64/128/256");
+  const int num_kb = (int)ceil_div(a->k, kRowBytes / eb);
 
+  int bn = a->block_n;
+  int splits = 1;
   dim3 grid;
   if (a->problems != nullptr) {
     GHN3_REQUIRE(a->tiles != nullptr && a->n_tiles >= 0, "ghn3_gemm: grouped launch needs a tile list");
     if (a->n_tiles == 0) return GHN3_OK;
+    if (bn == 0) bn = 128;
     grid = dim3((unsigned)a->n_tiles, 1, 1);
   } else {
     if (a->single.m <= 0 || a->single.n <= 0) return GHN3_OK;
-    grid = dim3((unsigned)ceil_div(a->single.n, bn), (unsigned)ceil_div(a->single.m, kBlockM), 1);
+    const int sms = num_sms();
+    const int64_t mt = ceil_div(a->single.m, kBlockM);
+    if (bn == 0) bn = (mt * ceil_div(a->single.n, 128) >= sms) ? 128 : 64;   // small problems: more, smaller tiles
+    const int64_t ctas = mt * ceil_div(a->single.n, bn);
+    if (a->k_splits > 0) {
+      splits = a->k_splits;
+    } else if (a->accumulate && a->out_dtype == GHN3_F32 && ctas < sms && num_kb >= 4) {
+      // residual updates are sums anyway: split K so that ~one wave of CTAs shares the reduction
+      splits = (int)std::min<int64_t>(std::max<int64_t>(sms / ctas, 1), num_kb / 2);
+    }
+    GHN3_REQUIRE(splits == 1 || (a->accumulate && a->out_dtype == GHN3_F32 && a->act == GHN3_ACT_NONE),
+                 "ghn3_gemm: split-K needs accumulate=1, an fp32 output and no activation");
+    grid = dim3((unsigned)ceil_div(a->single.n, bn), (unsigned)mt, (unsigned)splits);
   }
+  GHN3_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ghn3_gemm: block_n must be 64/128/256");
+  GHN3_REQUIRE(!(x3 && bn == 256), "ghn3_gemm: tf32_x3 supports block_n 64/128");
 
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, a->a, a->a_rows, a->k, a->lda, tf32, kBlockM);
@@ -410,20 +503,20 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.out_dtype = a->out_dtype;
   ka.act = a->act;
   ka.accumulate = a->accumulate;
+  ka.k_splits = splits;
 
-#define GHN3_GEMM_CASE(TF, BNV) \
-  if (tf32 == TF && bn == BNV) return launch_gemm<TF, BNV>(ma, mb, ka, grid, stream);
-  GHN3_GEMM_CASE(false, 32)
-  GHN3_GEMM_CASE(false, 64)
-  GHN3_GEMM_CASE(false, 128)
-  GHN3_GEMM_CASE(false, 256)
-  GHN3_GEMM_CASE(true, 32)
-  GHN3_GEMM_CASE(true, 64)
-  GHN3_GEMM_CASE(true, 128)
-  GHN3_GEMM_CASE(true, 256)
-#undef GHN3_GEMM_CASE
-  set_error("ghn3_gemm: unsupported configuration");
-  return GHN3_ERR_UNSUPPORTED;
+  if (x3) {
+    if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);
+    return launch_gemm<true, true, 128, 3>(ma, mb, ka, grid, stream);
+  }
+  if (tf32) {
+    if (bn == 64) return launch_gemm<true, false, 64, 6>(ma, mb, ka, grid, stream);
+    if (bn == 128) return launch_gemm<true, false, 128, 3>(ma, mb, ka, grid, stream);
+    return launch_gemm<true, false, 256, 4>(ma, mb, ka, grid, stream);
+  }
+  if (bn == 64) return launch_gemm<false, false, 64, 6>(ma, mb, ka, grid, stream);
+  if (bn == 128) return launch_gemm<false, false, 128, 3>(ma, mb, ka, grid, stream);
+  return launch_gemm<false, false, 256, 4>(ma, mb, ka, grid, stream);
 }
 
 }  // namespace ghn3

@@ -24,7 +24,11 @@ from .plan import (BatchPlan, ModelPlan, SCATTER_CHUNK, SRC_CLSB, SRC_CLSW, SRC_
 from .weights import (EDGE_EMBED_ROWS, MAX_DEGREE, MAX_INPUT_DIST, N_PRIMITIVES, channel_bins, normalize_config,
                       sinusoid_table, spatial_bins)
 
-DTYPES = {'bf16': ops.BF16, 'tf32': ops.TF32}
+# compute_dtype -> (GEMM input storage dtype, 3-term compensated tf32?)
+#   'bf16'   : bf16 operands, kind::f16 MMAs                                   (fast path, <= 2e-2)
+#   'tf32'   : fp32 operands, kind::tf32 MMAs with hi/lo error compensation     (accurate path, <= 1e-3)
+#   'tf32x1' : fp32 operands pre-rounded to tf32, single-pass kind::tf32 MMAs   (~1e-3, borderline)
+DTYPES = {'bf16': (ops.BF16, False), 'tf32': (ops.TF32, True), 'tf32x1': (ops.TF32, False)}
 
 
 def log(*a, **k):
@@ -197,12 +201,12 @@ class GHN3(GHN):
         if not self.layernorm:
             raise NotImplementedError('ghn3_b200: layernorm=False GHNs are not supported by the CUDA path')
         self.fix_embed_layers()
-        dt = DTYPES[self.compute_dtype]
+        dt, x3 = DTYPES[self.compute_dtype]
         C, S = self.hid, self.max_shape[2]
         f = lambda p: p.detach().contiguous().float()
-        cv = lambda p: ops.convert(f(p), dt)
+        cv = (lambda p: f(p)) if x3 else (lambda p: ops.convert(f(p), dt))      # x3 keeps the fp32 master weights
         g0 = self.gnn[0]
-        w = {'sig': sig, 'dtype': dt}
+        w = {'sig': sig, 'dtype': dt, 'x3': x3, 'act': ops.F32 if x3 else dt}
         w['tables'] = {'embed_op': f(self.embed.weight), 'embed_ch': f(self.shape_enc.embed_channel.weight),
                        'embed_sp': f(self.shape_enc.embed_spatial.weight),
                        'cent_in': f(g0.centrality_embed_in.weight), 'cent_out': f(g0.centrality_embed_out.weight),
@@ -226,7 +230,7 @@ class GHN3(GHN):
         # fc weight repacked position-major: [c*S*S + p][k] -> [p][c][k], so one decoder-grid position is one
         # contiguous [4C, C] block and a crop window is a set of row ranges (nn.py:738-745)
         fc_w = f(dec.fc[0].weight).view(4 * C, S * S, C).permute(1, 0, 2).contiguous().view(S * S * 4 * C, C)
-        w['fc_w'] = ops.convert(fc_w, dt)
+        w['fc_w'] = fc_w if x3 else ops.convert(fc_w, dt)
         del fc_w
         w['fc_b'] = f(dec.fc[0].bias).view(4 * C, S * S).t().contiguous().view(-1)
         w['c0_w'], w['c0_b'] = cv(dec.conv[0].weight), f(dec.conv[0].bias)
@@ -335,7 +339,7 @@ class GHN3(GHN):
 
     def _run(self, w, pack, bp, return_embeddings):
         device = self.embed.weight.device
-        dt = w['dtype']
+        dt, x3, act = w['dtype'], w['x3'], w['act']
         tdt = ops.TORCH_DTYPE[dt]
         C, H = self.hid, self.heads
         ms0, ms1, S, _ = self.max_shape
@@ -373,8 +377,8 @@ class GHN3(GHN):
                               ln_w=L.ptr(w['ln_w']), ln_b=L.ptr(w['ln_b']), n_graphs=pack.n_graphs, total_nodes=N,
                               max_nodes=pack.max_nodes, lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']),
                               mat_off=L.ptr(pack.d['mat_off']), pair=L.ptr(pack.pair), lut=L.ptr(lut), x=L.ptr(x),
-                              h=L.ptr(h), qkv=L.ptr(qkv), ff=L.ptr(ff), dec_in=L.ptr(dec_in), dec_dtype=dt,
-                              dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(emb))
+                              h=L.ptr(h), qkv=L.ptr(qkv), ff=L.ptr(ff), dec_in=L.ptr(dec_in), dec_dtype=act,
+                              dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(emb), tf32_x3=int(x3))
         L.call('graphormer_stack', ga, stream)
         mark('graphormer')
 
@@ -383,14 +387,14 @@ class GHN3(GHN):
         R = bp.conv_total_rows
         if R > 0:
             h0 = torch.empty(R, 4 * C, dtype=tdt, device=device)
-            ops.gemm(dec_in, w['fc_w'], bias=w['fc_b'], act=ops.ACT_RELU, in_dtype=dt, out=h0, out_dtype=dt,
-                     problems=st['fc_problems'], tiles=st['fc_tiles'])
+            ops.gemm(dec_in, w['fc_w'], bias=w['fc_b'], act=ops.ACT_RELU, in_dtype=dt, out=h0, out_dtype=act,
+                     problems=st['fc_problems'], tiles=st['fc_tiles'], x3=x3)
             mark('dec_fc')
-            h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=dt)
+            h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=act, x3=x3)
             mark('dec_conv0')
             wout = torch.empty(bp.wout_elems, dtype=torch.float32, device=device)
             ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
-                     problems=st['c2_problems'], tiles=st['c2_tiles'])
+                     problems=st['c2_problems'], tiles=st['c2_tiles'], x3=x3)
             mark('dec_conv2')
             bufs[SRC_WOUT] = wout
             if bp.clsw_elems:
@@ -403,8 +407,8 @@ class GHN3(GHN):
         # ---- 1-D decoder (+ classification bias head) ----
         if bp.n_1d > 0:
             d_in = dec_in[bp.n_conv:bp.n_conv + bp.n_1d]
-            hid1 = ops.gemm(d_in, w['d1_w0'], bias=w['d1_b0'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=dt)
-            d1 = ops.gemm(hid1, w['d1_w1'], bias=w['d1_b1'], in_dtype=dt, out_dtype=ops.F32)
+            hid1 = ops.gemm(d_in, w['d1_w0'], bias=w['d1_b0'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=act, x3=x3)
+            d1 = ops.gemm(hid1, w['d1_w1'], bias=w['d1_b1'], in_dtype=dt, out_dtype=ops.F32, x3=x3)
             bufs[SRC_D1] = d1
             if bp.n_clsb:
                 mc = bp.max_ch

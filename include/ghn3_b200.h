@@ -183,7 +183,9 @@ typedef struct {
   const ghn3_gemm_problem* problems;   /* device, or NULL */
   const int32_t* tiles;                /* device int32[n_tiles][4], or NULL */
   int32_t n_tiles;
-  int32_t block_n;           /* 0 = default (128); 32/64/128/256 */
+  int32_t block_n;           /* 0 = auto; 64/128/256 */
+  int32_t k_splits;          /* single-problem launches: 0 = auto, >1 splits K over blockIdx.z (needs accumulate) */
+  int32_t tf32_x3;           /* in_dtype TF32 only: 3-term error-compensated tf32 (hi/lo split in shared memory) */
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);
@@ -215,7 +217,7 @@ typedef struct {
   const int32_t* node_off;
   const int64_t* mat_off;
   const void* qkv;           /* [total_nodes][3C] in dtype: q | k | v, head-major inside each */
-  int32_t dtype;             /* GHN3_BF16 | GHN3_TF32 (fp32 storage) */
+  int32_t dtype;             /* GHN3_BF16 | GHN3_TF32 (fp32 storage, output rounded to tf32) | GHN3_F32 */
   const uint16_t* pair;
   const float* lut;          /* [H][lut_size] */
   void* out;                 /* [total_nodes][C] in dtype */
@@ -256,6 +258,8 @@ typedef struct {
   void* dec_in; int32_t dec_dtype;         /* rows scattered by dst_row */
   const int32_t* dst_row;                  /* [total_nodes] or NULL (identity) */
   float* emb_f32;                          /* optional [total_nodes][C] */
+  int32_t tf32_x3;                         /* dtype TF32 only: activations stay un-rounded fp32, GEMMs use the
+                                              3-term compensated tf32 mode (~fp32 accuracy) */
 } ghn3_graphormer_args;
 
 int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream);

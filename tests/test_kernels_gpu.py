@@ -43,7 +43,37 @@ def test_gemm_plain(m, n, k, dtype):
     assert _rel(out, ref) < 2e-5, (m, n, k, _rel(out, ref))
 
 
-@pytest.mark.parametrize('block_n', [32, 64, 128, 256])
+@pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
+def test_gemm_tf32_x3_is_fp32_accurate(m, n, k):
+    """3-term compensated tf32: un-rounded fp32 operands, error ~1e-6 instead of ~5e-4."""
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV)
+    b = torch.randn(n, k, device=DEV) / k ** 0.5
+    ref = (a.double() @ b.double().t()).float()
+    out = ops.gemm(a, b, in_dtype=ops.TF32, out_dtype=ops.F32, x3=True)
+    out1 = ops.gemm(ops.convert(a, ops.TF32), ops.convert(b, ops.TF32), in_dtype=ops.TF32, out_dtype=ops.F32)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 3e-6, (m, n, k, _rel(out, ref))
+    assert _rel(out1, ref) < 3e-3
+
+
+@pytest.mark.parametrize('x3', [False, True])
+@pytest.mark.parametrize('splits', [0, 2, 5])
+def test_gemm_split_k_accumulate(splits, x3):
+    torch.manual_seed(splits)
+    m, n, k = 457, 384, 1536
+    a = torch.randn(m, k, device=DEV)
+    b = torch.randn(n, k, device=DEV) / k ** 0.5
+    bias = torch.randn(n, device=DEV)
+    a_in, b_in, dt = (a, b, ops.TF32) if x3 else (a.bfloat16(), b.bfloat16(), ops.BF16)
+    x = torch.randn(m, n, device=DEV)
+    ref = (x.double() + a_in.double() @ b_in.double().t() + bias.double()).float()
+    ops.gemm(a_in, b_in, bias=bias, in_dtype=dt, out=x, out_dtype=ops.F32, accumulate=True, k_splits=splits, x3=x3)
+    torch.cuda.synchronize()
+    assert _rel(x, ref) < 2e-5
+
+
+@pytest.mark.parametrize('block_n', [64, 128, 256])
 def test_gemm_block_n(block_n):
     torch.manual_seed(block_n)
     a = torch.randn(200, 512, device=DEV).bfloat16()

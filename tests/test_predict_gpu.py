@@ -14,7 +14,9 @@ from tests import helpers as H
 
 DEV = 'cuda'
 # north_star tolerance: max relative error (max |a-b| / max |b| per tensor) <= 1e-3 (tf32), <= 2e-2 (bf16)
-TOL = {'tf32': 1e-3, 'bf16': 2e-2}
+# 'tf32' = kind::tf32 tensor-core MMAs with 3-term error compensation; 'tf32x1' = single-pass tf32 whose inherent
+# error on this network sits right at 1e-3 (7.7e-4 ... 1.2e-3 measured), so it is held to a looser bound.
+TOL = {'tf32': 1e-3, 'tf32x1': 4e-3, 'bf16': 2e-2}
 
 
 def make_ghn(cfg_name, dtype):
@@ -78,7 +80,7 @@ def test_tiny_single(arch, dtype):
     run_case('ghn3tiny', [arch], dtype)
 
 
-@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+@pytest.mark.parametrize('dtype', ['tf32', 'tf32x1', 'bf16'])
 def test_tm8_resnet50(dtype):
     run_case('ghn3tm8', ['resnet50'], dtype)
 
