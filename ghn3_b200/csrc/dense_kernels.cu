@@ -69,10 +69,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const ghn3_layernorm_arg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Attention. CTA = (graph, head, 16 queries); 8 warps, 2 queries per warp. Keys are processed in tiles of KT = 256
-// staged in shared memory as fp32 (rows padded to D+1 words: conflict-free when lanes walk over keys). Lane l
-// scores keys l, l+32, ...; the tile maximum and the normaliser are combined with warp shuffles; every lane keeps
-// a partial output over its own keys which is reduced across the warp once at the end.
+// Attention. CTA = (graph, head, 16 queries); 8 warps, 2 queries per warp. Keys are processed in tiles of KT = 256.
+// Per tile the CTA stages, with independent 16-byte loads, K and V of the head (fp32, rows padded to D+1 words:
+// conflict-free when lanes walk over keys) and the edge bias of its 16 x 256 (query, key) pairs, already looked up
+// in the head's LUT (bias = lut[h][pair[i][j]] * log2e). Lane l scores keys l, l+32, ... for BOTH queries of its
+// warp from one read of K / V; the tile maximum and the normaliser are combined with warp shuffles; every lane
+// keeps a partial output over its own keys which is reduced across the warp once at the end.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kAttnKT = 256;
 constexpr int kAttnQPerWarp = 2;
@@ -80,12 +82,14 @@ constexpr int kAttnWarps = 8;
 constexpr int kAttnQT = kAttnQPerWarp * kAttnWarps;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_attention_args a) {
+__global__ void __launch_bounds__(kAttnWarps * 32, (D <= 24) ? 2 : 1) attention_kernel(const ghn3_attention_args a) {
   extern __shared__ float attn_smem[];
   constexpr int DP = D + 1;
-  float* sK = attn_smem;                 // [KT][DP]
-  float* sV = sK + kAttnKT * DP;         // [KT][DP]
-  float* sLut = sV + kAttnKT * DP;       // [lut_size]
+  constexpr int R = kAttnKT / 32;
+  float* sK = attn_smem;                      // [KT][DP]
+  float* sV = sK + kAttnKT * DP;              // [KT][DP]
+  float* sBias = sV + kAttnKT * DP;           // [QT][KT]
+  float* sLut = sBias + kAttnQT * kAttnKT;    // [lut_size]
 
   const int g = blockIdx.z, h = blockIdx.y;
   const int n0 = a.node_off[g];
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_a
   const float scale_log2 = rsqrtf((float)D) * 1.44269504088896340736f;
   constexpr float kLog2e = 1.44269504088896340736f;
 
-  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i] * kLog2e;
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = __ldg(a.lut + (int64_t)h * a.lut_size + i) * kLog2e;
 
   float q[kAttnQPerWarp][D], acc[kAttnQPerWarp][D], m[kAttnQPerWarp], l[kAttnQPerWarp];
   int qi[kAttnQPerWarp];
@@ -117,10 +121,12 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_a
     m[t] = -INFINITY;
     l[t] = 0.f;
   }
+  const bool any_q = qi[0] < n;               // warp-uniform (qi[1] valid implies qi[0] valid)
+  const int nq = min(kAttnQT, n - q0);
 
   for (int k0 = 0; k0 < n; k0 += kAttnKT) {
     const int kt = min(kAttnKT, n - k0);
-    __syncthreads();   // previous tile fully consumed (also orders the LUT fill on the first iteration)
+    __syncthreads();   // previous tile fully consumed; orders the LUT fill before the first bias staging
     {
       // 16-byte (8-byte for D*sizeof(T) == 8) vector loads of the K and V head slices, all independent
       constexpr int ROW_BYTES = D * (int)sizeof(T);
@@ -146,43 +152,74 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_a
           sV[j * DP + c * EPV + e] = to_float(vv.e[e]);
         }
       }
+      // edge bias of the (query, key) pairs of this tile: 8 pair indices per 16-byte load -> 8 LUT values
+      const int kt8 = (kt + 7) >> 3;           // rows are padded to ld (multiple of 16), so this never overruns
+      for (int idx = threadIdx.x; idx < nq * kt8; idx += blockDim.x) {
+        const int qq = idx / kt8, c = idx - qq * kt8;
+        union { uint4 u4; uint16_t e[8]; } pv;
+        pv.u4 = __ldg((const uint4*)(pair + (int64_t)(q0 + qq) * ld + k0 + c * 8));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sBias[qq * kAttnKT + c * 8 + e] = sLut[pv.e[e]];
+      }
     }
     __syncthreads();
+    if (any_q) {
+      const float* b0 = sBias + (warp * kAttnQPerWarp) * kAttnKT;
+      float s[kAttnQPerWarp][R];
+      float tmax[kAttnQPerWarp];
 #pragma unroll
-    for (int t = 0; t < kAttnQPerWarp; ++t) {
-      if (qi[t] >= n) continue;   // warp-uniform
-      const uint16_t* prow = pair + (int64_t)qi[t] * ld + k0;
-      float s[kAttnKT / 32];
-      float tmax = -INFINITY;
+      for (int t = 0; t < kAttnQPerWarp; ++t) tmax[t] = -INFINITY;
 #pragma unroll
-      for (int r = 0; r < kAttnKT / 32; ++r) {
+      for (int r = 0; r < R; ++r) {
         const int j = lane + 32 * r;
-        float dot = -INFINITY;
         if (j < kt) {
-          dot = sLut[prow[j]];
           const float* kp = sK + j * DP;
+          float dot[kAttnQPerWarp];
 #pragma unroll
-          for (int d = 0; d < D; ++d) dot = fmaf(q[t][d], kp[d], dot);
+          for (int t = 0; t < kAttnQPerWarp; ++t) dot[t] = b0[t * kAttnKT + j];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const float kd = kp[d];
+#pragma unroll
+            for (int t = 0; t < kAttnQPerWarp; ++t) dot[t] = fmaf(q[t][d], kd, dot[t]);
+          }
+#pragma unroll
+          for (int t = 0; t < kAttnQPerWarp; ++t) {
+            s[t][r] = dot[t];
+            tmax[t] = fmaxf(tmax[t], dot[t]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < kAttnQPerWarp; ++t) s[t][r] = -INFINITY;
         }
-        s[r] = dot;
-        tmax = fmaxf(tmax, dot);
       }
-      tmax = warp_max(tmax);
-      const float m_new = fmaxf(m[t], tmax);
-      const float corr = exp2f(m[t] - m_new);
-      m[t] = m_new;
-      l[t] *= corr;
+      float m_new[kAttnQPerWarp];
 #pragma unroll
-      for (int d = 0; d < D; ++d) acc[t][d] *= corr;
+      for (int t = 0; t < kAttnQPerWarp; ++t) {
+        m_new[t] = fmaxf(m[t], warp_max(tmax[t]));
+        const float corr = exp2f(m[t] - m_new[t]);
+        m[t] = m_new[t];
+        l[t] *= corr;
 #pragma unroll
-      for (int r = 0; r < kAttnKT / 32; ++r) {
+        for (int d = 0; d < D; ++d) acc[t][d] *= corr;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
         const int j = lane + 32 * r;
         if (j < kt) {
-          const float p = exp2f(s[r] - m_new);
-          l[t] += p;
+          float p[kAttnQPerWarp];
+#pragma unroll
+          for (int t = 0; t < kAttnQPerWarp; ++t) {
+            p[t] = exp2f(s[t][r] - m_new[t]);
+            l[t] += p[t];
+          }
           const float* vp = sV + j * DP;
 #pragma unroll
-          for (int d = 0; d < D; ++d) acc[t][d] = fmaf(p, vp[d], acc[t][d]);
+          for (int d = 0; d < D; ++d) {
+            const float vd = vp[d];
+#pragma unroll
+            for (int t = 0; t < kAttnQPerWarp; ++t) acc[t][d] = fmaf(p[t], vd, acc[t][d]);
+          }
         }
       }
     }
@@ -208,7 +245,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const ghn3_a
 
 template <typename T, int D>
 static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
-  const int smem = (2 * kAttnKT * (D + 1) + a->lut_size) * (int)sizeof(float);
+  const int smem = (2 * kAttnKT * (D + 1) + kAttnQT * kAttnKT + a->lut_size) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
     GHN3_CUDA(cudaFuncSetAttribute(attention_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
