@@ -243,6 +243,238 @@ __global__ void __launch_bounds__(kAttnWarps * 32, (D <= 24) ? 2 : 1) attention_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Attention on the tensor cores (bf16 storage): mma.sync m16n8k16, flash-attention-2 register layout.
+// CTA = (graph, head, 64 queries); 4 warps x 16 queries. K (key-major, dims zero-padded to a multiple of 16) and
+// V^T (dim-major) of the head are staged per 256-key tile as bf16 with row strides chosen so that every
+// B-fragment load is bank-conflict free. Logits start from the edge bias lut[h][pair[i][j]] (pair indices are read
+// as 32-bit words straight from global memory, issued before the QK^T MMAs so their latency overlaps), softmax is
+// the usual online form with quad shuffles, P is re-packed in registers as the A operand of P.V.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+
+constexpr int kMmaKT = 256;      // keys staged per outer iteration
+constexpr int kMmaQT = 64;       // queries per CTA
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention_args a) {
+  constexpr int DK = (D + 15) / 16 * 16;   // k extent of Q.K^T
+  constexpr int DS = DK + 8;               // K row stride (bf16 elements)
+  constexpr int DN = (D + 7) / 8 * 8;      // n extent of P.V
+  constexpr int VS = kMmaKT + 8;           // V^T row stride (bf16 elements)
+  constexpr int NT2 = DN / 8;
+  constexpr int KK = DK / 16;
+  extern __shared__ __align__(16) uint8_t attn_mma_smem[];
+  __nv_bfloat16* sK = (__nv_bfloat16*)attn_mma_smem;            // [KT][DS]
+  __nv_bfloat16* sVt = sK + kMmaKT * DS;                        // [DN][VS]
+  float* sLut = (float*)(sVt + DN * VS);                        // [lut_size]
+
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int n0 = a.node_off[g];
+  const int n = a.node_off[g + 1] - n0;
+  const int q0 = blockIdx.x * kMmaQT;
+  if (q0 >= n) return;
+  const int ld = (n + 15) & ~15;
+  const int C = a.hid, C3 = 3 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const __nv_bfloat16* qkv = (const __nv_bfloat16*)a.qkv + (int64_t)n0 * C3;
+  const uint16_t* pair = a.pair + a.mat_off[g];
+  const float scale_log2 = rsqrtf((float)D) * 1.44269504088896340736f;
+  constexpr float kLog2e = 1.44269504088896340736f;
+
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = __ldg(a.lut + (int64_t)h * a.lut_size + i) * kLog2e;
+  // zero the padded dims of K once (they are never overwritten) and the padded dims of V^T
+  if (DK > D) {
+    for (int idx = threadIdx.x; idx < kMmaKT * (DK - D); idx += blockDim.x) {
+      const int j = idx / (DK - D), d = D + idx % (DK - D);
+      sK[j * DS + d] = __float2bfloat16_rn(0.f);
+    }
+  }
+  if (DN > D) {
+    for (int idx = threadIdx.x; idx < (DN - D) * VS; idx += blockDim.x) sVt[D * VS + idx] = __float2bfloat16_rn(0.f);
+  }
+
+  // Q fragments of this warp's 16 queries, pre-scaled by d^-1/2 * log2(e)
+  const int r0 = q0 + warp * 16 + gq, r1 = r0 + 8;
+  const bool ok0 = r0 < n, ok1 = r1 < n;
+  uint32_t aq[KK][4];
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int d = kk * 16 + half * 8 + 2 * tq;
+      float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+      if (d < D) {
+        if (ok0) {
+          const __nv_bfloat162 t = *(const __nv_bfloat162*)(qkv + (int64_t)r0 * C3 + h * D + d);
+          v00 = __low2float(t) * scale_log2; v01 = __high2float(t) * scale_log2;
+        }
+        if (ok1) {
+          const __nv_bfloat162 t = *(const __nv_bfloat162*)(qkv + (int64_t)r1 * C3 + h * D + d);
+          v10 = __low2float(t) * scale_log2; v11 = __high2float(t) * scale_log2;
+        }
+      }
+      aq[kk][half * 2 + 0] = pack_bf16(v00, v01);
+      aq[kk][half * 2 + 1] = pack_bf16(v10, v11);
+    }
+  }
+  const uint16_t* prow0 = pair + (int64_t)(ok0 ? r0 : q0) * ld;
+  const uint16_t* prow1 = pair + (int64_t)(ok1 ? r1 : q0) * ld;
+
+  float o[NT2][4];
+#pragma unroll
+  for (int i = 0; i < NT2; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const bool warp_active = (q0 + warp * 16) < n;     // warp-uniform
+
+  for (int k0 = 0; k0 < n; k0 += kMmaKT) {
+    const int kt = min(kMmaKT, n - k0);
+    const int kt64 = (kt + 63) & ~63;
+    __syncthreads();
+    {
+      constexpr int ROW_BYTES = D * 2;
+      constexpr int VB = (ROW_BYTES % 16 == 0) ? 16 : 8;
+      constexpr int VPR = ROW_BYTES / VB;
+      constexpr int EPV = VB / 2;
+      const char* kbase = (const char*)(qkv + (int64_t)k0 * C3 + C + h * D);
+      const size_t row_stride = (size_t)C3 * 2, v_off = (size_t)C * 2;
+      for (int idx = threadIdx.x; idx < kt64 * VPR; idx += blockDim.x) {
+        const int j = idx / VPR, c = idx - j * VPR;
+        union { uint4 u4; uint2 u2; __nv_bfloat16 e[EPV]; } kv, vv;
+        kv.u4 = make_uint4(0, 0, 0, 0);
+        vv.u4 = make_uint4(0, 0, 0, 0);
+        if (j < kt) {
+          const char* src = kbase + (size_t)j * row_stride + c * VB;
+          if constexpr (VB == 16) {
+            kv.u4 = __ldg((const uint4*)src);
+            vv.u4 = __ldg((const uint4*)(src + v_off));
+          } else {
+            kv.u2 = __ldg((const uint2*)src);
+            vv.u2 = __ldg((const uint2*)(src + v_off));
+          }
+        }
+        if constexpr (VB == 16) *(uint4*)(sK + j * DS + c * EPV) = kv.u4;
+        else *(uint2*)(sK + j * DS + c * EPV) = kv.u2;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) sVt[(c * EPV + e) * VS + j] = vv.e[e];
+      }
+    }
+    __syncthreads();
+    if (!warp_active) continue;
+    for (int c0 = 0; c0 < kt; c0 += 64) {
+      // edge-bias indices of this 16 x 64 block: two keys per 32-bit load
+      uint32_t pw0[8], pw1[8];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = k0 + c0 + nt * 8 + 2 * tq;
+        pw0[nt] = 0; pw1[nt] = 0;
+        if (col < n) {
+          pw0[nt] = __ldg((const uint32_t*)(prow0 + col));
+          pw1[nt] = __ldg((const uint32_t*)(prow1 + col));
+        }
+      }
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const __nv_bfloat16* kp = sK + (c0 + nt * 8 + gq) * DS + kk * 16 + 2 * tq;
+          mma_bf16_16816(s[nt], aq[kk], *(const uint32_t*)kp, *(const uint32_t*)(kp + 8));
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = k0 + c0 + nt * 8 + 2 * tq;
+        const bool v0 = col < n, v1 = col + 1 < n;
+        s[nt][0] = v0 ? s[nt][0] + sLut[pw0[nt] & 0xFFFFu] : -INFINITY;
+        s[nt][1] = v1 ? s[nt][1] + sLut[pw0[nt] >> 16] : -INFINITY;
+        s[nt][2] = v0 ? s[nt][2] + sLut[pw1[nt] & 0xFFFFu] : -INFINITY;
+        s[nt][3] = v1 ? s[nt][3] + sLut[pw1[nt] >> 16] : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= corr0; l1 *= corr1;
+#pragma unroll
+      for (int i = 0; i < NT2; ++i) { o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1; }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
+        s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        uint32_t ap[4];
+        ap[0] = pack_bf16(s[2 * k2][0], s[2 * k2][1]);
+        ap[1] = pack_bf16(s[2 * k2][2], s[2 * k2][3]);
+        ap[2] = pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+        ap[3] = pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+#pragma unroll
+        for (int i = 0; i < NT2; ++i) {
+          const __nv_bfloat16* vp = sVt + (i * 8 + gq) * VS + c0 + k2 * 16 + 2 * tq;
+          mma_bf16_16816(o[i], ap, *(const uint32_t*)vp, *(const uint32_t*)(vp + 8));
+        }
+      }
+    }
+  }
+  if (!warp_active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* out = (__nv_bfloat16*)a.out;
+#pragma unroll
+  for (int i = 0; i < NT2; ++i) {
+    const int d = i * 8 + 2 * tq;
+    if (d < D) {
+      if (ok0) *(uint32_t*)(out + (int64_t)(n0 + r0) * C + h * D + d) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
+      if (ok1) *(uint32_t*)(out + (int64_t)(n0 + r1) * C + h * D + d) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+    }
+  }
+}
+
+template <int D>
+static int launch_attention_mma(const ghn3_attention_args* a, cudaStream_t stream) {
+  constexpr int DK = (D + 15) / 16 * 16, DN = (D + 7) / 8 * 8;
+  const int smem = (kMmaKT * (DK + 8) + DN * (kMmaKT + 8)) * 2 + a->lut_size * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    GHN3_CUDA(cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) {
+    set_error("ghn3_attention: lut too large for shared memory");
+    return GHN3_ERR_UNSUPPORTED;
+  }
+  const dim3 grid((unsigned)ceil_div(a->max_nodes, kMmaQT), (unsigned)a->heads, (unsigned)a->n_graphs);
+  attention_mma_kernel<D><<<grid, 128, smem, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("attention_mma_kernel");
+  return GHN3_OK;
+}
+
 template <typename T, int D>
 static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
   const int smem = (2 * kAttnKT * (D + 1) + kAttnQT * kAttnKT + a->lut_size) * (int)sizeof(float);
@@ -269,7 +501,7 @@ int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   const int D = a->hid / a->heads;
   const bool bf = a->dtype == GHN3_BF16;
 #define GHN3_ATTN_CASE(DV)                                                     \
-  if (D == DV) return bf ? launch_attention<__nv_bfloat16, DV>(a, stream) : launch_attention<float, DV>(a, stream);
+  if (D == DV) return bf ? launch_attention_mma<DV>(a, stream) : launch_attention<float, DV>(a, stream);
   GHN3_ATTN_CASE(4)
   GHN3_ATTN_CASE(8)
   GHN3_ATTN_CASE(16)
