@@ -13,6 +13,8 @@ namespace ghn3 {
 __global__ void __launch_bounds__(256) layernorm_kernel(const ghn3_layernorm_args a) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= a.rows) return;
   const int C = a.hid, C4 = C >> 2;
   const float4* x4 = (const float4*)(a.x + (int64_t)row * C);
@@ -104,7 +106,9 @@ __global__ void __launch_bounds__(kAttnWarps * 32, (D <= 24) ? 2 : 1) attention_
   const float scale_log2 = rsqrtf((float)D) * 1.44269504088896340736f;
   constexpr float kLog2e = 1.44269504088896340736f;
 
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = __ldg(a.lut + (int64_t)h * a.lut_size + i) * kLog2e;
+  pdl_wait();
 
   float q[kAttnQPerWarp][D], acc[kAttnQPerWarp][D], m[kAttnQPerWarp], l[kAttnQPerWarp];
   int qi[kAttnQPerWarp];
@@ -305,6 +309,9 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention
     for (int idx = threadIdx.x; idx < (DN - D) * VS; idx += blockDim.x) sVt[D * VS + idx] = __float2bfloat16_rn(0.f);
   }
 
+  pdl_launch_dependents();
+  pdl_wait();       // everything above only touched the LUT and shared memory
+
   // Q fragments of this warp's 16 queries, pre-scaled by d^-1/2 * log2(e)
   const int r0 = q0 + warp * 16 + gq, r1 = r0 + 8;
   const bool ok0 = r0 < n, ok1 = r1 < n;
@@ -470,7 +477,7 @@ static int launch_attention_mma(const ghn3_attention_args* a, cudaStream_t strea
     return GHN3_ERR_UNSUPPORTED;
   }
   const dim3 grid((unsigned)ceil_div(a->max_nodes, kMmaQT), (unsigned)a->heads, (unsigned)a->n_graphs);
-  attention_mma_kernel<D><<<grid, 128, smem, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(attention_mma_kernel<D>, grid, dim3(128), (size_t)smem, stream, *a));
   GHN3_LAUNCH_CHECK("attention_mma_kernel");
   return GHN3_OK;
 }
@@ -488,7 +495,7 @@ static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
     return GHN3_ERR_UNSUPPORTED;
   }
   const dim3 grid((unsigned)ceil_div(a->max_nodes, kAttnQT), (unsigned)a->heads, (unsigned)a->n_graphs);
-  attention_kernel<T, D><<<grid, kAttnWarps * 32, smem, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(attention_kernel<T, D>, grid, dim3(kAttnWarps * 32), (size_t)smem, stream, *a));
   GHN3_LAUNCH_CHECK("attention_kernel");
   return GHN3_OK;
 }
@@ -517,7 +524,7 @@ int layernorm_impl(const ghn3_layernorm_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a->hid > 0 && a->hid % 4 == 0 && a->hid <= 1024, "ghn3_layernorm: hid must be a multiple of 4, <= 1024");
   GHN3_REQUIRE(a->out_dtype >= GHN3_BF16 && a->out_dtype <= GHN3_F32, "ghn3_layernorm: bad out_dtype");
   if (a->rows <= 0) return GHN3_OK;
-  layernorm_kernel<<<(unsigned)ceil_div(a->rows, 8), 256, 0, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(layernorm_kernel, dim3((unsigned)ceil_div(a->rows, 8)), dim3(256), 0, stream, *a));
   GHN3_LAUNCH_CHECK("layernorm_kernel");
   return GHN3_OK;
 }

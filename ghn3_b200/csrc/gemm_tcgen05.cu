@@ -226,11 +226,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
       const int a_row = p.a_row0 + mt * kBlockM;
       const int b_row = p.b_row0 + nt * BN;
-      for (int i = 0; i < num_kb; ++i) {
+      // B holds weights (never written during a step): its first ring-full of tiles is requested BEFORE waiting
+      // for the predecessor kernel, so the HBM latency of the weights hides behind the predecessor's tail.
+      const int pre = min(num_kb, kStages);
+      for (int i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(full_bar + 8 * i, A_BYTES + B_BYTES);
+        tma_load_2d(sB + i * B_BYTES, &tma_b, full_bar + 8 * i, (kb0 + i) * BK, b_row);
+      }
+      pdl_wait();
+      for (int i = 0; i < pre; ++i) tma_load_2d(sA + i * A_BYTES, &tma_a, full_bar + 8 * i, (kb0 + i) * BK, a_row);
+      for (int i = pre; i < num_kb; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -276,6 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const bool row_ok = m < p.m;
     const bool atomic = args.k_splits > 1 && args.tiles == nullptr;
     const bool use_bias = p.bias_off >= 0 && first_split;
+    pdl_wait();                                  // the epilogue reads / writes buffers of earlier kernels
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const int64_t d_row = p.d_off + (int64_t)m * p.ldd;
@@ -440,7 +451,8 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmK
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  gemm_tcgen05_kernel<kTf32, kX3, BN, kStages><<<grid, gemm_threads<kX3>(), smem, stream>>>(ma, mb, ka);
+  GHN3_CUDA(launch_pdl(gemm_tcgen05_kernel<kTf32, kX3, BN, kStages>, grid, dim3(gemm_threads<kX3>()), (size_t)smem,
+                       stream, ma, mb, ka));
   GHN3_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return GHN3_OK;
 }

@@ -13,6 +13,7 @@ ap.add_argument('--steps', type=int, default=1)
 ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--cfg', default='ghn3xlm16')
 ap.add_argument('--archs', default=','.join(bench.WORKLOAD_ARCHS))
+ap.add_argument('--stage', default='', help='profile only this stage of the step (e.g. dec_conv2, scatter, graphormer)')
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 cfg = CONFIGS[args.cfg]
@@ -28,9 +29,24 @@ with torch.no_grad():
     for _ in range(args.warmup):
         ghn(models, batch)
     torch.cuda.synchronize()
-    torch.cuda.profiler.start()
-    for _ in range(args.steps):
-        ghn(models, batch)
-    torch.cuda.synchronize()
-    torch.cuda.profiler.stop()
+    if args.stage:
+        order = ['start', 'node_features', 'graphormer', 'dec_fc', 'dec_conv0', 'dec_conv2', 'heads_1d', 'scatter']
+        prev = order[order.index(args.stage) - 1]
+
+        class Hook(list):
+            def append(self, item):
+                if item[0] == prev:
+                    torch.cuda.synchronize(); torch.cuda.profiler.start()
+                if item[0] == args.stage:
+                    torch.cuda.synchronize(); torch.cuda.profiler.stop()
+        ghn._profile = Hook()
+        for _ in range(args.steps):
+            ghn(models, batch)
+        torch.cuda.synchronize()
+    else:
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            ghn(models, batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 print('profiled', args.steps, 'steps')
