@@ -100,7 +100,7 @@ assert C.sizeof(ScatterDesc) == 88 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
-           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32']
+           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace']
 
 _lib = None
 

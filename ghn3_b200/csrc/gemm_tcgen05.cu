@@ -131,10 +131,29 @@ struct GemmKernelArgs {
   int32_t act;
   int32_t accumulate;
   int32_t k_splits;      // single-problem mode: blockIdx.z = K split; partial sums are added atomically (fp32)
+  long long* trace;      // optional [n_ctas][8] globaltimer stamps (bring-up / profiling aid, normally NULL)
 };
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GHN3_TRACE(slot)                                                                         \
+  do {                                                                                           \
+    if (args.trace != nullptr) {                                                                 \
+      const int cta__ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);          \
+      if (cta__ < 4096) args.trace[cta__ * 8 + (slot)] = gtimer();                                \
+    }                                                                                            \
+  } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&t;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -184,6 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GHN3_TRACE(0);
 
   ghn3_gemm_problem p;
   int mt, nt;
@@ -225,6 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) GHN3_TRACE(1);
 
   pdl_launch_dependents();
   if (warp == 0) {
@@ -255,6 +276,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait((kX3 ? split_bar : full_bar) + 8 * s, ph);
+        if (i == 0) GHN3_TRACE(4);
         tcgen05_fence_after();
         const uint64_t da = make_smem_desc(sA + s * A_BYTES);
         const uint64_t db = make_smem_desc(sB + s * B_BYTES);
@@ -277,19 +299,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tcgen05_commit(empty_bar + 8 * s);       // slot reusable once these MMAs have read it
       }
       tcgen05_commit(tmem_full_bar);             // accumulator complete
+      GHN3_TRACE(5);
     }
   } else if (warp < 6) {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // Epilogue. Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32): tcgen05.ld gives every thread one
+    // accumulator ROW (32 columns). Writing that straight out would scatter 16-byte pieces over 32 rows per store
+    // instruction (measured: ~half of a small GEMM's run time), so each 32x32 block is transposed through shared
+    // memory (the operand ring is idle once the accumulator is complete) and stored with lanes along columns:
+    // one contiguous 128-byte (fp32) or 64-byte (bf16) row segment per warp instruction.
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = mt * kBlockM + row;
-    const bool row_ok = m < p.m;
+    const int m_base = mt * kBlockM + q * 32;
+    const int rows_valid = min(32, p.m - m_base);
     const bool atomic = args.k_splits > 1 && args.tiles == nullptr;
     const bool use_bias = p.bias_off >= 0 && first_split;
+    float* stage = (float*)(smem_raw + (sA - smem_u32(smem_raw)) + q * 4736);   // >= 32*144 B and 32*33*4 B, 16B aligned
     pdl_wait();                                  // the epilogue reads / writes buffers of earlier kernels
     mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 64) GHN3_TRACE(6);
     tcgen05_fence_after();
-    const int64_t d_row = p.d_off + (int64_t)m * p.ldd;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int n0 = nt * BN + c0;
@@ -297,64 +324,121 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
-      if (row_ok) {
-        const int ncols = min(32, p.n - n0);
-        float v[32];
+      if (threadIdx.x == 64 && c0 == 0) GHN3_TRACE(2);
+      if (rows_valid <= 0) continue;             // warp-uniform
+      const bool bf16_out = args.out_dtype == GHN3_BF16;
+      const bool tf = args.out_dtype == GHN3_TF32;
+      const int eb_out = bf16_out ? 2 : 4;
+      // fast path: the whole 32-column chunk is inside the problem and every 16-byte piece is aligned
+      const bool vec_ok = (n0 + 32 <= p.n) && (((p.ldd * eb_out) & 15) == 0) &&
+                          ((((p.d_off + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
+      // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
+      const float b_lane = (use_bias && n0 + lane < p.n) ? __ldg(args.bias + p.bias_off + n0 + lane) : 0.f;
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (use_bias && j < ncols) x += __ldg(args.bias + p.bias_off + n0 + j);
-          v[j] = apply_act(x, args.act);
+      for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj);
+      // the activation is selected ONCE per chunk (a per-element runtime test gets if-converted and the erf
+      // polynomial would issue, predicated off, for every element of every GEMM)
+      if (!args.accumulate) {
+        if (args.act == GHN3_ACT_GELU) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = 0.5f * v[jj] * (1.f + erff(v[jj] * 0.70710678118654752440f));
+        } else if (args.act == GHN3_ACT_RELU) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.f);
         }
-        if (args.out_dtype == GHN3_BF16) {
-          __nv_bfloat16* dptr = (__nv_bfloat16*)args.d + d_row + n0;
-          if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
+        if (tf) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j + 0], v[j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
-              *(uint4*)(dptr + j) = pk;
-            }
-          } else {
+          for (int jj = 0; jj < 32; ++jj) v[jj] = round_tf32(v[jj]);
+        }
+      }
+      if (vec_ok) {
+        uint8_t* stage_b = (uint8_t*)stage;      // per-warp block of 32 rows x (row bytes + 16)
+        if (bf16_out) {
+          constexpr int RS = 64 + 16;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) dptr[j] = __float2bfloat16_rn(v[j]);
+          for (int c = 0; c < 4; ++c) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *(uint4*)(stage_b + lane * RS + 16 * c) = pk;
+          }
+          __syncwarp();
+          const int seg = lane & 3, rsub = lane >> 2;          // 4 lanes x 16 B per row, 8 rows per instruction
+          __nv_bfloat16* dbase = (__nv_bfloat16*)args.d + p.d_off + n0 + seg * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + rsub;
+            if (row < rows_valid)
+              *(uint4*)(dbase + (int64_t)(m_base + row) * p.ldd) = *(const uint4*)(stage_b + row * RS + 16 * seg);
           }
         } else {
-          float* dptr = (float*)args.d + d_row + n0;
-          const bool tf = args.out_dtype == GHN3_TF32;
+          constexpr int RS = 128 + 16;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *(float4*)(stage_b + lane * RS + 16 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          const int seg = lane & 7, rsub = lane >> 3;          // 8 lanes x 16 B per row, 4 rows per instruction
+          float* dbase = (float*)args.d + p.d_off + n0 + seg * 4;
           if (atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(dptr + j, v[j]);
-          } else if (ncols == 32 && ((((uintptr_t)dptr) & 15) == 0)) {
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              if (row < rows_valid)
+                atomicAdd((float4*)(dbase + (int64_t)(m_base + row) * p.ldd), *(const float4*)(stage_b + row * RS + 16 * seg));
+            }
+          } else if (args.accumulate) {
+            float4 old[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (args.accumulate) {
-                const float4 old = *(const float4*)(dptr + j);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              if (row < rows_valid) old[it] = *(const float4*)(dbase + (int64_t)(m_base + row) * p.ldd);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              if (row < rows_valid) {
+                const float4 t = *(const float4*)(stage_b + row * RS + 16 * seg);
+                float4 o = make_float4(old[it].x + t.x, old[it].y + t.y, old[it].z + t.z, old[it].w + t.w);
+                if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *(float4*)(dbase + (int64_t)(m_base + row) * p.ldd) = o;
               }
-              if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              *(float4*)(dptr + j) = o;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols) {
-                float o = v[j];
-                if (args.accumulate) o += dptr[j];
-                dptr[j] = tf ? round_tf32(o) : o;
-              }
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rsub;
+              if (row < rows_valid)
+                *(float4*)(dbase + (int64_t)(m_base + row) * p.ldd) = *(const float4*)(stage_b + row * RS + 16 * seg);
+            }
+          }
+        }
+      } else {
+        // general path (ragged column edge or unaligned output): lanes along columns, one element each
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) stage[lane * 33 + jj] = v[jj];
+        __syncwarp();
+        const int col = n0 + lane;
+        if (col < p.n) {
+          for (int rr = 0; rr < rows_valid; ++rr) {
+            const float t = stage[rr * 33 + lane];
+            const int64_t off = p.d_off + (int64_t)(m_base + rr) * p.ldd + col;
+            if (bf16_out) {
+              ((__nv_bfloat16*)args.d)[off] = __float2bfloat16_rn(t);
+            } else if (atomic) {
+              atomicAdd((float*)args.d + off, t);
+            } else if (args.accumulate) {
+              const float o = ((float*)args.d)[off] + t;
+              ((float*)args.d)[off] = tf ? round_tf32(o) : o;
+            } else {
+              ((float*)args.d)[off] = t;
             }
           }
         }
       }
+      __syncwarp();
     }
+    if (threadIdx.x == 64) GHN3_TRACE(3);
   } else {
     // kX3 only: warps 6..9 split each landed fp32 tile into hi (in place) and lo (second buffer)
     if constexpr (kX3) {
@@ -389,6 +473,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GHN3_TRACE(7);
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
@@ -457,6 +542,9 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmK
   return GHN3_OK;
 }
 
+static long long* g_gemm_trace = nullptr;
+void set_gemm_trace(long long* p) { g_gemm_trace = p; }
+
 int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_gemm: null args");
   GHN3_REQUIRE(a->in_dtype == GHN3_BF16 || a->in_dtype == GHN3_TF32, "ghn3_gemm: in_dtype must be BF16 or TF32");
@@ -516,22 +604,29 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.act = a->act;
   ka.accumulate = a->accumulate;
   ka.k_splits = splits;
+  ka.trace = g_gemm_trace;
 
   if (x3) {
     if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);
     return launch_gemm<true, true, 128, 3>(ma, mb, ka, grid, stream);
   }
   if (tf32) {
-    if (bn == 64) return launch_gemm<true, false, 64, 6>(ma, mb, ka, grid, stream);
+    if (bn == 64) return launch_gemm<true, false, 64, 4>(ma, mb, ka, grid, stream);
     if (bn == 128) return launch_gemm<true, false, 128, 3>(ma, mb, ka, grid, stream);
     return launch_gemm<true, false, 256, 4>(ma, mb, ka, grid, stream);
   }
-  if (bn == 64) return launch_gemm<false, false, 64, 6>(ma, mb, ka, grid, stream);
+  if (bn == 64) return launch_gemm<false, false, 64, 4>(ma, mb, ka, grid, stream);
   if (bn == 128) return launch_gemm<false, false, 128, 3>(ma, mb, ka, grid, stream);
   return launch_gemm<false, false, 256, 4>(ma, mb, ka, grid, stream);
 }
 
 }  // namespace ghn3
+
+// Bring-up aid: device buffer of [4096][8] int64 globaltimer stamps filled by subsequent GEMM launches (NULL = off).
+extern "C" int ghn3_debug_gemm_trace(void* device_buffer) {
+  ghn3::set_gemm_trace((long long*)device_buffer);
+  return GHN3_OK;
+}
 
 extern "C" int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream) {
   return ghn3::gemm_impl(args, (cudaStream_t)stream);

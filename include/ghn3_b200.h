@@ -189,6 +189,9 @@ typedef struct {
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);
+/* Profiling aid: subsequent ghn3_gemm launches write per-CTA phase timestamps (globaltimer) into a device buffer of
+ * int64[4096][8]; pass NULL to switch it off. */
+int ghn3_debug_gemm_trace(void* device_buffer);
 
 /* Small strided fp32 GEMM on CUDA cores for shapes that are too small or too oddly laid out for TMA:
  *   D[m][n] = act(bias[n] + sum_k f(A[m*sam + k*sak]) * B[n*sbn + k*sbk]),  f = relu if relu_a else identity.
