@@ -56,6 +56,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -132,6 +138,10 @@ struct GemmKernelArgs {
   int32_t accumulate;
   int32_t k_splits;      // single-problem mode: blockIdx.z = K split; partial sums are added atomically (fp32)
   long long* trace;      // optional [n_ctas][8] globaltimer stamps (bring-up / profiling aid, normally NULL)
+  // "grouped rows" view of B (decoder conv.2 column sub-blocks): B is seen as [outer][b_stride][K] and an N tile is
+  // the 3-D TMA box {K chunk, b_group inner rows, b_outer outer rows}: tile column c <-> B row (c / b_group) *
+  // b_stride + c % b_group, i.e. the compact o' x i' column order of the prediction buffer.
+  int32_t b_group, b_stride, b_outer;
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -251,13 +261,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       const int a_row = p.a_row0 + mt * kBlockM;
-      const int b_row = p.b_row0 + nt * BN;
+      const int b_row = p.b_row0 + nt * (args.b_group > 0 ? args.b_outer : BN);
+      const uint32_t b_bytes = args.b_group > 0 ? (uint32_t)(args.b_group * args.b_outer * kRowBytes) : B_BYTES;
+      auto load_b = [&](uint32_t dst, uint32_t bar, int kcoord) {
+        if (args.b_group > 0) tma_load_3d(dst, &tma_b, bar, kcoord, 0, b_row);
+        else tma_load_2d(dst, &tma_b, bar, kcoord, b_row);
+      };
       // B holds weights (never written during a step): its first ring-full of tiles is requested BEFORE waiting
       // for the predecessor kernel, so the HBM latency of the weights hides behind the predecessor's tail.
       const int pre = min(num_kb, kStages);
       for (int i = 0; i < pre; ++i) {
-        mbar_arrive_expect_tx(full_bar + 8 * i, A_BYTES + B_BYTES);
-        tma_load_2d(sB + i * B_BYTES, &tma_b, full_bar + 8 * i, (kb0 + i) * BK, b_row);
+        mbar_arrive_expect_tx(full_bar + 8 * i, A_BYTES + b_bytes);
+        load_b(sB + i * B_BYTES, full_bar + 8 * i, (kb0 + i) * BK);
       }
       pdl_wait();
       for (int i = 0; i < pre; ++i) tma_load_2d(sA + i * A_BYTES, &tma_a, full_bar + 8 * i, (kb0 + i) * BK, a_row);
@@ -265,9 +280,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + B_BYTES);
+        mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + b_bytes);
         tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, (kb0 + i) * BK, a_row);
-        tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, (kb0 + i) * BK, b_row);
+        load_b(sB + s * B_BYTES, full_bar + 8 * s, (kb0 + i) * BK);
       }
     }
   } else if (warp == 1) {
@@ -317,10 +332,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 64) GHN3_TRACE(6);
     tcgen05_fence_after();
+    const int tile_n = args.b_group > 0 ? args.b_group * args.b_outer : BN;   // valid columns of a full tile
+    const int n_end = min(p.n, (nt + 1) * tile_n);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      const int n0 = nt * BN + c0;
-      if (n0 >= p.n) break;                      // warp-uniform
+      const int n0 = nt * tile_n + c0;
+      if (n0 >= n_end) break;                    // warp-uniform
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
@@ -330,10 +347,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const bool tf = args.out_dtype == GHN3_TF32;
       const int eb_out = bf16_out ? 2 : 4;
       // fast path: the whole 32-column chunk is inside the problem and every 16-byte piece is aligned
-      const bool vec_ok = (n0 + 32 <= p.n) && (((p.ldd * eb_out) & 15) == 0) &&
+      const bool vec_ok = (n0 + 32 <= n_end) && (((p.ldd * eb_out) & 15) == 0) &&
                           ((((p.d_off + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
       // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
-      const float b_lane = (use_bias && n0 + lane < p.n) ? __ldg(args.bias + p.bias_off + n0 + lane) : 0.f;
+      float b_lane = 0.f;
+      if (use_bias && n0 + lane < n_end) {
+        const int c = n0 + lane;
+        const int bidx = args.b_group > 0 ? (c / args.b_group) * args.b_stride + c % args.b_group : c;
+        b_lane = __ldg(args.bias + p.bias_off + bidx);
+      }
       float v[32];
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj);
@@ -419,7 +441,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int jj = 0; jj < 32; ++jj) stage[lane * 33 + jj] = v[jj];
         __syncwarp();
         const int col = n0 + lane;
-        if (col < p.n) {
+        if (col < n_end) {
           for (int rr = 0; rr < rows_valid; ++rr) {
             const float t = stage[rr * 33 + lane];
             const int64_t off = p.d_off + (int64_t)(m_base + rr) * p.ldd + col;
@@ -500,6 +522,29 @@ static EncodeTiledFn get_encode_fn() {
     fn = (EncodeTiledFn)ptr;
   }
   return fn;
+}
+
+static int make_grouped_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, bool tf32,
+                            int group, int stride, int outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return GHN3_ERR_CUDA;
+  }
+  const int eb = tf32 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)stride, (cuuint64_t)(rows / stride)};
+  cuuint64_t strides[2] = {(cuuint64_t)(ld * eb), (cuuint64_t)(ld * eb * stride)};
+  cuuint32_t box[3] = {(cuuint32_t)(kRowBytes / eb), (cuuint32_t)group, (cuuint32_t)outer};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%lld group=%d stride=%d outer=%d)", (int)r,
+              (long long)rows, group, stride, outer);
+    return GHN3_ERR_CUDA;
+  }
+  return GHN3_OK;
 }
 
 static int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, bool tf32,
@@ -590,7 +635,16 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, a->a, a->a_rows, a->k, a->lda, tf32, kBlockM);
   if (rc != GHN3_OK) return rc;
-  rc = make_operand_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, bn);
+  int b_outer = 0;
+  if (a->b_group > 0) {
+    GHN3_REQUIRE(a->problems != nullptr, "ghn3_gemm: b_group needs a grouped launch");
+    GHN3_REQUIRE(a->b_group <= bn && a->b_group_stride >= a->b_group && a->b_rows % a->b_group_stride == 0,
+                 "ghn3_gemm: bad b_group / b_group_stride (%d / %d)", a->b_group, a->b_group_stride);
+    b_outer = (int)std::min<int64_t>(bn / a->b_group, a->b_rows / a->b_group_stride);
+    rc = make_grouped_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, a->b_group, a->b_group_stride, b_outer);
+  } else {
+    rc = make_operand_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, bn);
+  }
   if (rc != GHN3_OK) return rc;
 
   GemmKernelArgs ka;
@@ -605,6 +659,9 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.accumulate = a->accumulate;
   ka.k_splits = splits;
   ka.trace = g_gemm_trace;
+  ka.b_group = a->b_group;
+  ka.b_stride = a->b_group_stride;
+  ka.b_outer = b_outer;
 
   if (x3) {
     if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);

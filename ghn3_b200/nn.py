@@ -329,8 +329,9 @@ class GHN3(GHN):
         blob.add('dst_row', bp.dst_row)
         blob.add('fc_problems', bp.fc_problems.view(np.uint8))
         blob.add('fc_tiles', bp.fc_tiles)
-        blob.add('c2_problems', bp.c2_problems.view(np.uint8))
-        blob.add('c2_tiles', bp.c2_tiles)
+        for g_, pr, tl in bp.c2_launches:
+            blob.add('c2_%d_problems' % g_, pr.view(np.uint8))
+            blob.add('c2_%d_tiles' % g_, tl)
         st = blob.upload(device)
         st['device'] = device
         st['bytes'] = blob.size
@@ -393,8 +394,10 @@ class GHN3(GHN):
             h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=act, x3=x3)
             mark('dec_conv0')
             wout = torch.empty(bp.wout_elems, dtype=torch.float32, device=device)
-            ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
-                     problems=st['c2_problems'], tiles=st['c2_tiles'], x3=x3)
+            for g_, _, _ in bp.c2_launches:
+                ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
+                         problems=st['c2_%d_problems' % g_], tiles=st['c2_%d_tiles' % g_], x3=x3,
+                         b_group=g_, b_group_stride=ms1 if g_ else 0, block_n=128)
             mark('dec_conv2')
             bufs[SRC_WOUT] = wout
             if bp.clsw_elems:

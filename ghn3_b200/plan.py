@@ -297,6 +297,7 @@ class BatchPlan:
         self.n_conv = len(conv)
         dst_row = np.full(self.total_nodes, -1, dtype=np.int32)         # row of each node in the decoder inputs
         fc_probs, c2_probs = [], []
+        c2_grouped = {}                  # i' -> problems reading the compact o' x i' column set through a 3-D TMA box
         self.conv_rows = []              # (row0 in h0/h1, P, kwp, khp) per conv node
         self.seg_of = []                 # wout element offset of each conv node's first row, ld
         row = 0
@@ -341,6 +342,8 @@ class BatchPlan:
             seg_rows = row - seg_row0
             if ii == ms1:
                 c2_probs.append((seg_row0, 0, seg_rows, o * ms1, seg_base, ld, 0))
+            elif ii <= 128:
+                c2_grouped.setdefault(ii, []).append((seg_row0, 0, seg_rows, o * ii, seg_base, ld, 0))
             else:
                 for a in range(o):
                     c2_probs.append((seg_row0, a * ms1, seg_rows, ii, seg_base + a * ii, ld, a * ms1))
@@ -358,6 +361,15 @@ class BatchPlan:
             pr = self.c2_problems
             wrow = pr['b_row0'][self.c2_tiles[:, 0]].astype(np.int64) + self.c2_tiles[:, 2].astype(np.int64) * 128
             self.c2_tiles = self.c2_tiles[np.lexsort((self.c2_tiles[:, 1], wrow))]
+        # conv.2 launches: (b_group, problems, tiles); b_group 0 = dense rows, g > 0 = compact columns via 3-D boxes
+        self.c2_launches = []
+        if len(self.c2_problems):
+            self.c2_launches.append((0, self.c2_problems, self.c2_tiles))
+        for g_, probs in sorted(c2_grouped.items()):
+            pr = np.array(probs, dtype=PROBLEM_DT)
+            tl = tiles_for(pr, block_n=(128 // g_) * g_)
+            tl = tl[np.lexsort((tl[:, 1], tl[:, 2]))]
+            self.c2_launches.append((g_, pr, tl))
 
         # ---- 1-D nodes (decoder_1d), classification-bias nodes last ----
         one_d.sort(key=lambda bt: (bt[1].kind == KIND_CLS_B, bt[0], bt[1].node))

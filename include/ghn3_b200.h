@@ -186,6 +186,13 @@ typedef struct {
   int32_t block_n;           /* 0 = auto; 64/128/256 */
   int32_t k_splits;          /* single-problem launches: 0 = auto, >1 splits K over blockIdx.z (needs accumulate) */
   int32_t tf32_x3;           /* in_dtype TF32 only: 3-term error-compensated tf32 (hi/lo split in shared memory) */
+  /* Grouped launches only. b_group = g > 0 views B as [b_rows / b_group_stride][b_group_stride][K] and makes the
+   * problem's columns the COMPACT set {outer * g + inner : inner < g}: column c reads B row
+   * (b_row0 + c / g) * b_group_stride + c % g (b_row0 counts OUTER rows; bias is indexed the same way).
+   * An N tile holds floor(block_n / g) * g columns. Used for the decoder's o' x i' sub-blocks with i' < max_shape[1]
+   * (reference ghn3/nn.py:750,760: x[:, :o, :i]). */
+  int32_t b_group;
+  int32_t b_group_stride;
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);

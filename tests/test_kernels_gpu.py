@@ -390,3 +390,32 @@ def test_scatter_bilinear():
     _run_scatter([dict(dst=dst, src_ptr=src.data_ptr(), t1=i, t2=32, t3=32, so=o, si=i, ld=o * i, ca=i, kh_src=16,
                        kw_src=16, mode=3, scale=1.0)])
     assert _rel(dst, ref) < 1e-5
+
+
+@pytest.mark.parametrize('g', [1, 4, 40, 64, 128])
+def test_gemm_grouped_rows_3d_box(g):
+    """b_group: compact o' x i' column sub-blocks of the decoder conv.2 weight through a 3-D TMA box."""
+    torch.manual_seed(g)
+    ms, K, o = 384, 256, 96
+    a = torch.randn(70, K, device=DEV).bfloat16()
+    w = (torch.randn(ms * ms, K, device=DEV) / 16).bfloat16()
+    bias = torch.randn(ms * ms, device=DEV)
+    n = o * g
+    probs = np.zeros(2, dtype=[('a_row0', 'i4'), ('b_row0', 'i4'), ('m', 'i4'), ('n', 'i4'), ('d_off', 'i8'),
+                               ('ldd', 'i4'), ('bias_off', 'i4')])
+    probs[0] = (0, 0, 50, n, 0, n, 0)
+    probs[1] = (50, 0, 20, n, 50 * n, n, 0)
+    tile_n = (128 // g) * g
+    tiles = []
+    for p, m in enumerate([50, 20]):
+        for nt in range((n + tile_n - 1) // tile_n):
+            tiles.append((p, 0, nt, 0))
+    tiles = torch.tensor(tiles, dtype=torch.int32, device=DEV)
+    probs_dev = torch.from_numpy(probs.view(np.uint8).copy()).to(DEV)
+    out = torch.zeros(70, n, device=DEV)
+    ops.gemm(a, w, bias=bias, in_dtype=ops.BF16, out=out, out_dtype=ops.F32, problems=probs_dev, tiles=tiles,
+             b_group=g, b_group_stride=ms, block_n=128)
+    torch.cuda.synchronize()
+    rows = (torch.arange(o, device=DEV)[:, None] * ms + torch.arange(g, device=DEV)[None, :]).reshape(-1)
+    ref = (a.double() @ w[rows].double().t() + bias[rows].double()).float()
+    assert _rel(out, ref) < 2e-5
