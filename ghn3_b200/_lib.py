@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'libghn3_b200.so')
 
 BF16, TF32, F32 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-SCATTER_CHUNK = 4096
+SCATTER_CHUNK = 8192
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -85,18 +85,39 @@ class GraphormerArgs(C.Structure):
 class ScatterDesc(C.Structure):
     _fields_ = [('dst', vp), ('src', vp), ('numel', i64), ('chunk0', i64), ('t1', i32), ('t2', i32), ('t3', i32),
                 ('so', i32), ('si', i32), ('ld', i32), ('ca', i32), ('ra', i32), ('kh_src', i32), ('kw_src', i32),
-                ('cy', i32), ('cx', i32), ('scale', f32), ('mode', i32)]
+                ('cy', i32), ('cx', i32), ('scale', f32), ('mode', i32)] + \
+               [(n_, C.c_uint32) for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')]
+
+
+def fastdiv(d):
+    """(mul, shift) with n // d == (n * mul >> 32) >> shift for all 0 <= n < 2**31 (mul == 0 encodes d == 1)."""
+    d = int(d)
+    if d <= 1:
+        return 0, 0
+    s = (d - 1).bit_length()
+    mul = -(-(1 << (31 + s)) // d)
+    assert mul < (1 << 32)
+    return mul, s - 1
+
+
+def fill_fastdiv(desc):
+    """Fills the m_*/s_* fields of a ScatterDesc (ctypes) from its t1, t2, t3, so, si."""
+    for f in ('t1', 't2', 't3', 'so', 'si'):
+        m, s = fastdiv(getattr(desc, f))
+        setattr(desc, 'm_' + f, m)
+        setattr(desc, 's_' + f, s)
+    return desc
 
 
 class ScatterArgs(C.Structure):
-    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64)]
+    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp)]
 
 
 class SumsqArgs(C.Structure):
     _fields_ = [('ptrs', vp), ('numels', vp), ('n', i32), ('out', vp)]
 
 
-assert C.sizeof(ScatterDesc) == 88 and C.sizeof(GemmProblem) == 32
+assert C.sizeof(ScatterDesc) == 128 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',

@@ -327,6 +327,7 @@ class GHN3(GHN):
         blob = ops.HostBlob()
         blob.add('shape_idx', bp.shape_idx.astype(np.int32))
         blob.add('dst_row', bp.dst_row)
+        blob.add('chunk_desc', bp.chunk_desc)
         blob.add('fc_problems', bp.fc_problems.view(np.uint8))
         blob.add('fc_tiles', bp.fc_tiles)
         for g_, pr, tl in bp.c2_launches:
@@ -425,12 +426,12 @@ class GHN3(GHN):
 
         mark('heads_1d')
         # ---- tile / normalise / scatter into the target parameters ----
-        self._scatter(bp, bufs, device)
+        self._scatter(bp, bufs, device, st['chunk_desc'])
         mark('scatter')
         self._last_buffers = bufs if self.debug_level else None
         return emb
 
-    def _scatter(self, bp, bufs, device):
+    def _scatter(self, bp, bufs, device, chunk_desc=None):
         n = len(bp.desc_static)
         if n == 0:
             return
@@ -454,7 +455,7 @@ class GHN3(GHN):
             desc['mode'] = np.where(desc['mode'] == 3, 3, 0)
             desc['scale'] = 1.0
         dev_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(device)
-        ops.scatter(dev_desc, n, bp.n_chunks)
+        ops.scatter(dev_desc, n, bp.n_chunks, chunk_desc)
         self._desc_keepalive = (dev_desc, bufs)
 
 

@@ -229,8 +229,8 @@ def attention(qkv, pack, lut, hid, heads, dtype=BF16, out=None):
     return out
 
 
-def scatter(descs_dev, n_descs, n_chunks):
-    a = L.ScatterArgs(descs=L.ptr(descs_dev), n_descs=n_descs, n_chunks=n_chunks)
+def scatter(descs_dev, n_descs, n_chunks, chunk_desc=None):
+    a = L.ScatterArgs(descs=L.ptr(descs_dev), n_descs=n_descs, n_chunks=n_chunks, chunk_desc=L.ptr(chunk_desc))
     L.call('scatter', a, L.current_stream())
 
 

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ._lib import fastdiv
 from .weights import channel_bins, spatial_bins
 
 try:
@@ -250,9 +251,10 @@ PROBLEM_DT = np.dtype([('a_row0', 'i4'), ('b_row0', 'i4'), ('m', 'i4'), ('n', 'i
                        ('bias_off', 'i4')])
 DESC_DT = np.dtype([('dst', 'u8'), ('src', 'u8'), ('numel', 'i8'), ('chunk0', 'i8'), ('t1', 'i4'), ('t2', 'i4'),
                     ('t3', 'i4'), ('so', 'i4'), ('si', 'i4'), ('ld', 'i4'), ('ca', 'i4'), ('ra', 'i4'),
-                    ('kh_src', 'i4'), ('kw_src', 'i4'), ('cy', 'i4'), ('cx', 'i4'), ('scale', 'f4'), ('mode', 'i4')])
-assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 88
-SCATTER_CHUNK = 4096
+                    ('kh_src', 'i4'), ('kw_src', 'i4'), ('cy', 'i4'), ('cx', 'i4'), ('scale', 'f4'), ('mode', 'i4')] +
+                   [(n_, 'u4') for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')])
+assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 128
+SCATTER_CHUNK = 8192
 SRC_WOUT, SRC_D1, SRC_CLSW, SRC_CLSB, SRC_TOK = 0, 1, 2, 3, 4      # which device buffer a descriptor reads
 
 
@@ -395,6 +397,10 @@ class BatchPlan:
             for k_, v in dict(t1=1, t2=1, t3=1, so=1, si=1, ld=0, ca=0, ra=0, kh_src=1, kw_src=1, cy=0, cx=0,
                               scale=1.0, mode=0).items():
                 d[k_] = f.get(k_, v)
+            for f_ in ('t1', 't2', 't3', 'so', 'si'):
+                d['m_' + f_], d['s_' + f_] = fastdiv(int(d[f_]))
+            if numel >= (1 << 31):
+                raise NotImplementedError('target tensors with 2^31 or more elements are not supported')
             recs.append(d)
             # view: 'full' = the whole parameter; 'tok' / 'body' = row 0 / rows 1.. of a ViT pos_embedding
             targets.append((module, attr, tuple(shape), f.get('view', 'full')))
@@ -464,3 +470,4 @@ class BatchPlan:
         chunks = (self.desc_static['numel'] + SCATTER_CHUNK - 1) // SCATTER_CHUNK
         self.desc_static['chunk0'] = np.concatenate([[0], np.cumsum(chunks)[:-1]]) if len(chunks) else []
         self.n_chunks = int(chunks.sum())
+        self.chunk_desc = np.repeat(np.arange(len(chunks), dtype=np.int32), chunks)

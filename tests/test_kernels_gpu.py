@@ -325,6 +325,7 @@ def _run_scatter(entries):
                           ld=e['ld'], ca=e['ca'], ra=e.get('ra', 0), kh_src=e.get('kh_src', 1),
                           kw_src=e.get('kw_src', 1), cy=e.get('cy', 0), cx=e.get('cx', 0), scale=e.get('scale', 1.0),
                           mode=e.get('mode', 0))
+        L.fill_fastdiv(d)
         chunk += (e['dst'].numel() + L.SCATTER_CHUNK - 1) // L.SCATTER_CHUNK
         descs.append(d)
     dev = _desc_array(descs)
