@@ -113,6 +113,10 @@ class ScatterArgs(C.Structure):
     _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp)]
 
 
+class SeqOp(C.Structure):
+    _fields_ = [('op', i32), ('reserved', i32), ('args', vp)]
+
+
 class SumsqArgs(C.Structure):
     _fields_ = [('ptrs', vp), ('numels', vp), ('n', i32), ('out', vp)]
 
@@ -121,7 +125,7 @@ assert C.sizeof(ScatterDesc) == 128 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
-           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace']
+           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 
 _lib = None
 
@@ -145,6 +149,8 @@ def load(build_if_missing=True):
     for s in SYMBOLS[3:14]:
         getattr(lib, s).restype = C.c_int
         getattr(lib, s).argtypes = [C.c_void_p, C.c_void_p]
+    lib.ghn3_run_sequence.restype = C.c_int
+    lib.ghn3_run_sequence.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.ghn3_convert_f32.restype = C.c_int
     lib.ghn3_convert_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     _lib = lib

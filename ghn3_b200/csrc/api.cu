@@ -105,6 +105,28 @@ extern "C" const char* ghn3_last_error(void) { return ghn3::g_error; }
 extern "C" int ghn3_abi_version(void) { return 1; }
 extern "C" int64_t ghn3_launch_count(void) { return ghn3::g_launches.load(std::memory_order_relaxed); }
 
+extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream) {
+  if (ops == nullptr && n > 0) {
+    ghn3::set_error("ghn3_run_sequence: null op table");
+    return GHN3_ERR_BAD_ARG;
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc;
+    switch (ops[i].op) {
+      case GHN3_OP_NODE_FEATURES: rc = ghn3_node_features((const ghn3_node_features_args*)ops[i].args, stream); break;
+      case GHN3_OP_GRAPHORMER: rc = ghn3_graphormer_stack((const ghn3_graphormer_args*)ops[i].args, stream); break;
+      case GHN3_OP_GEMM: rc = ghn3_gemm((const ghn3_gemm_args*)ops[i].args, stream); break;
+      case GHN3_OP_GEMM_SIMT: rc = ghn3_gemm_simt((const ghn3_gemm_simt_args*)ops[i].args, stream); break;
+      case GHN3_OP_SCATTER: rc = ghn3_scatter((const ghn3_scatter_args*)ops[i].args, stream); break;
+      default:
+        ghn3::set_error("ghn3_run_sequence: unknown op %d at index %d", ops[i].op, i);
+        return GHN3_ERR_BAD_ARG;
+    }
+    if (rc != GHN3_OK) return rc;
+  }
+  return GHN3_OK;
+}
+
 extern "C" int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream) {
   return ghn3::graphormer_impl(args, (cudaStream_t)stream);
 }

@@ -9,6 +9,7 @@ as the reference, so checkpoints load unchanged); all arithmetic of the forward 
 
 There is no CPU path: the GHN must live on a CUDA device.
 """
+import ctypes as ct
 import math
 import weakref
 from collections import OrderedDict
@@ -189,7 +190,21 @@ class GHN3(GHN):
     # device-side weight cache
     # ------------------------------------------------------------------------------------------------------------
     def _weights_signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()), self.compute_dtype
+        plist = self.__dict__.get('_param_list')
+        if plist is None:
+            plist = list(self.parameters())
+            self.__dict__['_param_list'] = plist
+        return tuple([p._version for p in plist]), self.compute_dtype
+
+    def _apply(self, fn, *args, **kwargs):                 # .to() / .cuda() / .float(): parameters may be replaced
+        self.__dict__['_param_list'] = None
+        self._dev = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__['_param_list'] = None
+        self._dev = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _device_weights(self):
         sig = self._weights_signature()
@@ -340,103 +355,171 @@ class GHN3(GHN):
         return st
 
     def _run(self, w, pack, bp, return_embeddings):
+        """Executes the device program of this (batch plan, weight version): ONE C call enqueues every kernel."""
         device = self.embed.weight.device
+        prog = getattr(bp, 'program', None)
+        if prog is None or prog.w is not w or prog.device != device or prog.want_emb != bool(return_embeddings):
+            prog = _Program(self, w, bp, device, bool(return_embeddings))
+            bp.program = prog
+        prog.bind_pack(pack)
+        prog.refresh_targets(self.weight_norm)
+        prof = getattr(self, '_profile', None)
+        if bp.n_tok_elems:
+            # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
+            prog.tok.normal_(mean=0.0, std=0.02)
+        prog.run(prof)
+        return prog.emb
+
+
+class _Program:
+    """
+    The kernel sequence of one batch plan with every argument struct prebuilt and every workspace buffer allocated
+    once; per call only the graph-pack pointers and (if they moved) the target-parameter addresses are patched.
+    """
+    OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5}
+
+    def __init__(self, ghn, w, bp, device, want_emb):
+        self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
         dt, x3, act = w['dtype'], w['x3'], w['act']
         tdt = ops.TORCH_DTYPE[dt]
-        C, H = self.hid, self.heads
-        ms0, ms1, S, _ = self.max_shape
-        ncls = self.num_classes
-        st = self._static_device(bp, device)
+        C, H = ghn.hid, ghn.heads
+        ms0, ms1, S, _ = ghn.max_shape
+        ncls = ghn.num_classes
+        st = ghn._static_device(bp, device)
+        self.st = st
         N = bp.total_nodes
-        assert N == pack.total_nodes
-        stream = L.current_stream()
-
-        prof = getattr(self, '_profile', None)
-
-        def mark(name):
-            if prof is not None:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                prof.append((name, ev))
-
-        mark('start')
+        E = lambda *shape, dtype=tdt: torch.empty(*shape, dtype=dtype, device=device)
+        self.keep = []
+        self.ops = []            # (stage label, op code, ctypes args struct)
         # ---- node features ----
-        op = getattr(pack, 'op_dev', None)
-        if op is None:
-            raise RuntimeError('internal: graph pack has no op ids')
-        x = ops.node_features(op, st['shape_idx'], pack, w['tables'], C)
-        mark('node_features')
-
+        self.x = E(N, C, dtype=torch.float32)
+        t = w['tables']
+        self.nf = L.NodeFeaturesArgs(total_nodes=N, hid=C, shape_idx=L.ptr(st['shape_idx']),
+                                     embed_op=L.ptr(t['embed_op']), embed_ch=L.ptr(t['embed_ch']),
+                                     embed_sp=L.ptr(t['embed_sp']), cent_in=L.ptr(t['cent_in']),
+                                     cent_out=L.ptr(t['cent_out']), dist_embed=L.ptr(t['dist_embed']), x=L.ptr(self.x))
+        self.ops.append(('node_features', 'node_features', self.nf))
         # ---- Graphormer stack + final LN scattered into the decoder input rows ----
         n_dec = bp.n_conv + bp.n_1d
-        dec_in = torch.empty(max(n_dec, 1), C, dtype=tdt, device=device)
-        emb = torch.empty(N, C, dtype=torch.float32, device=device) if return_embeddings else None
-        h = torch.empty(N, C, dtype=tdt, device=device)
-        qkv = torch.empty(N, 3 * C, dtype=tdt, device=device)
-        ff = torch.empty(N, 4 * C, dtype=tdt, device=device)
-        lut = self._lut(w, pack.cutoff)
-        ga = L.GraphormerArgs(hid=C, heads=H, layers=self.layers, dtype=dt, layers_host=w['layers'],
-                              ln_w=L.ptr(w['ln_w']), ln_b=L.ptr(w['ln_b']), n_graphs=pack.n_graphs, total_nodes=N,
-                              max_nodes=pack.max_nodes, lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']),
-                              mat_off=L.ptr(pack.d['mat_off']), pair=L.ptr(pack.pair), lut=L.ptr(lut), x=L.ptr(x),
-                              h=L.ptr(h), qkv=L.ptr(qkv), ff=L.ptr(ff), dec_in=L.ptr(dec_in), dec_dtype=act,
-                              dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(emb), tf32_x3=int(x3))
-        L.call('graphormer_stack', ga, stream)
-        mark('graphormer')
-
+        self.dec_in = E(max(n_dec, 1), C)
+        self.emb = E(N, C, dtype=torch.float32) if want_emb else None
+        self.h, self.qkv, self.ff = E(N, C), E(N, 3 * C), E(N, 4 * C)
+        self.ghn = ghn
+        self.ga = L.GraphormerArgs(hid=C, heads=H, layers=ghn.layers, dtype=dt, layers_host=w['layers'],
+                                   ln_w=L.ptr(w['ln_w']), ln_b=L.ptr(w['ln_b']), total_nodes=N, x=L.ptr(self.x),
+                                   h=L.ptr(self.h), qkv=L.ptr(self.qkv), ff=L.ptr(self.ff), dec_in=L.ptr(self.dec_in),
+                                   dec_dtype=act, dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(self.emb),
+                                   tf32_x3=int(x3))
+        self.ops.append(('graphormer', 'graphormer_stack', self.ga))
         bufs = {}
+
+        def gemm_args(a, b, bias, act_, out, out_dtype, problems=None, tiles=None, **kw):
+            g = L.GemmArgs(a=L.ptr(a), a_rows=a.shape[0], lda=a.stride(0), b=L.ptr(b), b_rows=b.shape[0],
+                           ldb=b.stride(0), k=a.shape[1], in_dtype=dt, d=L.ptr(out), out_dtype=out_dtype,
+                           bias=L.ptr(bias), act=act_, tf32_x3=int(x3), **kw)
+            if problems is not None:
+                g.problems, g.tiles, g.n_tiles = L.ptr(problems), L.ptr(tiles), tiles.shape[0]
+            else:
+                g.single = L.GemmProblem(a_row0=0, b_row0=0, m=a.shape[0], n=b.shape[0], d_off=0,
+                                         ldd=out.stride(0), bias_off=0 if bias is not None else -1)
+            return g
+
         # ---- conv decoder: fc (cropped positions) -> conv.0 -> conv.2 (needed columns only) ----
         R = bp.conv_total_rows
         if R > 0:
-            h0 = torch.empty(R, 4 * C, dtype=tdt, device=device)
-            ops.gemm(dec_in, w['fc_w'], bias=w['fc_b'], act=ops.ACT_RELU, in_dtype=dt, out=h0, out_dtype=act,
-                     problems=st['fc_problems'], tiles=st['fc_tiles'], x3=x3)
-            mark('dec_fc')
-            h1 = ops.gemm(h0, w['c0_w'], bias=w['c0_b'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=act, x3=x3)
-            mark('dec_conv0')
-            wout = torch.empty(bp.wout_elems, dtype=torch.float32, device=device)
+            self.h0, self.h1 = E(R, 4 * C), E(R, 8 * C)
+            self.wout = E(bp.wout_elems, dtype=torch.float32)
+            self.ops.append(('dec_fc', 'gemm', gemm_args(self.dec_in, w['fc_w'], w['fc_b'], ops.ACT_RELU, self.h0, act,
+                                                         st['fc_problems'], st['fc_tiles'])))
+            self.ops.append(('dec_conv0', 'gemm', gemm_args(self.h0, w['c0_w'], w['c0_b'], ops.ACT_RELU, self.h1, act)))
             for g_, _, _ in bp.c2_launches:
-                ops.gemm(h1, w['c2_w'], bias=w['c2_b'], in_dtype=dt, out=wout, out_dtype=ops.F32,
-                         problems=st['c2_%d_problems' % g_], tiles=st['c2_%d_tiles' % g_], x3=x3,
-                         b_group=g_, b_group_stride=ms1 if g_ else 0, block_n=128)
-            mark('dec_conv2')
-            bufs[SRC_WOUT] = wout
+                self.ops.append(('dec_conv2', 'gemm',
+                                 gemm_args(self.h1, w['c2_w'], w['c2_b'], ops.ACT_NONE, self.wout, ops.F32,
+                                           st['c2_%d_problems' % g_], st['c2_%d_tiles' % g_], b_group=g_,
+                                           b_group_stride=ms1 if g_ else 0, block_n=128)))
+            bufs[SRC_WOUT] = self.wout
             if bp.clsw_elems:
-                clsw = torch.empty(bp.clsw_elems, dtype=torch.float32, device=device)
+                self.clsw = E(bp.clsw_elems, dtype=torch.float32)
                 for (woff, ld, ii, cnt, coff) in bp.cls_heads:
                     # out[node][cls][b] = b_cls[cls] + sum_a W_cls[cls][a] * relu(wout[node][a*i'+b])  (nn.py:757-758)
-                    ops.gemm_simt(wout, 1, ii, w['cls_w'], ms0, 1, w['cls_b'], clsw, 1, ii, m=ii, n=ncls, k=ms0,
-                                  relu_a=True, batch=cnt, a_bs=ld, d_bs=ncls * ii, a_off=woff, d_off=coff)
-                bufs[SRC_CLSW] = clsw
+                    sa = L.GemmSimtArgs(a=self.wout.data_ptr() + woff * 4, sam=1, sak=ii, b=L.ptr(w['cls_w']), sbn=ms0,
+                                        sbk=1, bias=L.ptr(w['cls_b']), d=self.clsw.data_ptr() + coff * 4, sdm=1,
+                                        sdn=ii, m=ii, n=ncls, k=ms0, relu_a=1, act=ops.ACT_NONE, batch=cnt, a_bs=ld,
+                                        d_bs=ncls * ii)
+                    self.ops.append(('heads_1d', 'gemm_simt', sa))
+                bufs[SRC_CLSW] = self.clsw
         # ---- 1-D decoder (+ classification bias head) ----
         if bp.n_1d > 0:
-            d_in = dec_in[bp.n_conv:bp.n_conv + bp.n_1d]
-            hid1 = ops.gemm(d_in, w['d1_w0'], bias=w['d1_b0'], act=ops.ACT_RELU, in_dtype=dt, out_dtype=act, x3=x3)
-            d1 = ops.gemm(hid1, w['d1_w1'], bias=w['d1_b1'], in_dtype=dt, out_dtype=ops.F32, x3=x3)
-            bufs[SRC_D1] = d1
+            d_in = self.dec_in[bp.n_conv:bp.n_conv + bp.n_1d]
+            mc = bp.max_ch
+            self.hid1, self.d1 = E(bp.n_1d, 2 * C), E(bp.n_1d, 2 * mc, dtype=torch.float32)
+            self.ops.append(('heads_1d', 'gemm', gemm_args(d_in, w['d1_w0'], w['d1_b0'], ops.ACT_RELU, self.hid1, act)))
+            self.ops.append(('heads_1d', 'gemm', gemm_args(self.hid1, w['d1_w1'], w['d1_b1'], ops.ACT_NONE, self.d1,
+                                                           ops.F32)))
+            bufs[SRC_D1] = self.d1
             if bp.n_clsb:
-                mc = bp.max_ch
-                clsb = torch.empty(2 * bp.n_clsb, ncls, dtype=torch.float32, device=device)
-                ops.gemm_simt(d1, mc, 1, w['bc_w'], mc, 1, w['bc_b'], clsb, ncls, 1, m=2 * bp.n_clsb, n=ncls, k=mc,
-                              relu_a=True, a_off=(bp.n_1d - bp.n_clsb) * 2 * mc)
-                bufs[SRC_CLSB] = clsb
-        if bp.n_tok_elems:
-            # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
-            bufs[SRC_TOK] = torch.normal(mean=0.0, std=0.02, size=(bp.n_tok_elems,), device=device)
-
-        mark('heads_1d')
+                self.clsb = E(2 * bp.n_clsb, ncls, dtype=torch.float32)
+                sa = L.GemmSimtArgs(a=self.d1.data_ptr() + (bp.n_1d - bp.n_clsb) * 2 * mc * 4, sam=mc, sak=1,
+                                    b=L.ptr(w['bc_w']), sbn=mc, sbk=1, bias=L.ptr(w['bc_b']), d=L.ptr(self.clsb),
+                                    sdm=ncls, sdn=1, m=2 * bp.n_clsb, n=ncls, k=mc, relu_a=1, act=ops.ACT_NONE,
+                                    batch=1)
+                self.ops.append(('heads_1d', 'gemm_simt', sa))
+                bufs[SRC_CLSB] = self.clsb
+        self.tok = E(max(bp.n_tok_elems, 1), dtype=torch.float32)
+        bufs[SRC_TOK] = self.tok
+        self.bufs = bufs
         # ---- tile / normalise / scatter into the target parameters ----
-        self._scatter(bp, bufs, device, st['chunk_desc'])
-        mark('scatter')
-        self._last_buffers = bufs if self.debug_level else None
-        return emb
-
-    def _scatter(self, bp, bufs, device, chunk_desc=None):
         n = len(bp.desc_static)
+        self.n_desc = n
+        self.desc_host = bp.desc_static.copy()
+        base = np.zeros(8, dtype=np.uint64)
+        for k_, v in bufs.items():
+            base[k_] = v.data_ptr()
+        if n:
+            self.desc_host['src'] = base[bp.desc_src_buf] + bp.desc_src_off * np.uint64(4)
+        self.desc_dev = torch.empty(max(n, 1) * self.desc_host.dtype.itemsize, dtype=torch.uint8, device=device)
+        self.last_ptrs = None
+        if n:
+            self.sc = L.ScatterArgs(descs=L.ptr(self.desc_dev), n_descs=n, n_chunks=bp.n_chunks,
+                                    chunk_desc=L.ptr(st['chunk_desc']))
+            self.ops.append(('scatter', 'scatter', self.sc))
+        # flat op table for ghn3_run_sequence
+        self.seq = (L.SeqOp * len(self.ops))()
+        for i, (_, name, args) in enumerate(self.ops):
+            self.seq[i].op = self.OP[name]
+            self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
+        self.bound_pack = None
+
+    def bind_pack(self, pack):
+        if pack is self.bound_pack:
+            return
+        assert pack.total_nodes == self.bp.total_nodes
+        if getattr(pack, 'op_dev', None) is None:
+            raise RuntimeError('internal: graph pack has no op ids')
+        nf, ga = self.nf, self.ga
+        nf.op, nf.deg_in, nf.deg_out, nf.dist0 = L.ptr(pack.op_dev), L.ptr(pack.deg_in), L.ptr(pack.deg_out), \
+            L.ptr(pack.dist0)
+        lut = self.ghn._lut(self.w, pack.cutoff)
+        ga.n_graphs, ga.max_nodes, ga.lut_size = pack.n_graphs, pack.max_nodes, lut.shape[1]
+        ga.node_off, ga.mat_off = L.ptr(pack.d['node_off']), L.ptr(pack.d['mat_off'])
+        ga.pair, ga.lut = L.ptr(pack.pair), L.ptr(lut)
+        self.bound_pack = pack
+
+    def refresh_targets(self, weight_norm):
+        """Re-reads the addresses of the target parameters; uploads the descriptor table only if one moved."""
+        n = self.n_desc
         if n == 0:
             return
+        device = self.device
         ptrs = np.empty(n, dtype=np.uint64)
-        for i, (module, attr, shape, view) in enumerate(bp.desc_targets):
+        for i, (module, attr, shape, view) in enumerate(self.bp.desc_targets):
+            p = module._parameters.get(attr)
+            if p is None:
+                p = getattr(module, attr)
+            ptrs[i] = p.data_ptr()
+        if self.last_ptrs is not None and np.array_equal(ptrs, self.last_ptrs):
+            return
+        for i, (module, attr, shape, view) in enumerate(self.bp.desc_targets):
             p = getattr(module, attr)
             if not isinstance(p, torch.Tensor):
                 raise RuntimeError('ghn3_b200: target %s.%s is not a tensor (light modules need keep_grads=True, '
@@ -444,19 +527,30 @@ class GHN3(GHN):
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
                 # reference semantics (nn.py:548): param.data is replaced by a tensor on the GHN's device
                 p.data = torch.empty(tuple(p.shape), dtype=torch.float32, device=device)
-            ptrs[i] = p.data_ptr()
-        desc = bp.desc_static.copy()
-        base = np.zeros(8, dtype=np.uint64)
-        for k, v in bufs.items():
-            base[k] = v.data_ptr()
-        desc['dst'] = ptrs + bp.desc_dst_shift
-        desc['src'] = base[bp.desc_src_buf] + bp.desc_src_off * np.uint64(4)
-        if not self.weight_norm:
+                ptrs[i] = p.data_ptr()
+        desc = self.desc_host
+        desc['dst'] = ptrs + self.bp.desc_dst_shift
+        if not weight_norm:
             desc['mode'] = np.where(desc['mode'] == 3, 3, 0)
             desc['scale'] = 1.0
-        dev_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1)).to(device)
-        ops.scatter(dev_desc, n, bp.n_chunks, chunk_desc)
-        self._desc_keepalive = (dev_desc, bufs)
+        self.desc_dev.copy_(torch.from_numpy(desc.view(np.uint8).reshape(-1)))
+        self.last_ptrs = ptrs
+
+    def run(self, prof=None):
+        stream = L.current_stream()
+        if prof is None:
+            L.check(L.load().ghn3_run_sequence(self.seq, len(self.ops), ct.c_void_p(stream)), 'ghn3_run_sequence')
+            return
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            prof.append((name, ev))
+        mark('start')
+        for i, (stage, name, args) in enumerate(self.ops):
+            L.call(name, args, stream)
+            if i + 1 == len(self.ops) or self.ops[i + 1][0] != stage:
+                mark(stage)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -323,6 +323,14 @@ typedef struct {
 
 int ghn3_sumsq(const ghn3_sumsq_args* args, ghn3_stream_t stream);
 
+/* Runs a prebuilt sequence of the entry points above with ONE call (the host side of `ghn(model)` is then a single
+ * FFI crossing per prediction): ops[i].args points to the argument struct of the entry point named by ops[i].op. */
+enum ghn3_opcode {
+  GHN3_OP_NODE_FEATURES = 1, GHN3_OP_GRAPHORMER = 2, GHN3_OP_GEMM = 3, GHN3_OP_GEMM_SIMT = 4, GHN3_OP_SCATTER = 5
+};
+typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
+int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);
+
 /* dtype conversion helpers used when a checkpoint is prepared for the device (one-time, not on the hot path). */
 int ghn3_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, ghn3_stream_t stream);
 
