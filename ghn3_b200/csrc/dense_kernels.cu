@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const ghn3_gemm_simt_arg
   float* Dp = a.d + (int64_t)bz * a.d_bs;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool a_k_fast = a.sak == 1, b_k_fast = a.sbk == 1;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -547,18 +548,17 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const ghn3_gemm_simt_arg
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < a.k; k0 += 16) {
     for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
-      const int kk = idx & 15, r = idx >> 4;
-      const int k = k0 + kk;
+      // consecutive threads walk the operand's contiguous dimension (k if its stride is 1, else the row index)
+      const int kka = a_k_fast ? (idx & 15) : (idx >> 6), ra = a_k_fast ? (idx >> 4) : (idx & 63);
+      const int kkb = b_k_fast ? (idx & 15) : (idx >> 6), rb = b_k_fast ? (idx >> 4) : (idx & 63);
       float va = 0.f, vb = 0.f;
-      if (k < a.k) {
-        if (m0 + r < a.m) {
-          va = A[(int64_t)(m0 + r) * a.sam + (int64_t)k * a.sak];
-          if (a.relu_a) va = fmaxf(va, 0.f);
-        }
-        if (n0 + r < a.n) vb = a.b[(int64_t)(n0 + r) * a.sbn + (int64_t)k * a.sbk];
+      if (k0 + kka < a.k && m0 + ra < a.m) {
+        va = __ldg(A + (int64_t)(m0 + ra) * a.sam + (int64_t)(k0 + kka) * a.sak);
+        if (a.relu_a) va = fmaxf(va, 0.f);
       }
-      sA[kk][r] = va;
-      sB[kk][r] = vb;
+      if (k0 + kkb < a.k && n0 + rb < a.n) vb = __ldg(a.b + (int64_t)(n0 + rb) * a.sbn + (int64_t)(k0 + kkb) * a.sbk);
+      sA[kka][ra] = va;
+      sB[kkb][rb] = vb;
     }
     __syncthreads();
 #pragma unroll
@@ -590,6 +590,41 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const ghn3_gemm_simt_arg
   }
 }
 
+// Skinny case (m <= 8 rows, unit k strides): one warp per output column n, lanes over k, all rows at once.
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const ghn3_gemm_simt_args a) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= a.n) return;
+  const float* A = a.a + (int64_t)blockIdx.z * a.a_bs;
+  float* Dp = a.d + (int64_t)blockIdx.z * a.d_bs;
+  const float* brow = a.b + (int64_t)n * a.sbn;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k = lane; k < a.k; k += 32) {
+    const float w = __ldg(brow + k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < a.m) {
+        float v = __ldg(A + (int64_t)i * a.sam + k);
+        if (a.relu_a) v = fmaxf(v, 0.f);
+        acc[i] = fmaf(v, w, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < a.m) {
+      float v = warp_sum(acc[i]);
+      if (lane == 0) {
+        v += a.bias ? a.bias[n] : 0.f;
+        if (a.act == GHN3_ACT_RELU) v = fmaxf(v, 0.f);
+        Dp[(int64_t)i * a.sdm + (int64_t)n * a.sdn] = v;
+      }
+    }
+  }
+}
+
 __global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t n, int dst_dtype) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -616,6 +651,11 @@ extern "C" int ghn3_gemm_simt(const ghn3_gemm_simt_args* a, ghn3_stream_t stream
   GHN3_REQUIRE(a != nullptr, "ghn3_gemm_simt: null args");
   if (a->m <= 0 || a->n <= 0) return GHN3_OK;
   const int batch = a->batch <= 0 ? 1 : a->batch;
+  if (a->m <= 8 && a->sak == 1 && a->sbk == 1) {
+    gemm_skinny_kernel<<<dim3((unsigned)ceil_div(a->n, 8), 1, (unsigned)batch), 256, 0, stream>>>(*a);
+    GHN3_LAUNCH_CHECK("gemm_skinny_kernel");
+    return GHN3_OK;
+  }
   const dim3 grid((unsigned)ceil_div(a->n, 64), (unsigned)ceil_div(a->m, 64), (unsigned)batch);
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(*a);
   GHN3_LAUNCH_CHECK("gemm_simt_kernel");

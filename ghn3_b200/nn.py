@@ -618,14 +618,27 @@ def from_pretrained(ghn3_name='ghn3xlm16.pt', **kwargs):
     return ghn
 
 
-def param_norm(model):
+def param_norm(model, out=None):
     """Total L2 norm of a model's parameters, computed on the device by ghn3_sumsq (the norm_check metric of
-    nn.py:783-797). Returns a 0-d float64 CUDA tensor (no host sync)."""
-    ps = [p.data for p in model.parameters() if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()]
-    dev = ps[0].device
-    meta = np.array([[p.data_ptr() for p in ps], [p.numel() for p in ps]], dtype=np.int64)
-    meta_dev = torch.from_numpy(meta).to(dev)
-    out = torch.empty(1, dtype=torch.float64, device=dev)
-    a = L.SumsqArgs(ptrs=meta_dev[0].data_ptr(), numels=meta_dev[1].data_ptr(), n=len(ps), out=out.data_ptr())
+    nn.py:783-797). Returns a 1-element float64 CUDA tensor (no host sync). The (pointer, numel) table of the model
+    is cached on the model and re-uploaded only when a parameter moved."""
+    cache = model.__dict__.get('_ghn3_b200_norm')
+    if cache is None:
+        cache = {'params': [p for p in model.parameters()], 'ptrs': None, 'meta': None}
+        model.__dict__['_ghn3_b200_norm'] = cache
+    ps = cache['params']
+    ptrs = [p.data_ptr() for p in ps]
+    if ptrs != cache['ptrs']:
+        for p in ps:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise RuntimeError('ghn3_b200.param_norm: parameters must be contiguous fp32 CUDA tensors')
+        meta = np.array([ptrs, [p.numel() for p in ps]], dtype=np.int64)
+        cache['meta'] = torch.from_numpy(meta).to(ps[0].device)
+        cache['ptrs'] = ptrs
+        cache['args'] = L.SumsqArgs(ptrs=cache['meta'][0].data_ptr(), numels=cache['meta'][1].data_ptr(), n=len(ps))
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=ps[0].device)
+    a = cache['args']
+    a.out = out.data_ptr()
     L.call('sumsq', a, L.current_stream())
     return out.sqrt_()

@@ -420,3 +420,16 @@ def test_gemm_grouped_rows_3d_box(g):
     rows = (torch.arange(o, device=DEV)[:, None] * ms + torch.arange(g, device=DEV)[None, :]).reshape(-1)
     ref = (a.double() @ w[rows].double().t() + bias[rows].double()).float()
     assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_simt_skinny_rows():
+    """bias_class head (nn.py:294): 2 rows per class-bias node, K = max_shape, N = classes."""
+    torch.manual_seed(4)
+    m, k, n = 4, 384, 1000
+    a = torch.randn(m, k, device=DEV)
+    w = torch.randn(n, k, device=DEV) / 20
+    bias = torch.randn(n, device=DEV)
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm_simt(a, k, 1, w, k, 1, bias, out, n, 1, m=m, n=n, k=k, relu_a=True)
+    torch.cuda.synchronize()
+    assert _rel(out, torch.relu(a) @ w.t() + bias) < 1e-5
