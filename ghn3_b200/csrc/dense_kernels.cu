@@ -268,16 +268,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 constexpr int kMmaKT = 256;      // keys staged per outer iteration
-constexpr int kMmaQT = 64;       // queries per CTA
+constexpr int kMmaWarps = 8;
+constexpr int kMmaQT = 16 * kMmaWarps;       // queries per CTA
 
 template <int D>
-__global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention_args a) {
+__global__ void __launch_bounds__(kMmaWarps * 32) attention_mma_kernel(const ghn3_attention_args a) {
   constexpr int DK = (D + 15) / 16 * 16;   // k extent of Q.K^T
   constexpr int DS = DK + 8;               // K row stride (bf16 elements)
   constexpr int DN = (D + 7) / 8 * 8;      // n extent of P.V
   constexpr int VS = kMmaKT + 8;           // V^T row stride (bf16 elements)
   constexpr int NT2 = DN / 8;
   constexpr int KK = DK / 16;
+  constexpr int NTHREADS = kMmaWarps * 32;
+  constexpr int ROW_BYTES = D * 2;
+  constexpr int VB = (ROW_BYTES % 16 == 0) ? 16 : 8;
+  constexpr int VPR = ROW_BYTES / VB;      // vectors per K / V row
+  constexpr int EPV = VB / 2;
+  constexpr int NV = (kMmaKT * VPR + NTHREADS - 1) / NTHREADS;   // staging vectors per thread and operand
   extern __shared__ __align__(16) uint8_t attn_mma_smem[];
   __nv_bfloat16* sK = (__nv_bfloat16*)attn_mma_smem;            // [KT][DS]
   __nv_bfloat16* sVt = sK + kMmaKT * DS;                        // [DN][VS]
@@ -297,20 +304,62 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention
   const float scale_log2 = rsqrtf((float)D) * 1.44269504088896340736f;
   constexpr float kLog2e = 1.44269504088896340736f;
 
-  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = __ldg(a.lut + (int64_t)h * a.lut_size + i) * kLog2e;
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < a.lut_size; i += NTHREADS) sLut[i] = __ldg(a.lut + (int64_t)h * a.lut_size + i) * kLog2e;
   // zero the padded dims of K once (they are never overwritten) and the padded dims of V^T
   if (DK > D) {
-    for (int idx = threadIdx.x; idx < kMmaKT * (DK - D); idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < kMmaKT * (DK - D); idx += NTHREADS) {
       const int j = idx / (DK - D), d = D + idx % (DK - D);
       sK[j * DS + d] = __float2bfloat16_rn(0.f);
     }
   }
   if (DN > D) {
-    for (int idx = threadIdx.x; idx < (DN - D) * VS; idx += blockDim.x) sVt[D * VS + idx] = __float2bfloat16_rn(0.f);
+    for (int idx = threadIdx.x; idx < (DN - D) * VS; idx += NTHREADS) sVt[D * VS + idx] = __float2bfloat16_rn(0.f);
   }
-
-  pdl_launch_dependents();
   pdl_wait();       // everything above only touched the LUT and shared memory
+
+  // K / V staging: every thread owns NV (row, vector) slots of a tile; all loads of a tile are issued back to back
+  // into registers (one memory round trip), and the NEXT tile is fetched while the current one is being consumed.
+  uint4 kreg[NV], vreg[NV];
+  const size_t row_stride = (size_t)C3 * 2, v_off = (size_t)C * 2;
+  auto load_tile = [&](int k0) {
+    const int kt = min(kMmaKT, n - k0);
+    const char* kbase = (const char*)(qkv + (int64_t)k0 * C3 + C + h * D);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int idx = threadIdx.x + u * NTHREADS;
+      const int j = idx / VPR, c = idx - j * VPR;
+      kreg[u] = make_uint4(0, 0, 0, 0);
+      vreg[u] = make_uint4(0, 0, 0, 0);
+      if (j < kt) {
+        const char* src = kbase + (size_t)j * row_stride + c * VB;
+        if constexpr (VB == 16) {
+          kreg[u] = __ldg((const uint4*)src);
+          vreg[u] = __ldg((const uint4*)(src + v_off));
+        } else {
+          const uint2 t0 = __ldg((const uint2*)src), t1 = __ldg((const uint2*)(src + v_off));
+          kreg[u].x = t0.x; kreg[u].y = t0.y;
+          vreg[u].x = t1.x; vreg[u].y = t1.y;
+        }
+      }
+    }
+  };
+  auto store_tile = [&](int k0) {
+    const int kt64 = (min(kMmaKT, n - k0) + 63) & ~63;      // rows up to the 64-key chunk boundary get zeros
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int idx = threadIdx.x + u * NTHREADS;
+      const int j = idx / VPR, c = idx - j * VPR;
+      if (j < kt64) {
+        if constexpr (VB == 16) *(uint4*)(sK + j * DS + c * EPV) = kreg[u];
+        else *(uint2*)(sK + j * DS + c * EPV) = make_uint2(kreg[u].x, kreg[u].y);
+        const __nv_bfloat16* ve = (const __nv_bfloat16*)&vreg[u];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) sVt[(c * EPV + e) * VS + j] = ve[e];
+      }
+    }
+  };
+  load_tile(0);
 
   // Q fragments of this warp's 16 queries, pre-scaled by d^-1/2 * log2(e)
   const int r0 = q0 + warp * 16 + gq, r1 = r0 + 8;
@@ -338,59 +387,40 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention
   }
   const uint16_t* prow0 = pair + (int64_t)(ok0 ? r0 : q0) * ld;
   const uint16_t* prow1 = pair + (int64_t)(ok1 ? r1 : q0) * ld;
+  const bool warp_active = (q0 + warp * 16) < n;     // warp-uniform
+
+  // edge-bias indices of a 16 x 64 block: two keys per 32-bit load, fetched one block ahead of their use
+  uint32_t pw0[8], pw1[8];
+  auto load_pairs = [&](int kbase) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = kbase + nt * 8 + 2 * tq;
+      pw0[nt] = 0; pw1[nt] = 0;
+      if (warp_active && col < n) {
+        pw0[nt] = __ldg((const uint32_t*)(prow0 + col));
+        pw1[nt] = __ldg((const uint32_t*)(prow1 + col));
+      }
+    }
+  };
+  load_pairs(0);
 
   float o[NT2][4];
 #pragma unroll
   for (int i = 0; i < NT2; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const bool warp_active = (q0 + warp * 16) < n;     // warp-uniform
 
   for (int k0 = 0; k0 < n; k0 += kMmaKT) {
     const int kt = min(kMmaKT, n - k0);
-    const int kt64 = (kt + 63) & ~63;
+    __syncthreads();                       // the previous tile has been consumed by every warp
+    store_tile(k0);
     __syncthreads();
-    {
-      constexpr int ROW_BYTES = D * 2;
-      constexpr int VB = (ROW_BYTES % 16 == 0) ? 16 : 8;
-      constexpr int VPR = ROW_BYTES / VB;
-      constexpr int EPV = VB / 2;
-      const char* kbase = (const char*)(qkv + (int64_t)k0 * C3 + C + h * D);
-      const size_t row_stride = (size_t)C3 * 2, v_off = (size_t)C * 2;
-      for (int idx = threadIdx.x; idx < kt64 * VPR; idx += blockDim.x) {
-        const int j = idx / VPR, c = idx - j * VPR;
-        union { uint4 u4; uint2 u2; __nv_bfloat16 e[EPV]; } kv, vv;
-        kv.u4 = make_uint4(0, 0, 0, 0);
-        vv.u4 = make_uint4(0, 0, 0, 0);
-        if (j < kt) {
-          const char* src = kbase + (size_t)j * row_stride + c * VB;
-          if constexpr (VB == 16) {
-            kv.u4 = __ldg((const uint4*)src);
-            vv.u4 = __ldg((const uint4*)(src + v_off));
-          } else {
-            kv.u2 = __ldg((const uint2*)src);
-            vv.u2 = __ldg((const uint2*)(src + v_off));
-          }
-        }
-        if constexpr (VB == 16) *(uint4*)(sK + j * DS + c * EPV) = kv.u4;
-        else *(uint2*)(sK + j * DS + c * EPV) = kv.u2;
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) sVt[(c * EPV + e) * VS + j] = vv.e[e];
-      }
-    }
-    __syncthreads();
+    if (k0 + kMmaKT < n) load_tile(k0 + kMmaKT);       // in flight while this tile is consumed
     if (!warp_active) continue;
     for (int c0 = 0; c0 < kt; c0 += 64) {
-      // edge-bias indices of this 16 x 64 block: two keys per 32-bit load
-      uint32_t pw0[8], pw1[8];
+      uint32_t cw0[8], cw1[8];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = k0 + c0 + nt * 8 + 2 * tq;
-        pw0[nt] = 0; pw1[nt] = 0;
-        if (col < n) {
-          pw0[nt] = __ldg((const uint32_t*)(prow0 + col));
-          pw1[nt] = __ldg((const uint32_t*)(prow1 + col));
-        }
-      }
+      for (int nt = 0; nt < 8; ++nt) { cw0[nt] = pw0[nt]; cw1[nt] = pw1[nt]; }
+      if (k0 + c0 + 64 < n) load_pairs(k0 + c0 + 64);  // next block's indices, consumed one iteration later
       float s[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -407,10 +437,10 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const ghn3_attention
       for (int nt = 0; nt < 8; ++nt) {
         const int col = k0 + c0 + nt * 8 + 2 * tq;
         const bool v0 = col < n, v1 = col + 1 < n;
-        s[nt][0] = v0 ? s[nt][0] + sLut[pw0[nt] & 0xFFFFu] : -INFINITY;
-        s[nt][1] = v1 ? s[nt][1] + sLut[pw0[nt] >> 16] : -INFINITY;
-        s[nt][2] = v0 ? s[nt][2] + sLut[pw1[nt] & 0xFFFFu] : -INFINITY;
-        s[nt][3] = v1 ? s[nt][3] + sLut[pw1[nt] >> 16] : -INFINITY;
+        s[nt][0] = v0 ? s[nt][0] + sLut[cw0[nt] & 0xFFFFu] : -INFINITY;
+        s[nt][1] = v1 ? s[nt][1] + sLut[cw0[nt] >> 16] : -INFINITY;
+        s[nt][2] = v0 ? s[nt][2] + sLut[cw1[nt] & 0xFFFFu] : -INFINITY;
+        s[nt][3] = v1 ? s[nt][3] + sLut[cw1[nt] >> 16] : -INFINITY;
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -477,7 +507,7 @@ static int launch_attention_mma(const ghn3_attention_args* a, cudaStream_t strea
     return GHN3_ERR_UNSUPPORTED;
   }
   const dim3 grid((unsigned)ceil_div(a->max_nodes, kMmaQT), (unsigned)a->heads, (unsigned)a->n_graphs);
-  GHN3_CUDA(launch_pdl(attention_mma_kernel<D>, grid, dim3(128), (size_t)smem, stream, *a));
+  GHN3_CUDA(launch_pdl(attention_mma_kernel<D>, grid, dim3(kMmaWarps * 32), (size_t)smem, stream, *a));
   GHN3_LAUNCH_CHECK("attention_mma_kernel");
   return GHN3_OK;
 }
