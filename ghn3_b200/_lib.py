@@ -53,7 +53,7 @@ class GemmArgs(C.Structure):
     _fields_ = [('a', vp), ('a_rows', i64), ('lda', i64), ('b', vp), ('b_rows', i64), ('ldb', i64), ('k', i32),
                 ('in_dtype', i32), ('d', vp), ('out_dtype', i32), ('bias', vp), ('act', i32), ('accumulate', i32),
                 ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32),
-                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32)]
+                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32)]
 
 
 class GemmSimtArgs(C.Structure):
@@ -113,6 +113,11 @@ class ScatterArgs(C.Structure):
     _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp)]
 
 
+class ReluTransposeArgs(C.Structure):
+    _fields_ = [('src', vp), ('ld', i64), ('src_bs', i64), ('dst', vp), ('dst_dtype', i32), ('rows', i32),
+                ('cols', i32), ('batch', i32)]
+
+
 class SeqOp(C.Structure):
     _fields_ = [('op', i32), ('reserved', i32), ('args', vp)]
 
@@ -125,7 +130,7 @@ assert C.sizeof(ScatterDesc) == 128 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
-           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
+           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 
 _lib = None
 
@@ -146,7 +151,7 @@ def load(build_if_missing=True):
             raise RuntimeError('ghn3_b200: %s does not export %s' % (LIB_PATH, s))
     lib.ghn3_last_error.restype = C.c_char_p
     lib.ghn3_launch_count.restype = C.c_int64
-    for s in SYMBOLS[3:14]:
+    for s in SYMBOLS[3:15]:
         getattr(lib, s).restype = C.c_int
         getattr(lib, s).argtypes = [C.c_void_p, C.c_void_p]
     lib.ghn3_run_sequence.restype = C.c_int

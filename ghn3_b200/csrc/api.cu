@@ -118,6 +118,7 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
       case GHN3_OP_GEMM: rc = ghn3_gemm((const ghn3_gemm_args*)ops[i].args, stream); break;
       case GHN3_OP_GEMM_SIMT: rc = ghn3_gemm_simt((const ghn3_gemm_simt_args*)ops[i].args, stream); break;
       case GHN3_OP_SCATTER: rc = ghn3_scatter((const ghn3_scatter_args*)ops[i].args, stream); break;
+      case GHN3_OP_RELU_TRANSPOSE: rc = ghn3_relu_transpose((const ghn3_relu_transpose_args*)ops[i].args, stream); break;
       default:
         ghn3::set_error("ghn3_run_sequence: unknown op %d at index %d", ops[i].op, i);
         return GHN3_ERR_BAD_ARG;

@@ -655,6 +655,31 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const ghn3_gemm_simt_a
   }
 }
 
+// 32 x 32 tiles through shared memory: coalesced reads along c, coalesced writes along r
+__global__ void __launch_bounds__(256) relu_transpose_kernel(const ghn3_relu_transpose_args a) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* src = a.src + (int64_t)z * a.src_bs;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < a.rows && c < a.cols) ? fmaxf(src[(int64_t)r * a.ld + c], 0.f) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < a.cols && r < a.rows) {
+      const float v = tile[tx][i];
+      const int64_t o = ((int64_t)z * a.cols + c) * a.rows + r;
+      if (a.dst_dtype == GHN3_BF16) ((__nv_bfloat16*)a.dst)[o] = __float2bfloat16_rn(v);
+      else ((float*)a.dst)[o] = a.dst_dtype == GHN3_TF32 ? round_tf32(v) : v;
+    }
+  }
+}
+
 __global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, int64_t n, int dst_dtype) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -689,6 +714,17 @@ extern "C" int ghn3_gemm_simt(const ghn3_gemm_simt_args* a, ghn3_stream_t stream
   const dim3 grid((unsigned)ceil_div(a->n, 64), (unsigned)ceil_div(a->m, 64), (unsigned)batch);
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(*a);
   GHN3_LAUNCH_CHECK("gemm_simt_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_relu_transpose(const ghn3_relu_transpose_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_relu_transpose: null args");
+  GHN3_REQUIRE(a->dst_dtype >= GHN3_BF16 && a->dst_dtype <= GHN3_F32, "ghn3_relu_transpose: bad dtype");
+  if (a->rows <= 0 || a->cols <= 0 || a->batch <= 0) return GHN3_OK;
+  const dim3 grid((unsigned)ceil_div(a->cols, 32), (unsigned)ceil_div(a->rows, 32), (unsigned)a->batch);
+  GHN3_CUDA(launch_pdl(relu_transpose_kernel, grid, dim3(256), 0, stream, *a));
+  GHN3_LAUNCH_CHECK("relu_transpose_kernel");
   return GHN3_OK;
 }
 

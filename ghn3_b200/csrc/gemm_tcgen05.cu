@@ -142,6 +142,8 @@ struct GemmKernelArgs {
   // the 3-D TMA box {K chunk, b_group inner rows, b_outer outer rows}: tile column c <-> B row (c / b_group) *
   // b_stride + c % b_group, i.e. the compact o' x i' column order of the prediction buffer.
   int32_t b_group, b_stride, b_outer;
+  int32_t bias_rows;
+  int32_t b_dynamic;     // B is produced by an earlier kernel of the step: do not fetch it before pdl_wait()
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -270,6 +272,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // B holds weights (never written during a step): its first ring-full of tiles is requested BEFORE waiting
       // for the predecessor kernel, so the HBM latency of the weights hides behind the predecessor's tail.
       const int pre = min(num_kb, kStages);
+      if (args.b_dynamic) pdl_wait();
       for (int i = 0; i < pre; ++i) {
         mbar_arrive_expect_tx(full_bar + 8 * i, A_BYTES + b_bytes);
         load_b(sB + i * B_BYTES, full_bar + 8 * i, (kb0 + i) * BK);
@@ -351,14 +354,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                           ((((p.d_off + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
       // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
       float b_lane = 0.f;
-      if (use_bias && n0 + lane < n_end) {
+      const float b_row = (use_bias && args.bias_rows && lane < rows_valid)
+                              ? __ldg(args.bias + p.bias_off + m_base + lane) : 0.f;
+      if (use_bias && !args.bias_rows && n0 + lane < n_end) {
         const int c = n0 + lane;
         const int bidx = args.b_group > 0 ? (c / args.b_group) * args.b_stride + c % args.b_group : c;
         b_lane = __ldg(args.bias + p.bias_off + bidx);
       }
       float v[32];
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj);
+      for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj) + b_row;
       // the activation is selected ONCE per chunk (a per-element runtime test gets if-converted and the erf
       // polynomial would issue, predicated off, for every element of every GEMM)
       if (!args.accumulate) {
@@ -662,6 +667,8 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.b_group = a->b_group;
   ka.b_stride = a->b_group_stride;
   ka.b_outer = b_outer;
+  ka.bias_rows = a->bias_rows;
+  ka.b_dynamic = a->b_dynamic;
 
   if (x3) {
     if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);

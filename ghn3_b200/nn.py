@@ -250,7 +250,7 @@ class GHN3(GHN):
         w['fc_b'] = f(dec.fc[0].bias).view(4 * C, S * S).t().contiguous().view(-1)
         w['c0_w'], w['c0_b'] = cv(dec.conv[0].weight), f(dec.conv[0].bias)
         w['c2_w'], w['c2_b'] = cv(dec.conv[2].weight), f(dec.conv[2].bias)
-        w['cls_w'], w['cls_b'] = f(dec.class_layer_predictor[1].weight), f(dec.class_layer_predictor[1].bias)
+        w['cls_w'], w['cls_b'] = cv(dec.class_layer_predictor[1].weight), f(dec.class_layer_predictor[1].bias)
         w['d1_w0'], w['d1_b0'] = cv(self.decoder_1d.fc[0].weight), f(self.decoder_1d.fc[0].bias)
         w['d1_w1'], w['d1_b1'] = cv(self.decoder_1d.fc[2].weight), f(self.decoder_1d.fc[2].bias)
         w['bc_w'], w['bc_b'] = f(self.bias_class[1].weight), f(self.bias_class[1].bias)
@@ -376,7 +376,7 @@ class _Program:
     The kernel sequence of one batch plan with every argument struct prebuilt and every workspace buffer allocated
     once; per call only the graph-pack pointers and (if they moved) the target-parameter addresses are patched.
     """
-    OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5}
+    OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6}
 
     def __init__(self, ghn, w, bp, device, want_emb):
         self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
@@ -441,12 +441,16 @@ class _Program:
             if bp.clsw_elems:
                 self.clsw = E(bp.clsw_elems, dtype=torch.float32)
                 for (woff, ld, ii, cnt, coff) in bp.cls_heads:
-                    # out[node][cls][b] = b_cls[cls] + sum_a W_cls[cls][a] * relu(wout[node][a*i'+b])  (nn.py:757-758)
-                    sa = L.GemmSimtArgs(a=self.wout.data_ptr() + woff * 4, sam=1, sak=ii, b=L.ptr(w['cls_w']), sbn=ms0,
-                                        sbk=1, bias=L.ptr(w['cls_b']), d=self.clsw.data_ptr() + coff * 4, sdm=1,
-                                        sdn=ii, m=ii, n=ncls, k=ms0, relu_a=1, act=ops.ACT_NONE, batch=cnt, a_bs=ld,
-                                        d_bs=ncls * ii)
-                    self.ops.append(('heads_1d', 'gemm_simt', sa))
+                    # out[cls][(node, b)] = b_cls[cls] + sum_a W_cls[cls][a] * relu(wout[node][a*i'+b])  (nn.py:757-758):
+                    # relu + transpose of the (ms x i') block into a K-major operand, then a tensor-core GEMM
+                    rt = E(cnt * ii, ms0)
+                    self.keep.append(rt)
+                    ta = L.ReluTransposeArgs(src=self.wout.data_ptr() + woff * 4, ld=ii, src_bs=ld, dst=L.ptr(rt),
+                                             dst_dtype=act, rows=ms0, cols=ii, batch=cnt)
+                    self.ops.append(('heads_1d', 'relu_transpose', ta))
+                    out_view = self.clsw[coff:coff + ncls * cnt * ii].view(ncls, cnt * ii)
+                    self.ops.append(('heads_1d', 'gemm', gemm_args(w['cls_w'], rt, w['cls_b'], ops.ACT_NONE, out_view,
+                                                                   ops.F32, bias_rows=1, b_dynamic=1)))
                 bufs[SRC_CLSW] = self.clsw
         # ---- 1-D decoder (+ classification bias head) ----
         if bp.n_1d > 0:

@@ -337,7 +337,9 @@ class BatchPlan:
                 if t0.kind == KIND_CLS_W:
                     self.cls_heads.append((seg_base + (row - seg_row0) * ld, ld, ii, cnt, clsw_elems))
                     for q in range(k, m):
-                        self.seg_of[q] = (clsw_elems + (q - k) * ncls * ii, 0)     # cls nodes read the head output
+                        # cls nodes read the class-head output [classes][cnt * i'] (element (cls, b) of node j at
+                        # cls * cnt*i' + j*i' + b): base offset + column stride of the class index
+                        self.seg_of[q] = (clsw_elems + (q - k) * ii, cnt * ii)
                     clsw_elems += cnt * ncls * ii
                 row += cnt * P
                 k = m
@@ -415,7 +417,7 @@ class BatchPlan:
             if t.kind == KIND_CLS_W:
                 tt = tuple(tsz) + (1,) * (4 - len(tsz))
                 add(mod, attr, tsz, SRC_CLSW, base, t1=tt[1], t2=tt[2], t3=tt[3], so=ncls, si=t.i_need, ld=0,
-                    ca=t.i_need, scale=scale_for(tsz))
+                    ca=ld, scale=scale_for(tsz))
                 continue
             common = dict(so=t.o_need, si=t.i_need, ld=ld, ca=t.i_need, kh_src=khp, kw_src=kwp)
             if len(tsz) == 3:

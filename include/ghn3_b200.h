@@ -193,6 +193,9 @@ typedef struct {
    * (reference ghn3/nn.py:750,760: x[:, :o, :i]). */
   int32_t b_group;
   int32_t b_group_stride;
+  int32_t bias_rows;         /* 1: bias is indexed by the output ROW (bias[bias_off + m]) instead of the column */
+  int32_t b_dynamic;         /* 1: B is written by an earlier kernel of the same step. By default B is assumed to hold
+                                weights and its first tiles are fetched BEFORE the programmatic-dependent-launch wait. */
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);
@@ -323,10 +326,21 @@ typedef struct {
 
 int ghn3_sumsq(const ghn3_sumsq_args* args, ghn3_stream_t stream);
 
+/* dst[(z*cols + c)][r] = relu(src[z*src_bs + r*ld + c]) converted to dst_dtype, for r < rows, c < cols, z < batch:
+ * turns the (ms x i') prediction block of a classification-weight node into the K-major operand of the class-head
+ * GEMM (reference ghn3/nn.py:757-758: class_layer_predictor = [ReLU, Linear] applied along the out-channel axis). */
+typedef struct {
+  const float* src; int64_t ld; int64_t src_bs;
+  void* dst; int32_t dst_dtype;
+  int32_t rows, cols, batch;
+} ghn3_relu_transpose_args;
+int ghn3_relu_transpose(const ghn3_relu_transpose_args* args, ghn3_stream_t stream);
+
 /* Runs a prebuilt sequence of the entry points above with ONE call (the host side of `ghn(model)` is then a single
  * FFI crossing per prediction): ops[i].args points to the argument struct of the entry point named by ops[i].op. */
 enum ghn3_opcode {
-  GHN3_OP_NODE_FEATURES = 1, GHN3_OP_GRAPHORMER = 2, GHN3_OP_GEMM = 3, GHN3_OP_GEMM_SIMT = 4, GHN3_OP_SCATTER = 5
+  GHN3_OP_NODE_FEATURES = 1, GHN3_OP_GRAPHORMER = 2, GHN3_OP_GEMM = 3, GHN3_OP_GEMM_SIMT = 4, GHN3_OP_SCATTER = 5,
+  GHN3_OP_RELU_TRANSPOSE = 6
 };
 typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
 int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);
