@@ -436,7 +436,8 @@ class _Program:
                 self.ops.append(('dec_conv2', 'gemm',
                                  gemm_args(self.h1, w['c2_w'], w['c2_b'], ops.ACT_NONE, self.wout, ops.F32,
                                            st['c2_%d_problems' % g_], st['c2_%d_tiles' % g_], b_group=g_,
-                                           b_group_stride=ms1 if g_ else 0, block_n=128)))
+                                           b_group_stride=ms1 if g_ else 0,
+                                           block_n=128 if g_ else bp.c2_block_n)))
             bufs[SRC_WOUT] = self.wout
             if bp.clsw_elems:
                 self.clsw = E(bp.clsw_elems, dtype=torch.float32)

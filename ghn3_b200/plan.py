@@ -256,6 +256,8 @@ DESC_DT = np.dtype([('dst', 'u8'), ('src', 'u8'), ('numel', 'i8'), ('chunk0', 'i
 assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 128
 SCATTER_CHUNK = 8192
 SRC_WOUT, SRC_D1, SRC_CLSW, SRC_CLSB, SRC_TOK = 0, 1, 2, 3, 4      # which device buffer a descriptor reads
+import os as _os
+C2_DENSE_BLOCK_N = int(_os.environ.get('GHN3_C2_BLOCK_N', '128'))    # N tile of the dense conv.2 launch
 
 
 def tiles_for(problems, block_m=128, block_n=128):
@@ -359,11 +361,13 @@ class BatchPlan:
         self.fc_problems = np.array(fc_probs, dtype=PROBLEM_DT) if fc_probs else np.zeros(0, PROBLEM_DT)
         self.c2_problems = np.array(c2_probs, dtype=PROBLEM_DT) if c2_probs else np.zeros(0, PROBLEM_DT)
         self.fc_tiles = tiles_for(self.fc_problems)
-        self.c2_tiles = tiles_for(self.c2_problems)
+        self.c2_block_n = C2_DENSE_BLOCK_N
+        self.c2_tiles = tiles_for(self.c2_problems, block_n=self.c2_block_n)
         # order conv2 tiles by weight block so CTAs that run together share the streamed weight rows through L2
         if len(self.c2_tiles):
             pr = self.c2_problems
-            wrow = pr['b_row0'][self.c2_tiles[:, 0]].astype(np.int64) + self.c2_tiles[:, 2].astype(np.int64) * 128
+            wrow = pr['b_row0'][self.c2_tiles[:, 0]].astype(np.int64) + \
+                self.c2_tiles[:, 2].astype(np.int64) * self.c2_block_n
             self.c2_tiles = self.c2_tiles[np.lexsort((self.c2_tiles[:, 1], wrow))]
         # conv.2 launches: (b_group, problems, tiles); b_group 0 = dense rows, g > 0 = compact columns via 3-D boxes
         self.c2_launches = []
