@@ -144,6 +144,7 @@ struct GemmKernelArgs {
   int32_t b_group, b_stride, b_outer;
   int32_t bias_rows;
   int32_t b_dynamic;     // B is produced by an earlier kernel of the step: do not fetch it before pdl_wait()
+  const int32_t* rowmap; // optional: output row of problem row m is rowmap[p.d_off + m] (d_off is then a table offset)
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -346,12 +347,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tmem_ld_wait();
       if (threadIdx.x == 64 && c0 == 0) GHN3_TRACE(2);
       if (rows_valid <= 0) continue;             // warp-uniform
+      // element offset of output row `row` (local to this warp's 32-row slab)
+      auto row_off = [&](int row) -> int64_t {
+        const int m = m_base + row;
+        return args.rowmap ? (int64_t)__ldg(args.rowmap + p.d_off + m) * p.ldd : p.d_off + (int64_t)m * p.ldd;
+      };
       const bool bf16_out = args.out_dtype == GHN3_BF16;
       const bool tf = args.out_dtype == GHN3_TF32;
       const int eb_out = bf16_out ? 2 : 4;
       // fast path: the whole 32-column chunk is inside the problem and every 16-byte piece is aligned
       const bool vec_ok = (n0 + 32 <= n_end) && (((p.ldd * eb_out) & 15) == 0) &&
-                          ((((p.d_off + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
+                          (((((args.rowmap ? 0 : p.d_off) + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
       // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
       float b_lane = 0.f;
       const float b_row = (use_bias && args.bias_rows && lane < rows_valid)
@@ -392,12 +398,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           __syncwarp();
           const int seg = lane & 3, rsub = lane >> 2;          // 4 lanes x 16 B per row, 8 rows per instruction
-          __nv_bfloat16* dbase = (__nv_bfloat16*)args.d + p.d_off + n0 + seg * 8;
+          __nv_bfloat16* dbase = (__nv_bfloat16*)args.d + n0 + seg * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int row = it * 8 + rsub;
             if (row < rows_valid)
-              *(uint4*)(dbase + (int64_t)(m_base + row) * p.ldd) = *(const uint4*)(stage_b + row * RS + 16 * seg);
+              *(uint4*)(dbase + row_off(row)) = *(const uint4*)(stage_b + row * RS + 16 * seg);
           }
         } else {
           constexpr int RS = 128 + 16;
@@ -406,20 +412,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             *(float4*)(stage_b + lane * RS + 16 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           __syncwarp();
           const int seg = lane & 7, rsub = lane >> 3;          // 8 lanes x 16 B per row, 4 rows per instruction
-          float* dbase = (float*)args.d + p.d_off + n0 + seg * 4;
+          float* dbase = (float*)args.d + n0 + seg * 4;
           if (atomic) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + rsub;
               if (row < rows_valid)
-                atomicAdd((float4*)(dbase + (int64_t)(m_base + row) * p.ldd), *(const float4*)(stage_b + row * RS + 16 * seg));
+                atomicAdd((float4*)(dbase + row_off(row)), *(const float4*)(stage_b + row * RS + 16 * seg));
             }
           } else if (args.accumulate) {
             float4 old[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + rsub;
-              if (row < rows_valid) old[it] = *(const float4*)(dbase + (int64_t)(m_base + row) * p.ldd);
+              if (row < rows_valid) old[it] = *(const float4*)(dbase + row_off(row));
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -428,7 +434,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const float4 t = *(const float4*)(stage_b + row * RS + 16 * seg);
                 float4 o = make_float4(old[it].x + t.x, old[it].y + t.y, old[it].z + t.z, old[it].w + t.w);
                 if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                *(float4*)(dbase + (int64_t)(m_base + row) * p.ldd) = o;
+                *(float4*)(dbase + row_off(row)) = o;
               }
             }
           } else {
@@ -436,7 +442,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int it = 0; it < 8; ++it) {
               const int row = it * 4 + rsub;
               if (row < rows_valid)
-                *(float4*)(dbase + (int64_t)(m_base + row) * p.ldd) = *(const float4*)(stage_b + row * RS + 16 * seg);
+                *(float4*)(dbase + row_off(row)) = *(const float4*)(stage_b + row * RS + 16 * seg);
             }
           }
         }
@@ -449,7 +455,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (col < n_end) {
           for (int rr = 0; rr < rows_valid; ++rr) {
             const float t = stage[rr * 33 + lane];
-            const int64_t off = p.d_off + (int64_t)(m_base + rr) * p.ldd + col;
+            const int64_t off = row_off(rr) + col;
             if (bf16_out) {
               ((__nv_bfloat16*)args.d)[off] = __float2bfloat16_rn(t);
             } else if (atomic) {
@@ -669,6 +675,7 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.b_outer = b_outer;
   ka.bias_rows = a->bias_rows;
   ka.b_dynamic = a->b_dynamic;
+  ka.rowmap = a->rowmap;
 
   if (x3) {
     if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);

@@ -327,15 +327,8 @@ class BatchPlan:
                 P = khp * kwp
                 cnt = m - k
                 for q in range(k, m):
-                    b, t = conv[q]
-                    dst_row[offs[b] + t.node] = q
                     self.conv_rows.append((row + (q - k) * P, P, kwp, khp))
                     self.seg_of.append((seg_base + (row + (q - k) * P - seg_row0) * ld, ld))
-                for py in range(khp):
-                    for px in range(kwp):
-                        pos = (y0 + py) * S + (x0 + px)
-                        pl = py * kwp + px
-                        fc_probs.append((k, pos * 4 * C, cnt, 4 * C, (row + pl) * 4 * C, P * 4 * C, pos * 4 * C))
                 if t0.kind == KIND_CLS_W:
                     self.cls_heads.append((seg_base + (row - seg_row0) * ld, ld, ii, cnt, clsw_elems))
                     for q in range(k, m):
@@ -357,6 +350,35 @@ class BatchPlan:
             i = j
         self.conv_total_rows = row
         self.wout_elems = wout_elems
+        # ---- fc stage: ONE problem per decoder-grid position over all nodes whose crop window contains it.
+        # The decoder-input rows (dec_in) are ordered by window, largest first (centred windows are nested, so the
+        # nodes that need a position form a prefix / a few runs); the (node, position)-major h0 rows keep the
+        # class-major order above through a row map.
+        fc_order = sorted(range(len(conv)), key=lambda q: (-(conv[q][1].win[1] - conv[q][1].win[0]) *
+                                                           (conv[q][1].win[3] - conv[q][1].win[2]),
+                                                           conv[q][1].win, q))
+        for r, q in enumerate(fc_order):
+            b, t = conv[q]
+            dst_row[offs[b] + t.node] = r
+        wins = np.array([conv[q][1].win for q in fc_order], dtype=np.int64).reshape(-1, 4)
+        rowmap = []
+        for py in range(S):
+            for px in range(S):
+                if len(wins) == 0:
+                    break
+                need = np.nonzero((wins[:, 0] <= py) & (py < wins[:, 1]) & (wins[:, 2] <= px) & (px < wins[:, 3]))[0]
+                if len(need) == 0:
+                    continue
+                pos = py * S + px
+                breaks = np.nonzero(np.diff(need) != 1)[0] + 1
+                for run in np.split(need, breaks):
+                    fc_probs.append((int(run[0]), pos * 4 * C, len(run), 4 * C, len(rowmap), 4 * C, pos * 4 * C))
+                    for r in run:
+                        q = fc_order[r]
+                        row0, P, kwp, khp = self.conv_rows[q]
+                        y0, _, x0, _ = conv[q][1].win
+                        rowmap.append(row0 + (py - y0) * kwp + (px - x0))
+        self.fc_rowmap = np.asarray(rowmap, dtype=np.int32)
         self.clsw_elems = clsw_elems
         self.fc_problems = np.array(fc_probs, dtype=PROBLEM_DT) if fc_probs else np.zeros(0, PROBLEM_DT)
         self.c2_problems = np.array(c2_probs, dtype=PROBLEM_DT) if c2_probs else np.zeros(0, PROBLEM_DT)

@@ -196,6 +196,10 @@ typedef struct {
   int32_t bias_rows;         /* 1: bias is indexed by the output ROW (bias[bias_off + m]) instead of the column */
   int32_t b_dynamic;         /* 1: B is written by an earlier kernel of the same step. By default B is assumed to hold
                                 weights and its first tiles are fetched BEFORE the programmatic-dependent-launch wait. */
+  const int32_t* rowmap;     /* optional device table (static per plan): row m of a problem is stored to output row
+                                rowmap[problem.d_off + m] instead of d_off / ldd addressing. Lets the decoder's fc
+                                stage run one problem per grid POSITION over all nodes whose crop window contains it
+                                (reference ghn3/nn.py:738-745) while writing the (node, position)-major h0 layout. */
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);

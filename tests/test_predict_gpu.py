@@ -116,8 +116,9 @@ def test_accepts_dense_adj_and_device_batch():
         ghn(m1, g_dense)
         batch = GraphBatch([Graph.from_record(rec)], dense=True).to_device(DEV)
         ghn(m2, batch)
+    # not bit-identical run to run: the split-K residual GEMMs accumulate with fp32 atomics (order varies)
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert torch.equal(p1, p2), n1
+        assert H.max_rel_err(p1, p2) < 1e-4, n1
 
 
 def test_cpu_model_gets_device_params_and_no_cpu_fallback():
