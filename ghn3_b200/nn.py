@@ -554,9 +554,12 @@ class _Program:
             ev.record()
             prof.append((name, ev))
         mark('start')
+        per_op = getattr(prof, 'per_op', False)       # per-launch events (bench.py's roofline leg)
         for i, (stage, name, args) in enumerate(self.ops):
             L.call(name, args, stream)
-            if i + 1 == len(self.ops) or self.ops[i + 1][0] != stage:
+            if per_op:
+                mark('%s#%d' % (stage, i))
+            elif i + 1 == len(self.ops) or self.ops[i + 1][0] != stage:
                 mark(stage)
 
 
