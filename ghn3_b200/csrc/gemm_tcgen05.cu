@@ -12,6 +12,8 @@
 // Two CTAs are resident per SM (3 stages x 32 KB each, 2 x 128 TMEM columns) so one CTA's epilogue overlaps the
 // other's main loop. Rows/columns outside a problem are loaded (TMA zero-fills outside the tensor) and masked at
 // the store; every output element depends only on its own A row and B row, so neighbours' data never leaks in.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ghn3 {
@@ -145,6 +147,7 @@ struct GemmKernelArgs {
   int32_t bias_rows;
   int32_t b_dynamic;     // B is produced by an earlier kernel of the step: do not fetch it before pdl_wait()
   const int32_t* rowmap; // optional: output row of problem row m is rowmap[p.d_off + m] (d_off is then a table offset)
+  int32_t n_tiles;       // grouped launches: length of `tiles` (the persistent kernel strides over it)
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -176,6 +179,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 constexpr int kBlockM = 128;
+constexpr int kStageBlock = 4736;         // per-warp epilogue transposition block: 32 rows x 144 B (+ slack)
+constexpr int kMetaBlock = 256 + 1024;    // per-warp epilogue metadata: 32 row offsets (int64) + 256 column biases
 constexpr int kRowBytes = 128;   // bytes of K per ring stage row = one swizzle span
 
 // kX3: error-compensated tf32 ("3xTF32"): four extra warps split every fp32 tile in shared memory into
@@ -183,10 +188,182 @@ constexpr int kRowBytes = 128;   // bytes of K per ring stage row = one swizzle 
 // kind::tf32 tensor-core instructions, no extra HBM traffic.
 template <bool kX3, int BN, int kStages>
 constexpr int gemm_smem_bytes() {
-  return kStages * (kBlockM + BN) * kRowBytes * (kX3 ? 2 : 1) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return kStages * (kBlockM + BN) * kRowBytes * (kX3 ? 2 : 1) + 4 * kMetaBlock + 1024 /*alignment slack*/ +
+         256 /*barriers*/;
 }
 template <bool kX3>
 constexpr int gemm_threads() { return kX3 ? 320 : 192; }
+
+// Epilogue of one 128 x BN accumulator tile (called by the four epilogue warps, q = warp % 4). tcgen05.ld gives every
+// thread one accumulator ROW (32 columns per chunk). Writing that straight out would scatter 16-byte pieces over 32
+// rows per store instruction (measured: ~half of a small GEMM's run time), so each 32x32 block is transposed through
+// a per-warp shared-memory staging block and stored with lanes along columns: one contiguous 128-byte (fp32) or
+// 64-byte (bf16) row segment per warp instruction.
+// Per-tile epilogue inputs that do not depend on the accumulator (output row offsets through the optional row map,
+// column biases): fetched into the warp's staging block BEFORE waiting for the MMAs, so their global-memory latency
+// overlaps the main loop.
+template <int BN>
+__device__ __forceinline__ void epilogue_prepare(const GemmKernelArgs& args, const ghn3_gemm_problem& p, int mt, int nt,
+                                                 uint8_t* meta, int q, int lane, bool use_bias) {
+  const int m_base = mt * kBlockM + q * 32;
+  const int rows_valid = min(32, p.m - m_base);
+  int64_t* rowoff_s = (int64_t*)meta;
+  float* bias_s = (float*)(rowoff_s + 32);
+  if (lane < rows_valid) {
+    const int m = m_base + lane;
+    rowoff_s[lane] = args.rowmap ? (int64_t)__ldg(args.rowmap + p.d_off + m) * p.ldd : p.d_off + (int64_t)m * p.ldd;
+  }
+  if (rows_valid > 0) {
+    const int tile_n0 = args.b_group > 0 ? args.b_group * args.b_outer : BN;
+    const int n_end0 = min(p.n, (nt + 1) * tile_n0);
+#pragma unroll
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      const int c = nt * tile_n0 + cc * 32 + lane;
+      float bv = 0.f;
+      if (use_bias && !args.bias_rows && c < n_end0) {
+        const int bidx = args.b_group > 0 ? (c / args.b_group) * args.b_stride + c % args.b_group : c;
+        bv = __ldg(args.bias + p.bias_off + bidx);
+      }
+      bias_s[cc * 32 + lane] = bv;
+    }
+  }
+  __syncwarp();
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_store_tile(const GemmKernelArgs& args, const ghn3_gemm_problem& p, int mt,
+                                                    int nt, uint32_t tmem_base, float* stage, const uint8_t* meta,
+                                                    int q, int lane, bool use_bias, bool atomic) {
+  const int m_base = mt * kBlockM + q * 32;
+  const int rows_valid = min(32, p.m - m_base);
+  const int64_t* rowoff_s = (const int64_t*)meta;
+  const float* bias_s = (const float*)(rowoff_s + 32);
+  const int tile_n = args.b_group > 0 ? args.b_group * args.b_outer : BN;   // valid columns of a full tile
+  const int n_end = min(p.n, (nt + 1) * tile_n);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    const int n0 = nt * tile_n + c0;
+    if (n0 >= n_end) break;                    // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (rows_valid <= 0) continue;             // warp-uniform
+    auto row_off = [&](int row) -> int64_t { return rowoff_s[row]; };
+    const bool bf16_out = args.out_dtype == GHN3_BF16;
+    const bool tf = args.out_dtype == GHN3_TF32;
+    const int eb_out = bf16_out ? 2 : 4;
+    // fast path: the whole 32-column chunk is inside the problem and every 16-byte piece is aligned
+    const bool vec_ok = (n0 + 32 <= n_end) && (((p.ldd * eb_out) & 15) == 0) &&
+                        (((((args.rowmap ? 0 : p.d_off) + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
+    // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
+    const float b_lane = bias_s[c0 + lane];
+    const float b_row = (use_bias && args.bias_rows && lane < rows_valid)
+                            ? __ldg(args.bias + p.bias_off + m_base + lane) : 0.f;
+    float v[32];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj) + b_row;
+    // the activation is selected ONCE per chunk (a per-element runtime test gets if-converted and the erf
+    // polynomial would issue, predicated off, for every element of every GEMM)
+    if (!args.accumulate) {
+      if (args.act == GHN3_ACT_GELU) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = 0.5f * v[jj] * (1.f + erff(v[jj] * 0.70710678118654752440f));
+      } else if (args.act == GHN3_ACT_RELU) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+      }
+      if (tf) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = round_tf32(v[jj]);
+      }
+    }
+    if (vec_ok) {
+      uint8_t* stage_b = (uint8_t*)stage;      // per-warp block of 32 rows x (row bytes + 16)
+      if (bf16_out) {
+        constexpr int RS = 64 + 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+          pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+          *(uint4*)(stage_b + lane * RS + 16 * c) = pk;
+        }
+        __syncwarp();
+        const int seg = lane & 3, rsub = lane >> 2;          // 4 lanes x 16 B per row, 8 rows per instruction
+        __nv_bfloat16* dbase = (__nv_bfloat16*)args.d + n0 + seg * 8;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + rsub;
+          if (row < rows_valid)
+            *(uint4*)(dbase + row_off(row)) = *(const uint4*)(stage_b + row * RS + 16 * seg);
+        }
+      } else {
+        constexpr int RS = 128 + 16;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *(float4*)(stage_b + lane * RS + 16 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        const int seg = lane & 7, rsub = lane >> 3;          // 8 lanes x 16 B per row, 4 rows per instruction
+        float* dbase = (float*)args.d + n0 + seg * 4;
+        if (atomic) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rsub;
+            if (row < rows_valid)
+              atomicAdd((float4*)(dbase + row_off(row)), *(const float4*)(stage_b + row * RS + 16 * seg));
+          }
+        } else if (args.accumulate) {
+          float4 old[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rsub;
+            if (row < rows_valid) old[it] = *(const float4*)(dbase + row_off(row));
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rsub;
+            if (row < rows_valid) {
+              const float4 t = *(const float4*)(stage_b + row * RS + 16 * seg);
+              float4 o = make_float4(old[it].x + t.x, old[it].y + t.y, old[it].z + t.z, old[it].w + t.w);
+              if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              *(float4*)(dbase + row_off(row)) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rsub;
+            if (row < rows_valid)
+              *(float4*)(dbase + row_off(row)) = *(const float4*)(stage_b + row * RS + 16 * seg);
+          }
+        }
+      }
+    } else {
+      // general path (ragged column edge or unaligned output): lanes along columns, one element each
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) stage[lane * 33 + jj] = v[jj];
+      __syncwarp();
+      const int col = n0 + lane;
+      if (col < n_end) {
+        for (int rr = 0; rr < rows_valid; ++rr) {
+          const float t = stage[rr * 33 + lane];
+          const int64_t off = row_off(rr) + col;
+          if (bf16_out) {
+            ((__nv_bfloat16*)args.d)[off] = __float2bfloat16_rn(t);
+          } else if (atomic) {
+            atomicAdd((float*)args.d + off, t);
+          } else if (args.accumulate) {
+            const float o = ((float*)args.d)[off] + t;
+            ((float*)args.d)[off] = tf ? round_tf32(o) : o;
+          } else {
+            ((float*)args.d)[off] = t;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 template <bool kTf32, bool kX3, int BN, int kStages>
 __global__ void __launch_bounds__(gemm_threads<kX3>(), (2 * gemm_smem_bytes<kX3, BN, kStages>() <= 227 * 1024) ? 2 : 1)
@@ -206,7 +383,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t sB = sA + kStages * A_BYTES;
   const uint32_t sAlo = sB + kStages * B_BYTES;                     // only used when kX3
   const uint32_t sBlo = sAlo + (kX3 ? kStages * A_BYTES : 0);
-  const uint32_t bar_base = sBlo + (kX3 ? kStages * B_BYTES : 0);   // 8-byte aligned
+  const uint32_t sMeta = sBlo + (kX3 ? kStages * B_BYTES : 0);      // epilogue metadata (never aliases the ring)
+  const uint32_t bar_base = sMeta + 4 * kMetaBlock;                 // 8-byte aligned
   const uint32_t full_bar = bar_base;                                // kStages barriers each
   const uint32_t empty_bar = bar_base + 8 * kStages;
   const uint32_t split_bar = bar_base + 16 * kStages;
@@ -321,157 +499,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       GHN3_TRACE(5);
     }
   } else if (warp < 6) {
-    // Epilogue. Warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32): tcgen05.ld gives every thread one
-    // accumulator ROW (32 columns). Writing that straight out would scatter 16-byte pieces over 32 rows per store
-    // instruction (measured: ~half of a small GEMM's run time), so each 32x32 block is transposed through shared
-    // memory (the operand ring is idle once the accumulator is complete) and stored with lanes along columns:
-    // one contiguous 128-byte (fp32) or 64-byte (bf16) row segment per warp instruction.
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the operand ring is idle once the
+    // accumulator is complete, so its first bytes serve as the staging blocks
     const int q = warp & 3;
-    const int m_base = mt * kBlockM + q * 32;
-    const int rows_valid = min(32, p.m - m_base);
     const bool atomic = args.k_splits > 1 && args.tiles == nullptr;
     const bool use_bias = p.bias_off >= 0 && first_split;
-    float* stage = (float*)(smem_raw + (sA - smem_u32(smem_raw)) + q * 4736);   // >= 32*144 B and 32*33*4 B, 16B aligned
+    float* stage = (float*)(smem_raw + (sA - smem_u32(smem_raw)) + q * kStageBlock);
+    uint8_t* meta = smem_raw + (sMeta - smem_u32(smem_raw)) + q * kMetaBlock;
+    epilogue_prepare<BN>(args, p, mt, nt, meta, q, lane, use_bias);    // static tables only: legal before pdl_wait
+    if (threadIdx.x == 128) GHN3_TRACE(2);
     pdl_wait();                                  // the epilogue reads / writes buffers of earlier kernels
     mbar_wait(tmem_full_bar, 0);
-    if (threadIdx.x == 64) GHN3_TRACE(6);
+    if (threadIdx.x == 128) GHN3_TRACE(6);
     tcgen05_fence_after();
-    const int tile_n = args.b_group > 0 ? args.b_group * args.b_outer : BN;   // valid columns of a full tile
-    const int n_end = min(p.n, (nt + 1) * tile_n);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      const int n0 = nt * tile_n + c0;
-      if (n0 >= n_end) break;                    // warp-uniform
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (threadIdx.x == 64 && c0 == 0) GHN3_TRACE(2);
-      if (rows_valid <= 0) continue;             // warp-uniform
-      // element offset of output row `row` (local to this warp's 32-row slab)
-      auto row_off = [&](int row) -> int64_t {
-        const int m = m_base + row;
-        return args.rowmap ? (int64_t)__ldg(args.rowmap + p.d_off + m) * p.ldd : p.d_off + (int64_t)m * p.ldd;
-      };
-      const bool bf16_out = args.out_dtype == GHN3_BF16;
-      const bool tf = args.out_dtype == GHN3_TF32;
-      const int eb_out = bf16_out ? 2 : 4;
-      // fast path: the whole 32-column chunk is inside the problem and every 16-byte piece is aligned
-      const bool vec_ok = (n0 + 32 <= n_end) && (((p.ldd * eb_out) & 15) == 0) &&
-                          (((((args.rowmap ? 0 : p.d_off) + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
-      // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
-      float b_lane = 0.f;
-      const float b_row = (use_bias && args.bias_rows && lane < rows_valid)
-                              ? __ldg(args.bias + p.bias_off + m_base + lane) : 0.f;
-      if (use_bias && !args.bias_rows && n0 + lane < n_end) {
-        const int c = n0 + lane;
-        const int bidx = args.b_group > 0 ? (c / args.b_group) * args.b_stride + c % args.b_group : c;
-        b_lane = __ldg(args.bias + p.bias_off + bidx);
-      }
-      float v[32];
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj) + b_row;
-      // the activation is selected ONCE per chunk (a per-element runtime test gets if-converted and the erf
-      // polynomial would issue, predicated off, for every element of every GEMM)
-      if (!args.accumulate) {
-        if (args.act == GHN3_ACT_GELU) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = 0.5f * v[jj] * (1.f + erff(v[jj] * 0.70710678118654752440f));
-        } else if (args.act == GHN3_ACT_RELU) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.f);
-        }
-        if (tf) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = round_tf32(v[jj]);
-        }
-      }
-      if (vec_ok) {
-        uint8_t* stage_b = (uint8_t*)stage;      // per-warp block of 32 rows x (row bytes + 16)
-        if (bf16_out) {
-          constexpr int RS = 64 + 16;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-            pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-            *(uint4*)(stage_b + lane * RS + 16 * c) = pk;
-          }
-          __syncwarp();
-          const int seg = lane & 3, rsub = lane >> 2;          // 4 lanes x 16 B per row, 8 rows per instruction
-          __nv_bfloat16* dbase = (__nv_bfloat16*)args.d + n0 + seg * 8;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int row = it * 8 + rsub;
-            if (row < rows_valid)
-              *(uint4*)(dbase + row_off(row)) = *(const uint4*)(stage_b + row * RS + 16 * seg);
-          }
-        } else {
-          constexpr int RS = 128 + 16;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *(float4*)(stage_b + lane * RS + 16 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          __syncwarp();
-          const int seg = lane & 7, rsub = lane >> 3;          // 8 lanes x 16 B per row, 4 rows per instruction
-          float* dbase = (float*)args.d + n0 + seg * 4;
-          if (atomic) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + rsub;
-              if (row < rows_valid)
-                atomicAdd((float4*)(dbase + row_off(row)), *(const float4*)(stage_b + row * RS + 16 * seg));
-            }
-          } else if (args.accumulate) {
-            float4 old[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + rsub;
-              if (row < rows_valid) old[it] = *(const float4*)(dbase + row_off(row));
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + rsub;
-              if (row < rows_valid) {
-                const float4 t = *(const float4*)(stage_b + row * RS + 16 * seg);
-                float4 o = make_float4(old[it].x + t.x, old[it].y + t.y, old[it].z + t.z, old[it].w + t.w);
-                if (tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                *(float4*)(dbase + row_off(row)) = o;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + rsub;
-              if (row < rows_valid)
-                *(float4*)(dbase + row_off(row)) = *(const float4*)(stage_b + row * RS + 16 * seg);
-            }
-          }
-        }
-      } else {
-        // general path (ragged column edge or unaligned output): lanes along columns, one element each
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) stage[lane * 33 + jj] = v[jj];
-        __syncwarp();
-        const int col = n0 + lane;
-        if (col < n_end) {
-          for (int rr = 0; rr < rows_valid; ++rr) {
-            const float t = stage[rr * 33 + lane];
-            const int64_t off = row_off(rr) + col;
-            if (bf16_out) {
-              ((__nv_bfloat16*)args.d)[off] = __float2bfloat16_rn(t);
-            } else if (atomic) {
-              atomicAdd((float*)args.d + off, t);
-            } else if (args.accumulate) {
-              const float o = ((float*)args.d)[off] + t;
-              ((float*)args.d)[off] = tf ? round_tf32(o) : o;
-            } else {
-              ((float*)args.d)[off] = t;
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-    if (threadIdx.x == 64) GHN3_TRACE(3);
+    epilogue_store_tile<BN>(args, p, mt, nt, tmem_base, stage, meta, q, lane, use_bias, atomic);
+    if (threadIdx.x == 128) GHN3_TRACE(3);
   } else {
     // kX3 only: warps 6..9 split each landed fp32 tile into hi (in place) and lo (second buffer)
     if constexpr (kX3) {
@@ -511,6 +553,168 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for grouped (decoder) launches: one CTA per SM walks the tile list with stride gridDim.x.
+// The TMA producer runs ahead across tile boundaries (the ring never drains), the accumulator is double-buffered in
+// TMEM (2 x BN columns) so the MMA warp starts tile j+1 while the epilogue warps are still storing tile j. This is
+// what a weight-streaming GEMM needs to stay at HBM speed: per-tile prologue / epilogue bubbles disappear.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStagingBytes = 4 * (kStageBlock + kMetaBlock);
+
+template <int BN, int kStages>
+constexpr int gemm_persistent_smem_bytes() {
+  return kStages * (kBlockM + BN) * kRowBytes + kStagingBytes + 1024 + 256;
+}
+
+template <bool kTf32, int BN, int kStages>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                               const GemmKernelArgs args) {
+  constexpr int EB = kTf32 ? 4 : 2;
+  constexpr int BK = kRowBytes / EB;
+  constexpr int kMmaPerStage = 4;
+  constexpr uint32_t A_BYTES = kBlockM * kRowBytes;
+  constexpr uint32_t B_BYTES = BN * kRowBytes;
+  constexpr uint32_t kIdesc = make_idesc(kTf32, kBlockM, BN);
+  static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + kStages * A_BYTES;
+  const uint32_t sStage = sB + kStages * B_BYTES;
+  const uint32_t bar_base = sStage + kStagingBytes;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8 * kStages;
+  const uint32_t tmem_full_bar = bar_base + 16 * kStages;        // 2 barriers
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;            // 2 barriers
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
+  uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (args.k + BK - 1) / BK;
+  const int n_tiles = args.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar + 8 * b, 1);
+      mbar_init(tmem_empty_bar + 8 * b, 4);      // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t b_bytes = args.b_group > 0 ? (uint32_t)(args.b_group * args.b_outer * kRowBytes) : B_BYTES;
+      bool waited = false;
+      uint32_t it = 0;
+      int4 tile_next = make_int4(0, 0, 0, 0);
+      ghn3_gemm_problem p_next = {};
+      if ((int)blockIdx.x < n_tiles) {
+        tile_next = args.tiles[blockIdx.x];
+        p_next = args.problems[tile_next.x];
+      }
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int4 tile = tile_next;
+        const ghn3_gemm_problem p = p_next;
+        if (t + (int)gridDim.x < n_tiles) {
+          tile_next = args.tiles[t + gridDim.x];
+          p_next = args.problems[tile_next.x];
+        }
+        const int a_row = p.a_row0 + tile.y * kBlockM;
+        const int b_row = p.b_row0 + tile.z * (args.b_group > 0 ? args.b_outer : BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + b_bytes);
+          if (args.b_dynamic && !waited) { pdl_wait(); waited = true; }
+          if (args.b_group > 0) tma_load_3d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, 0, b_row);
+          else tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, b_row);
+          if (!waited) { pdl_wait(); waited = true; }        // weights first, then wait for the activations
+          tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, kb * BK, a_row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int j = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+        const int ab = j & 1;
+        mbar_wait(tmem_empty_bar + 8 * ab, (uint32_t)(((j >> 1) & 1) ^ 1));     // epilogue has drained this buffer
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc(sA + s * A_BYTES);
+          const uint64_t db = make_smem_desc(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < kMmaPerStage; ++k)
+            umma<kTf32>(acc, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          tcgen05_commit(empty_bar + 8 * s);
+        }
+        tcgen05_commit(tmem_full_bar + 8 * ab);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stage = (float*)(smem_raw + (sStage - smem_u32(smem_raw)) + q * kStageBlock);
+    uint8_t* meta = smem_raw + (sStage - smem_u32(smem_raw)) + 4 * kStageBlock + q * kMetaBlock;
+    pdl_wait();
+    int j = 0;
+    int4 tile_next = make_int4(0, 0, 0, 0);
+    ghn3_gemm_problem p_next = {};
+    if ((int)blockIdx.x < n_tiles) {
+      tile_next = args.tiles[blockIdx.x];
+      p_next = args.problems[tile_next.x];
+    }
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+      const int4 tile = tile_next;
+      const ghn3_gemm_problem p = p_next;
+      if (t + (int)gridDim.x < n_tiles) {                 // descriptor of the next tile: latency hidden by this tile
+        tile_next = args.tiles[t + gridDim.x];
+        p_next = args.problems[tile_next.x];
+      }
+      const int ab = j & 1;
+      epilogue_prepare<BN>(args, p, tile.y, tile.z, meta, q, lane, p.bias_off >= 0);
+      mbar_wait(tmem_full_bar + 8 * ab, (uint32_t)((j >> 1) & 1));
+      tcgen05_fence_after();
+      epilogue_store_tile<BN>(args, p, tile.y, tile.z, tmem_base + (uint32_t)(ab * BN), stage, meta, q, lane,
+                              p.bias_off >= 0, false);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * ab);
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -601,6 +805,24 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmK
 static long long* g_gemm_trace = nullptr;
 void set_gemm_trace(long long* p) { g_gemm_trace = p; }
 
+template <bool kTf32, int BN, int kStages>
+static int launch_gemm_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelArgs& ka, int n_tiles,
+                                  cudaStream_t stream) {
+  constexpr int smem = gemm_persistent_smem_bytes<BN, kStages>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const dim3 grid((unsigned)std::min(n_tiles, num_sms()));
+  GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages>, grid, dim3(192), (size_t)smem, stream, ma, mb,
+                       ka));
+  GHN3_LAUNCH_CHECK("gemm_tcgen05_persistent_kernel");
+  return GHN3_OK;
+}
+
 int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_gemm: null args");
   GHN3_REQUIRE(a->in_dtype == GHN3_BF16 || a->in_dtype == GHN3_TF32, "ghn3_gemm: in_dtype must be BF16 or TF32");
@@ -676,6 +898,14 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.bias_rows = a->bias_rows;
   ka.b_dynamic = a->b_dynamic;
   ka.rowmap = a->rowmap;
+  ka.n_tiles = a->n_tiles;
+
+  // grouped launches with enough tiles run on the persistent kernel (one CTA per SM, double-buffered accumulator)
+  static const bool no_persistent = getenv("GHN3_NO_PERSISTENT") != nullptr;
+  if (a->problems != nullptr && !x3 && bn == 128 && a->n_tiles >= 2 * num_sms() && !no_persistent) {
+    if (tf32) return launch_gemm_persistent<true, 128, 5>(ma, mb, ka, a->n_tiles, stream);
+    return launch_gemm_persistent<false, 128, 5>(ma, mb, ka, a->n_tiles, stream);
+  }
 
   if (x3) {
     if (bn == 64) return launch_gemm<true, true, 64, 4>(ma, mb, ka, grid, stream);

@@ -433,3 +433,43 @@ def test_gemm_simt_skinny_rows():
     ops.gemm_simt(a, k, 1, w, k, 1, bias, out, n, 1, m=m, n=n, k=k, relu_a=True)
     torch.cuda.synchronize()
     assert _rel(out, torch.relu(a) @ w.t() + bias) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', [ops.BF16, ops.TF32])
+def test_gemm_grouped_persistent_many_tiles(dtype):
+    """Enough tiles (>= 2 per SM) to take the persistent kernel: double-buffered TMEM, ring across tile boundaries."""
+    torch.manual_seed(11)
+    K = 512
+    n_prob = 40
+    rng = np.random.default_rng(0)
+    a = torch.randn(3000, K, device=DEV)
+    b = torch.randn(4096, K, device=DEV) / K ** 0.5
+    bias = torch.randn(4096, device=DEV)
+    a_in, b_in = (a.bfloat16(), b.bfloat16()) if dtype == ops.BF16 else (ops.convert(a, ops.TF32), ops.convert(b, ops.TF32))
+    probs = np.zeros(n_prob, dtype=[('a_row0', 'i4'), ('b_row0', 'i4'), ('m', 'i4'), ('n', 'i4'), ('d_off', 'i8'),
+                                    ('ldd', 'i4'), ('bias_off', 'i4')])
+    tiles, off, specs = [], 0, []
+    for p in range(n_prob):
+        m = int(rng.integers(1, 400)); n = int(rng.integers(1, 700))
+        a0 = int(rng.integers(0, 3000 - m)); b0 = int(rng.integers(0, 4096 - n))
+        ldd = n + int(rng.integers(0, 9))
+        probs[p] = (a0, b0, m, n, off, ldd, b0 if p % 2 == 0 else -1)
+        specs.append((a0, b0, m, n, off, ldd, p % 2 == 0))
+        off += m * ldd
+        for mt in range((m + 127) // 128):
+            for nt in range((n + 127) // 128):
+                tiles.append((p, mt, nt, 0))
+    assert len(tiles) >= 2 * 148
+    out = torch.full((off,), 3.0, device=DEV)
+    ops.gemm(a_in, b_in, bias=bias, act=ops.ACT_RELU, in_dtype=dtype, out=out, out_dtype=ops.F32,
+             problems=torch.from_numpy(probs.view(np.uint8).copy()).to(DEV),
+             tiles=torch.tensor(tiles, dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    for (a0, b0, m, n, o, ldd, hb) in specs:
+        ref = a_in[a0:a0 + m].double() @ b_in[b0:b0 + n].double().t()
+        if hb:
+            ref = ref + bias[b0:b0 + n].double()
+        ref = torch.relu(ref).float()
+        got = out[o:o + m * ldd].view(m, ldd)
+        assert _rel(got[:, :n], ref) < 2e-5
+        assert bool((got[:, n:] == 3.0).all())          # padding columns untouched

@@ -31,3 +31,17 @@ with torch.no_grad():
     print('full forward        %.3f ms' % T(lambda: ghn(models, batch), 100))
     print('GraphBatch+to_dev   %.3f ms' % T(lambda: GraphBatch(graphs, dense=True).to_device(dev)))
     print('param_norm x2       %.3f ms' % T(lambda: [param_norm(m) for m in models]))
+    # true host cost of the C sequence: GPU idle before every call, do not wait for completion
+    import time as _t
+    tt = 0.0
+    for _ in range(50):
+        torch.cuda.synchronize(); t0 = _t.perf_counter(); prog.run(None); tt += _t.perf_counter() - t0
+    torch.cuda.synchronize()
+    print('run() host-only     %.3f ms' % (tt / 50 * 1e3))
+    x = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    for name, fn in (('memset 1GiB', lambda: x.zero_()), ('copy 0.5GiB', lambda: x[:1 << 29].copy_(x[1 << 29:]))):
+        for _ in range(3): fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); [fn() for _ in range(10)]; e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print('%s: %.3f ms -> %.0f GB/s' % (name, ms, (1 << 30) / ms / 1e6))
