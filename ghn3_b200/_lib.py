@@ -86,7 +86,8 @@ class ScatterDesc(C.Structure):
     _fields_ = [('dst', vp), ('src', vp), ('numel', i64), ('chunk0', i64), ('t1', i32), ('t2', i32), ('t3', i32),
                 ('so', i32), ('si', i32), ('ld', i32), ('ca', i32), ('ra', i32), ('kh_src', i32), ('kw_src', i32),
                 ('cy', i32), ('cx', i32), ('scale', f32), ('mode', i32)] + \
-               [(n_, C.c_uint32) for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')]
+               [(n_, C.c_uint32) for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')] + \
+               [('norm_slot', i32), ('reserved', i32)]
 
 
 def fastdiv(d):
@@ -110,7 +111,8 @@ def fill_fastdiv(desc):
 
 
 class ScatterArgs(C.Structure):
-    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp)]
+    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp), ('norm_out', vp),
+                ('n_norm_slots', i32)]
 
 
 class ReluTransposeArgs(C.Structure):
@@ -126,7 +128,7 @@ class SumsqArgs(C.Structure):
     _fields_ = [('ptrs', vp), ('numels', vp), ('n', i32), ('out', vp)]
 
 
-assert C.sizeof(ScatterDesc) == 128 and C.sizeof(GemmProblem) == 32
+assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',

@@ -41,8 +41,22 @@ __device__ __forceinline__ float fetch_bilinear(const ghn3_scatter_desc& d, int 
 // One CTA per 4096-element chunk of one target tensor; a thread handles 4 consecutive target elements per step
 // (one 16-byte store), 4 steps. All index arithmetic is 32-bit with multiply-high divisions; the descriptor lives in
 // registers.
+__device__ __forceinline__ void block_sumsq(float acc, double* out) {
+  __shared__ float part[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(out, (double)t);
+  }
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(const ghn3_scatter_desc* __restrict__ descs, int n_descs,
-                                                      const int32_t* __restrict__ chunk_desc) {
+                                                      const int32_t* __restrict__ chunk_desc,
+                                                      double* __restrict__ norm_out) {
   int di;
   if (chunk_desc != nullptr) {
     di = __ldg(chunk_desc + blockIdx.x);               // host-built chunk -> descriptor table: one load
@@ -67,6 +81,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ghn3_scatter_desc* _
   const int hw = d.t2 * d.t3;
   const int mode = d.mode;
   const float scale = d.scale;
+  const bool want_norm = norm_out != nullptr && d.norm_slot >= 0;
+  float sq = 0.f;
 
   if (hw == 1 && mode != 3) {
     // matrices and vectors: row `a` = e / t1, column b = e % t1
@@ -92,6 +108,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ghn3_scatter_desc* _
         float4 o;
         o.x = finish(v.x, mode, scale); o.y = finish(v.y, mode, scale);
         o.z = finish(v.z, mode, scale); o.w = finish(v.w, mode, scale);
+        sq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
         __stcs((float4*)(d.dst + e), o);
       } else {
         float o[4];
@@ -108,10 +125,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ghn3_scatter_desc* _
             }
           }
         }
+        for (int i = 0; i < cnt; ++i) sq += o[i] * o[i];
         if (cnt == 4 && dst_vec) __stcs((float4*)(d.dst + e), make_float4(o[0], o[1], o[2], o[3]));
         else for (int i = 0; i < cnt; ++i) d.dst[e + i] = o[i];
       }
     }
+    if (want_norm) block_sumsq(sq, norm_out + d.norm_slot);
     return;
   }
 
@@ -155,9 +174,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ghn3_scatter_desc* _
         }
       }
     }
+    for (int i = 0; i < cnt; ++i) sq += o[i] * o[i];
     if (cnt == 4 && dst_vec) __stcs((float4*)(d.dst + e), make_float4(o[0], o[1], o[2], o[3]));
     else for (int i = 0; i < cnt; ++i) d.dst[e + i] = o[i];
   }
+  if (want_norm) block_sumsq(sq, norm_out + d.norm_slot);
 }
 
 // sum of squares over a list of tensors: grid.y = tensor, grid.x strides over its elements
@@ -190,10 +211,12 @@ using namespace ghn3;
 extern "C" int ghn3_scatter(const ghn3_scatter_args* a, ghn3_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHN3_REQUIRE(a != nullptr, "ghn3_scatter: null args");
-  static_assert(sizeof(ghn3_scatter_desc) == 128, "descriptor layout is part of the ABI");
+  static_assert(sizeof(ghn3_scatter_desc) == 136, "descriptor layout is part of the ABI");
   if (a->n_descs <= 0 || a->n_chunks <= 0) return GHN3_OK;
   GHN3_REQUIRE(a->n_chunks < (int64_t)2147483647, "ghn3_scatter: too many chunks");
-  scatter_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(a->descs, a->n_descs, a->chunk_desc);
+  if (a->norm_out != nullptr && a->n_norm_slots > 0)
+    GHN3_CUDA(cudaMemsetAsync(a->norm_out, 0, sizeof(double) * a->n_norm_slots, stream));
+  scatter_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(a->descs, a->n_descs, a->chunk_desc, a->norm_out);
   GHN3_LAUNCH_CHECK("scatter_kernel");
   return GHN3_OK;
 }

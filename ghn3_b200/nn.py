@@ -369,7 +369,47 @@ class GHN3(GHN):
             # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
             prog.tok.normal_(mean=0.0, std=0.02)
         prog.run(prof)
+        self.last_program = prog
         return prog.emb
+
+    def param_norms(self, nets):
+        """Total L2 norm of each network's parameters after the last forward call (the reference's norm_check metric,
+        nn.py:783-797) as a float64 device tensor [n_models], without re-reading the predicted tensors: their sum of
+        squares comes from the scatter kernel; only the (few, small) parameters the GHN does not predict are read."""
+        prog = self.last_program
+        nets = list(nets) if isinstance(nets, (list, tuple)) else [nets]
+        cache = prog.__dict__.setdefault('_unpred', None)
+        if cache is None:
+            written = {(id(m), a) for (m, a, _, _) in prog.bp.desc_targets}
+            cache = []
+            for net in nets:
+                rest = []
+                for mod in net.modules():
+                    for a, p in mod._parameters.items():
+                        if p is not None and (id(mod), a) not in written:
+                            rest.append(p)
+                cache.append(rest)
+            prog._unpred = cache
+            prog._unpred_out = torch.zeros(len(nets), dtype=torch.float64, device=prog.device)
+            prog._unpred_meta = [None] * len(nets)
+        out = prog._unpred_out
+        for i, rest in enumerate(cache):
+            if not rest:
+                continue
+            ptrs = [p.data_ptr() for p in rest]
+            meta = prog._unpred_meta[i]
+            if meta is None or meta[0] != ptrs:
+                arr = torch.from_numpy(np.array([ptrs, [p.numel() for p in rest]], dtype=np.int64)).to(prog.device)
+                meta = (ptrs, arr, L.SumsqArgs(ptrs=arr[0].data_ptr(), numels=arr[1].data_ptr(), n=len(rest)))
+                prog._unpred_meta[i] = meta
+            meta[2].out = out[i:i + 1].data_ptr()
+            L.call('sumsq', meta[2], L.current_stream())
+        return (prog.pred_sumsq + out).sqrt_()
+
+    def predicted_sumsq(self):
+        """Device tensor [n_models] (float64): sum of squares of every parameter value written by the last forward
+        call, accumulated inside the scatter kernel (no second pass over the parameters, no host sync)."""
+        return self.last_program.pred_sumsq
 
 
 class _Program:
@@ -487,8 +527,10 @@ class _Program:
         self.desc_dev = torch.empty(max(n, 1) * self.desc_host.dtype.itemsize, dtype=torch.uint8, device=device)
         self.last_ptrs = None
         if n:
+            self.pred_sumsq = torch.zeros(len(bp.plans), dtype=torch.float64, device=device)
             self.sc = L.ScatterArgs(descs=L.ptr(self.desc_dev), n_descs=n, n_chunks=bp.n_chunks,
-                                    chunk_desc=L.ptr(st['chunk_desc']))
+                                    chunk_desc=L.ptr(st['chunk_desc']), norm_out=L.ptr(self.pred_sumsq),
+                                    n_norm_slots=len(bp.plans))
             self.ops.append(('scatter', 'scatter', self.sc))
         # flat op table for ghn3_run_sequence
         self.seq = (L.SeqOp * len(self.ops))()

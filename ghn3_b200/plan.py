@@ -252,8 +252,9 @@ PROBLEM_DT = np.dtype([('a_row0', 'i4'), ('b_row0', 'i4'), ('m', 'i4'), ('n', 'i
 DESC_DT = np.dtype([('dst', 'u8'), ('src', 'u8'), ('numel', 'i8'), ('chunk0', 'i8'), ('t1', 'i4'), ('t2', 'i4'),
                     ('t3', 'i4'), ('so', 'i4'), ('si', 'i4'), ('ld', 'i4'), ('ca', 'i4'), ('ra', 'i4'),
                     ('kh_src', 'i4'), ('kw_src', 'i4'), ('cy', 'i4'), ('cx', 'i4'), ('scale', 'f4'), ('mode', 'i4')] +
-                   [(n_, 'u4') for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')])
-assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 128
+                   [(n_, 'u4') for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')] +
+                   [('norm_slot', 'i4'), ('reserved', 'i4')])
+assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 136
 SCATTER_CHUNK = 8192
 SRC_WOUT, SRC_D1, SRC_CLSW, SRC_CLSB, SRC_TOK = 0, 1, 2, 3, 4      # which device buffer a descriptor reads
 import os as _os
@@ -418,10 +419,13 @@ class BatchPlan:
         recs, targets, srcs = [], [], []
         self.n_tok_elems = 0
 
+        cur_model = [0]
+
         def add(module, attr, shape, src_buf, src_off, **f):
             numel = int(np.prod(shape))
             d = np.zeros((), dtype=DESC_DT)
             d['numel'] = numel
+            d['norm_slot'] = cur_model[0]
             for k_, v in dict(t1=1, t2=1, t3=1, so=1, si=1, ld=0, ca=0, ra=0, kh_src=1, kw_src=1, cy=0, cx=0,
                               scale=1.0, mode=0).items():
                 d[k_] = f.get(k_, v)
@@ -436,6 +440,7 @@ class BatchPlan:
 
         for q, (b, t) in enumerate(self.conv):
             e = t.entry
+            cur_model[0] = b
             mod, tsz = e['module'], e['sz']
             attr = param_attr(mod, e['is_w'])
             base, ld = self.seg_of[q]
@@ -475,6 +480,7 @@ class BatchPlan:
         n_plain = self.n_1d - self.n_clsb
         for r, (b, t) in enumerate(self.one_d):
             e = t.entry
+            cur_model[0] = b
             mod, tsz, is_w = e['module'], e['sz'], e['is_w']
             if t.kind == KIND_CLS_B:
                 # bias_class output [(node, row)][classes], row 1 (nn.py:294,317)

@@ -307,7 +307,9 @@ typedef struct {
   /* multiply-high division constants for d in {t1, t2, t3, so, si}: d == 1 -> m = 0; else with s = ceil(log2 d):
    * m = ceil(2^(31+s) / d), shift = s - 1; n / d == umulhi(n, m) >> shift for every n < 2^31 */
   uint32_t m_t1, s_t1, m_t2, s_t2, m_t3, s_t3, m_so, s_so, m_si, s_si;
-} ghn3_scatter_desc;       /* 128 bytes; numel < 2^31 */
+  int32_t norm_slot;     /* >= 0: the sum of squares of the written values is added to norm_out[norm_slot] */
+  int32_t reserved;
+} ghn3_scatter_desc;       /* 136 bytes; numel < 2^31 */
 
 #define GHN3_SCATTER_CHUNK 8192
 
@@ -316,6 +318,9 @@ typedef struct {
   int32_t n_descs;
   int64_t n_chunks;
   const int32_t* chunk_desc;        /* optional device [n_chunks]: descriptor index of every chunk (else binary search) */
+  double* norm_out;                 /* optional device [n_norm_slots]: zeroed, then receives sum(v^2) per norm_slot
+                                       (the norm_check metric of ghn3/nn.py:783-797 without re-reading the parameters) */
+  int32_t n_norm_slots;
 } ghn3_scatter_args;
 
 int ghn3_scatter(const ghn3_scatter_args* args, ghn3_stream_t stream);

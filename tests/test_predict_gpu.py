@@ -102,6 +102,8 @@ def test_param_count_matched_and_norm():
     n = param_norm(model).item()
     ref = torch.norm(torch.stack([p.norm() for p in model.parameters()]), 2).item()
     assert abs(n - ref) / ref < 1e-5
+    n2 = ghn.param_norms(model)[0].item()          # accumulated inside the scatter kernel
+    assert abs(n2 - ref) / ref < 1e-5
 
 
 def test_accepts_dense_adj_and_device_batch():
