@@ -119,6 +119,9 @@ class Graph:
         return self.n_nodes
 
 
+_PACK_CACHE = {}      # (graph ids, cutoff, device) -> (graphs, GraphPack): host-side packing is done once per batch
+
+
 def _norm_device(device):
     device = torch.device(device)
     if device.type == 'cuda' and device.index is None:
@@ -173,6 +176,15 @@ class GraphBatch:
         if len(cutoffs) > 1:
             raise RuntimeError('all graphs of a batch must use the same ve_cutoff')
         cutoff = cutoffs.pop() if cutoffs else 50
+        key = (tuple(id(g) for g in self.graphs), cutoff, str(device))
+        cached = _PACK_CACHE.get(key)
+        if cached is not None and all(a is b for a, b in zip(cached[0], self.graphs)):
+            # same (immutable) Graph objects as an earlier batch: reuse the packed host layout, repeat only the
+            # H2D copy and the kernels
+            self.pack = cached[1].clone_for_upload(device)
+            self.pack.build()
+            self.device = device
+            return self
         op = np.concatenate([g.node_feat[:, 0].numpy() for g in self.graphs]).astype(np.int32)
         if all(g._spd is None for g in self.graphs):
             self.pack = ops.GraphPack(self.n_nodes, edges=[g.edges1 for g in self.graphs], cutoff=cutoff,
@@ -183,6 +195,9 @@ class GraphBatch:
                                       device=device, op=op)
         self.pack.build()
         self.device = device
+        if len(_PACK_CACHE) >= 64:
+            _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
+        _PACK_CACHE[key] = (list(self.graphs), self.pack)
         return self
 
     def on_device(self, device=None):

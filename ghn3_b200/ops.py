@@ -34,10 +34,12 @@ class HostBlob:
 
     def upload(self, device, pin=True):
         total = max(self.size, 16)
-        host = torch.empty(total, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
-        hnp = host.numpy()
-        for _, off, arr in self.parts:
-            hnp[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        host = getattr(self, 'host', None)
+        if host is None:                      # packed once; repeated uploads copy from the same pinned buffer
+            host = torch.empty(total, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+            hnp = host.numpy()
+            for _, off, arr in self.parts:
+                hnp[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
         dev = host.to(device, non_blocking=True)
         views = {}
         for name, off, arr in self.parts:
@@ -99,12 +101,24 @@ class GraphPack:
         if op is not None:
             blob.add('op', np.asarray(op, dtype=np.int32))
         self.h2d_bytes = blob.size
-        v = blob.upload(self.device)
         self._blob = blob
+        self._upload()
+
+    def _upload(self):
+        v = self._blob.upload(self.device)
         self.d = v
         self.spd = v.get('spd')
         self.op_dev = v.get('op')
         self.pair = self.deg_in = self.deg_out = self.dist0 = None
+
+    def clone_for_upload(self, device=None):
+        """A new pack with the same (immutable) host-side layout: only the H2D copy and the kernels are repeated."""
+        import copy as _copy
+        new = _copy.copy(self)
+        if device is not None:
+            new.device = torch.device(device)
+        new._upload()
+        return new
 
     def build(self, stream=None):
         """Runs the SPD BFS (if edges were given) and the derive kernel."""
