@@ -195,7 +195,7 @@ class GraphBatch:
                                       device=device, op=op)
         self.pack.build()
         self.device = device
-        if len(_PACK_CACHE) >= 64:
+        if len(_PACK_CACHE) >= 1024:
             _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
         _PACK_CACHE[key] = (list(self.graphs), self.pack)
         return self

@@ -330,7 +330,7 @@ class GHN3(GHN):
         if bp is None or any(a is not b for a, b in zip(bp.plans, plans)):
             bp = BatchPlan(plans, self.config)
             self._plan_cache[key] = bp
-            while len(self._plan_cache) > 64:
+            while len(self._plan_cache) > 1024:
                 self._plan_cache.popitem(last=False)
         return bp
 

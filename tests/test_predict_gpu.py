@@ -139,3 +139,25 @@ def test_cpu_model_gets_device_params_and_no_cpu_fallback():
 def test_xl_bench_models(arch, dtype):
     """BASELINE.json config 2: ghn3xlm16 (random-init) on ViT-B/16 and ConvNeXt-Base."""
     run_case('ghn3xlm16', [arch], dtype)
+
+
+def test_trace_on_the_fly_graphs_none():
+    """The drop-in call of the reference README: model = ghn(model) with no prebuilt graph (host tracer + CUDA SPD)."""
+    ghn, cfg = make_ghn('ghn3tiny', 'bf16')
+    m1, m2 = H.build_model('resnet18').to(DEV), H.build_model('resnet18').to(DEV)
+    with torch.no_grad():
+        out = ghn(m1)                                                  # traced here
+        ghn(m2, Graph.from_record(H.graph_records()['resnet18']))      # graph produced by the reference's tracer
+    assert out is m1
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert H.max_rel_err(p1, p2) < 1e-4, n1
+    g = Graph(H.build_model('alexnet'), ve_cutoff=50, verbose=False)
+    A = g._Adj                                                         # dense SPD matrix via the CUDA BFS kernel
+    assert H.spd_crc(A.numpy()) == H.graph_records()['alexnet']['spd_crc']
+    assert g.edges.shape[1] == 3
+
+
+@pytest.mark.parametrize('arch', ['efficientnet_v2_l', 'swin_v2_b'])
+def test_xl_large_graphs(arch):
+    """BASELINE.json config 4: the largest torchvision graph (N = 816) and a cyclic graph (Swin-V2), ghn3xlm16, bf16."""
+    run_case('ghn3xlm16', [arch], 'bf16', check_logits=False)
