@@ -53,7 +53,7 @@ class GemmArgs(C.Structure):
     _fields_ = [('a', vp), ('a_rows', i64), ('lda', i64), ('b', vp), ('b_rows', i64), ('ldb', i64), ('k', i32),
                 ('in_dtype', i32), ('d', vp), ('out_dtype', i32), ('bias', vp), ('act', i32), ('accumulate', i32),
                 ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32),
-                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp)]
+                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp), ('swap_ab', i32)]
 
 
 class GemmSimtArgs(C.Structure):

@@ -556,6 +556,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 }
 
+// Epilogue of a "swapped" tile: the 128 TMEM lanes hold WEIGHT rows (output columns n), the BN accumulator columns
+// hold activation rows m. Every thread owns one output column: for a given m the 32 lanes of a warp write 32
+// consecutive columns (64 B bf16 / 128 B fp32) -- coalesced without any shared-memory transposition, and all four
+// epilogue warps are busy even when the problem has only a handful of rows (the decoder's fc stage).
+template <int BN>
+__device__ __forceinline__ void epilogue_store_tile_swapped(const GemmKernelArgs& args, const ghn3_gemm_problem& p,
+                                                            int mt, int nt, uint32_t tmem_base, uint8_t* meta, int q,
+                                                            int lane, bool use_bias) {
+  static_assert(BN <= 64, "row offsets of a swapped tile live in a 64-entry table");
+  const int tile_n = args.b_group > 0 ? args.b_group * args.b_outer : kBlockM;
+  const int n_end = min(p.n, (nt + 1) * tile_n);
+  const int w = q * 32 + lane;                    // weight row inside the tile == TMEM lane
+  const int n = nt * tile_n + w;
+  const bool n_ok = w < tile_n && n < n_end;
+  const int m0 = mt * BN;
+  const int rows_valid = min(BN, p.m - m0);
+  const int64_t* rowoff_s = (const int64_t*)meta;
+  float bias = 0.f;
+  if (use_bias && n_ok) {
+    const int bidx = args.b_group > 0 ? (n / args.b_group) * args.b_stride + n % args.b_group : n;
+    bias = __ldg(args.bias + p.bias_off + bidx);
+  }
+  const bool bf16_out = args.out_dtype == GHN3_BF16;
+  const bool tf = args.out_dtype == GHN3_TF32;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (c0 >= rows_valid) break;                  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    const int cnt = min(32, rows_valid - c0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < cnt && n_ok) {
+        float v = __uint_as_float(r[j]) + bias;
+        if (args.act == GHN3_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (args.act == GHN3_ACT_GELU) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        const int64_t off = rowoff_s[c0 + j] + n;
+        if (bf16_out) ((__nv_bfloat16*)args.d)[off] = __float2bfloat16_rn(v);
+        else ((float*)args.d)[off] = tf ? round_tf32(v) : v;
+      }
+    }
+  }
+}
+
+// row offsets of the BN activation rows of a swapped tile (one table per warp; lanes cover rows lane, lane + 32)
+template <int BN>
+__device__ __forceinline__ void epilogue_prepare_swapped(const GemmKernelArgs& args, const ghn3_gemm_problem& p, int mt,
+                                                         uint8_t* meta, int lane) {
+  int64_t* rowoff_s = (int64_t*)meta;
+#pragma unroll
+  for (int jj = 0; jj < BN; jj += 32) {
+    const int m = mt * BN + jj + lane;
+    if (jj + lane < BN && m < p.m)
+      rowoff_s[jj + lane] = args.rowmap ? (int64_t)__ldg(args.rowmap + p.d_off + m) * p.ldd
+                                        : p.d_off + (int64_t)m * p.ldd;
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent variant for grouped (decoder) launches: one CTA per SM walks the tile list with stride gridDim.x.
 // The TMA producer runs ahead across tile boundaries (the ring never drains), the accumulator is double-buffered in
@@ -569,7 +629,7 @@ constexpr int gemm_persistent_smem_bytes() {
   return kStages * (kBlockM + BN) * kRowBytes + kStagingBytes + 1024 + 256;
 }
 
-template <bool kTf32, int BN, int kStages>
+template <bool kTf32, int BN, int kStages, bool kSwap>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                                const GemmKernelArgs args) {
@@ -622,7 +682,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
   pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t b_bytes = args.b_group > 0 ? (uint32_t)(args.b_group * args.b_outer * kRowBytes) : B_BYTES;
+      // bytes delivered by the WEIGHT box: a full tile, or g * outer rows through the 3-D "grouped rows" view
+      const uint32_t w_rows = kSwap ? kBlockM : BN;
+      const uint32_t w_bytes = args.b_group > 0 ? (uint32_t)(args.b_group * args.b_outer * kRowBytes) : w_rows * kRowBytes;
+      const uint32_t act_bytes = (kSwap ? BN : kBlockM) * kRowBytes;
       bool waited = false;
       uint32_t it = 0;
       int4 tile_next = make_int4(0, 0, 0, 0);
@@ -638,18 +701,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
           tile_next = args.tiles[t + gridDim.x];
           p_next = args.problems[tile_next.x];
         }
-        const int a_row = p.a_row0 + tile.y * kBlockM;
-        const int b_row = p.b_row0 + tile.z * (args.b_group > 0 ? args.b_outer : BN);
+        // normal: activations (tma_a) fill the 128-row UMMA-A slot, weights (tma_b) the BN-row UMMA-B slot;
+        // swapped: weights fill the 128-row slot, activations the BN-row slot
+        const int act_row = p.a_row0 + tile.y * (kSwap ? BN : kBlockM);
+        const int w_row = p.b_row0 + tile.z * (args.b_group > 0 ? args.b_outer : (int)w_rows);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
+          const uint32_t w_dst = kSwap ? sA + s * A_BYTES : sB + s * B_BYTES;
+          const uint32_t act_dst = kSwap ? sB + s * B_BYTES : sA + s * A_BYTES;
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + b_bytes);
+          mbar_arrive_expect_tx(full_bar + 8 * s, w_bytes + act_bytes);
           if (args.b_dynamic && !waited) { pdl_wait(); waited = true; }
-          if (args.b_group > 0) tma_load_3d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, 0, b_row);
-          else tma_load_2d(sB + s * B_BYTES, &tma_b, full_bar + 8 * s, kb * BK, b_row);
+          if (args.b_group > 0) tma_load_3d(w_dst, &tma_b, full_bar + 8 * s, kb * BK, 0, w_row);
+          else tma_load_2d(w_dst, &tma_b, full_bar + 8 * s, kb * BK, w_row);
           if (!waited) { pdl_wait(); waited = true; }        // weights first, then wait for the activations
-          tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, kb * BK, a_row);
+          tma_load_2d(act_dst, &tma_a, full_bar + 8 * s, kb * BK, act_row);
         }
       }
     }
@@ -697,11 +764,16 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
         p_next = args.problems[tile_next.x];
       }
       const int ab = j & 1;
-      epilogue_prepare<BN>(args, p, tile.y, tile.z, meta, q, lane, p.bias_off >= 0);
+      if constexpr (kSwap) epilogue_prepare_swapped<BN>(args, p, tile.y, meta, lane);
+      else epilogue_prepare<BN>(args, p, tile.y, tile.z, meta, q, lane, p.bias_off >= 0);
       mbar_wait(tmem_full_bar + 8 * ab, (uint32_t)((j >> 1) & 1));
       tcgen05_fence_after();
-      epilogue_store_tile<BN>(args, p, tile.y, tile.z, tmem_base + (uint32_t)(ab * BN), stage, meta, q, lane,
-                              p.bias_off >= 0, false);
+      if constexpr (kSwap)
+        epilogue_store_tile_swapped<BN>(args, p, tile.y, tile.z, tmem_base + (uint32_t)(ab * BN), meta, q, lane,
+                                        p.bias_off >= 0);
+      else
+        epilogue_store_tile<BN>(args, p, tile.y, tile.z, tmem_base + (uint32_t)(ab * BN), stage, meta, q, lane,
+                                p.bias_off >= 0, false);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * ab);
@@ -805,19 +877,19 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmK
 static long long* g_gemm_trace = nullptr;
 void set_gemm_trace(long long* p) { g_gemm_trace = p; }
 
-template <bool kTf32, int BN, int kStages>
+template <bool kTf32, int BN, int kStages, bool kSwap>
 static int launch_gemm_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelArgs& ka, int n_tiles,
                                   cudaStream_t stream) {
   constexpr int smem = gemm_persistent_smem_bytes<BN, kStages>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages>,
+    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const dim3 grid((unsigned)std::min(n_tiles, num_sms()));
-  GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages>, grid, dim3(192), (size_t)smem, stream, ma, mb,
+  GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap>, grid, dim3(192), (size_t)smem, stream, ma, mb,
                        ka));
   GHN3_LAUNCH_CHECK("gemm_tcgen05_persistent_kernel");
   return GHN3_OK;
@@ -840,6 +912,12 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
 
   int bn = a->block_n;
   int splits = 1;
+  const bool swap = a->swap_ab != 0;
+  if (swap) {
+    GHN3_REQUIRE(a->problems != nullptr && !x3 && !a->accumulate,
+                 "ghn3_gemm: swap_ab needs a grouped, non-accumulating launch and is not available with tf32_x3");
+    bn = 64;                                   // activation rows per tile (UMMA N); weights fill the 128 UMMA-M rows
+  }
   dim3 grid;
   if (a->problems != nullptr) {
     GHN3_REQUIRE(a->tiles != nullptr && a->n_tiles >= 0, "ghn3_gemm: grouped launch needs a tile list");
@@ -866,17 +944,18 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(!(x3 && bn == 256), "ghn3_gemm: tf32_x3 supports block_n 64/128");
 
   CUtensorMap ma, mb;
-  int rc = make_operand_map(&ma, a->a, a->a_rows, a->k, a->lda, tf32, kBlockM);
+  const int w_rows = swap ? kBlockM : bn;      // rows of a weight tile
+  int rc = make_operand_map(&ma, a->a, a->a_rows, a->k, a->lda, tf32, swap ? bn : kBlockM);
   if (rc != GHN3_OK) return rc;
   int b_outer = 0;
   if (a->b_group > 0) {
     GHN3_REQUIRE(a->problems != nullptr, "ghn3_gemm: b_group needs a grouped launch");
-    GHN3_REQUIRE(a->b_group <= bn && a->b_group_stride >= a->b_group && a->b_rows % a->b_group_stride == 0,
+    GHN3_REQUIRE(a->b_group <= w_rows && a->b_group_stride >= a->b_group && a->b_rows % a->b_group_stride == 0,
                  "ghn3_gemm: bad b_group / b_group_stride (%d / %d)", a->b_group, a->b_group_stride);
-    b_outer = (int)std::min<int64_t>(bn / a->b_group, a->b_rows / a->b_group_stride);
+    b_outer = (int)std::min<int64_t>(w_rows / a->b_group, a->b_rows / a->b_group_stride);
     rc = make_grouped_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, a->b_group, a->b_group_stride, b_outer);
   } else {
-    rc = make_operand_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, bn);
+    rc = make_operand_map(&mb, a->b, a->b_rows, a->k, a->ldb, tf32, w_rows);
   }
   if (rc != GHN3_OK) return rc;
 
@@ -900,11 +979,15 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.rowmap = a->rowmap;
   ka.n_tiles = a->n_tiles;
 
+  if (swap) {
+    if (tf32) return launch_gemm_persistent<true, 64, 6, true>(ma, mb, ka, a->n_tiles, stream);
+    return launch_gemm_persistent<false, 64, 6, true>(ma, mb, ka, a->n_tiles, stream);
+  }
   // grouped launches with enough tiles run on the persistent kernel (one CTA per SM, double-buffered accumulator)
   static const bool no_persistent = getenv("GHN3_NO_PERSISTENT") != nullptr;
   if (a->problems != nullptr && !x3 && bn == 128 && a->n_tiles >= 2 * num_sms() && !no_persistent) {
-    if (tf32) return launch_gemm_persistent<true, 128, 5>(ma, mb, ka, a->n_tiles, stream);
-    return launch_gemm_persistent<false, 128, 5>(ma, mb, ka, a->n_tiles, stream);
+    if (tf32) return launch_gemm_persistent<true, 128, 5, false>(ma, mb, ka, a->n_tiles, stream);
+    return launch_gemm_persistent<false, 128, 5, false>(ma, mb, ka, a->n_tiles, stream);
   }
 
   if (x3) {

@@ -345,6 +345,7 @@ class GHN3(GHN):
         blob.add('chunk_desc', bp.chunk_desc)
         blob.add('fc_problems', bp.fc_problems.view(np.uint8))
         blob.add('fc_tiles', bp.fc_tiles)
+        blob.add('fc_tiles_swap', bp.fc_tiles_swap)
         blob.add('fc_rowmap', bp.fc_rowmap if len(bp.fc_rowmap) else np.zeros(1, np.int32))
         for g_, pr, tl in bp.c2_launches:
             blob.add('c2_%d_problems' % g_, pr.view(np.uint8))
@@ -470,9 +471,11 @@ class _Program:
         if R > 0:
             self.h0, self.h1 = E(R, 4 * C), E(R, 8 * C)
             self.wout = E(bp.wout_elems, dtype=torch.float32)
+            fc_swap = bp.fc_swap and not x3
             self.ops.append(('dec_fc', 'gemm', gemm_args(self.dec_in, w['fc_w'], w['fc_b'], ops.ACT_RELU, self.h0, act,
-                                                         st['fc_problems'], st['fc_tiles'],
-                                                         rowmap=L.ptr(st['fc_rowmap']))))
+                                                         st['fc_problems'],
+                                                         st['fc_tiles_swap'] if fc_swap else st['fc_tiles'],
+                                                         rowmap=L.ptr(st['fc_rowmap']), swap_ab=int(fc_swap))))
             self.ops.append(('dec_conv0', 'gemm', gemm_args(self.h0, w['c0_w'], w['c0_b'], ops.ACT_RELU, self.h1, act)))
             for g_, _, _ in bp.c2_launches:
                 self.ops.append(('dec_conv2', 'gemm',

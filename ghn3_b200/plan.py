@@ -384,6 +384,10 @@ class BatchPlan:
         self.fc_problems = np.array(fc_probs, dtype=PROBLEM_DT) if fc_probs else np.zeros(0, PROBLEM_DT)
         self.c2_problems = np.array(c2_probs, dtype=PROBLEM_DT) if c2_probs else np.zeros(0, PROBLEM_DT)
         self.fc_tiles = tiles_for(self.fc_problems)
+        # most grid positions are needed by a handful of nodes only: the "swapped" GEMM formulation (weights on the
+        # 128 UMMA-M rows, 64 activation rows per tile) keeps all epilogue warps busy there
+        self.fc_swap = len(self.fc_problems) > 0 and float(np.median(self.fc_problems['m'])) <= 64
+        self.fc_tiles_swap = tiles_for(self.fc_problems, block_m=64) if self.fc_swap else self.fc_tiles
         self.c2_block_n = C2_DENSE_BLOCK_N
         self.c2_tiles = tiles_for(self.c2_problems, block_n=self.c2_block_n)
         # order conv2 tiles by weight block so CTAs that run together share the streamed weight rows through L2

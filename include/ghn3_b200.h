@@ -200,6 +200,10 @@ typedef struct {
                                 rowmap[problem.d_off + m] instead of d_off / ldd addressing. Lets the decoder's fc
                                 stage run one problem per grid POSITION over all nodes whose crop window contains it
                                 (reference ghn3/nn.py:738-745) while writing the (node, position)-major h0 layout. */
+  int32_t swap_ab;           /* grouped launches whose problems have few rows (m <~ 64): the WEIGHT rows fill the 128
+                                UMMA-M lanes and the activation rows become the N dimension (64 per tile), so all four
+                                epilogue warps work and the output is stored column-coalesced without staging.
+                                Tiles are then {problem, m / 64, n / 128 (or the b_group tile), 0}. */
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);

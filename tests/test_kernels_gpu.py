@@ -473,3 +473,52 @@ def test_gemm_grouped_persistent_many_tiles(dtype):
         got = out[o:o + m * ldd].view(m, ldd)
         assert _rel(got[:, :n], ref) < 2e-5
         assert bool((got[:, n:] == 3.0).all())          # padding columns untouched
+
+
+@pytest.mark.parametrize('dtype', [ops.BF16, ops.TF32])
+@pytest.mark.parametrize('g', [0, 4])
+def test_gemm_grouped_swap_ab(dtype, g):
+    """swap_ab: weights on the 128 UMMA-M rows, 64 activation rows per tile, row-mapped column-coalesced stores."""
+    torch.manual_seed(21 + g)
+    K, ms = 384, 96
+    rng = np.random.default_rng(1)
+    a = torch.randn(500, K, device=DEV)
+    w = torch.randn(ms * ms, K, device=DEV) / K ** 0.5
+    bias = torch.randn(ms * ms, device=DEV)
+    a_in, w_in = (a.bfloat16(), w.bfloat16()) if dtype == ops.BF16 else (ops.convert(a, ops.TF32), ops.convert(w, ops.TF32))
+    n_prob = 30
+    probs = np.zeros(n_prob, dtype=[('a_row0', 'i4'), ('b_row0', 'i4'), ('m', 'i4'), ('n', 'i4'), ('d_off', 'i8'),
+                                    ('ldd', 'i4'), ('bias_off', 'i4')])
+    tiles, rowmap, specs = [], [], []
+    total_rows = 0
+    ldd = 1536
+    for p in range(n_prob):
+        m = int(rng.integers(1, 150))
+        a0 = int(rng.integers(0, 500 - m))
+        if g == 0:
+            n = int(rng.integers(1, 1500)); b0 = int(rng.integers(0, ms * ms - n)); tile_n = 128
+            rows_w = np.arange(b0, b0 + n)
+        else:
+            o = int(rng.integers(1, ms)); n = o * g; b0 = 0; tile_n = (128 // g) * g
+            rows_w = (np.arange(o)[:, None] * ms + np.arange(g)[None, :]).reshape(-1)
+        probs[p] = (a0, b0, m, n, len(rowmap), ldd, b0)
+        perm = total_rows + rng.permutation(m)
+        rowmap.extend(perm.tolist())
+        specs.append((a0, m, rows_w, perm))
+        total_rows += m
+        for mt in range((m + 63) // 64):
+            for nt in range((n + tile_n - 1) // tile_n):
+                tiles.append((p, mt, nt, 0))
+    out = torch.full((total_rows, ldd), -5.0, device=DEV, dtype=torch.bfloat16 if dtype == ops.BF16 else torch.float32)
+    ops.gemm(a_in, w_in, bias=bias, act=ops.ACT_RELU, in_dtype=dtype, out=out, out_dtype=dtype if dtype == ops.BF16 else ops.F32,
+             problems=torch.from_numpy(probs.view(np.uint8).copy()).to(DEV),
+             tiles=torch.tensor(tiles, dtype=torch.int32, device=DEV),
+             rowmap=torch.tensor(rowmap, dtype=torch.int32, device=DEV), swap_ab=True, b_group=g,
+             b_group_stride=ms if g else 0, b_dynamic=False)
+    torch.cuda.synchronize()
+    for (a0, m, rows_w, perm) in specs:
+        rw = torch.from_numpy(rows_w).to(DEV)
+        ref = torch.relu(a_in[a0:a0 + m].double() @ w_in[rw].double().t() + bias[rw].double()).float()
+        got = out[torch.from_numpy(perm).to(DEV)].float()
+        assert _rel(got[:, :len(rows_w)], ref) < (6e-3 if dtype == ops.BF16 else 2e-5)
+        assert bool((got[:, len(rows_w):] == -5.0).all())
