@@ -53,7 +53,8 @@ class GemmArgs(C.Structure):
     _fields_ = [('a', vp), ('a_rows', i64), ('lda', i64), ('b', vp), ('b_rows', i64), ('ldb', i64), ('k', i32),
                 ('in_dtype', i32), ('d', vp), ('out_dtype', i32), ('bias', vp), ('act', i32), ('accumulate', i32),
                 ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32),
-                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp), ('swap_ab', i32)]
+                ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp), ('swap_ab', i32), ('ln_out', vp),
+                ('ln_gamma', vp), ('ln_beta', vp), ('ln_counters', vp), ('ln_out_dtype', i32)]
 
 
 class GemmSimtArgs(C.Structure):
@@ -79,7 +80,8 @@ class GraphormerArgs(C.Structure):
                 ('n_graphs', i32), ('total_nodes', i32), ('max_nodes', i32), ('lut_size', i32),
                 ('node_off', vp), ('mat_off', vp), ('pair', vp), ('lut', vp), ('x', vp),
                 ('h', vp), ('qkv', vp), ('ff', vp),
-                ('dec_in', vp), ('dec_dtype', i32), ('dst_row', vp), ('emb_f32', vp), ('tf32_x3', i32)]
+                ('dec_in', vp), ('dec_dtype', i32), ('dst_row', vp), ('emb_f32', vp), ('ln_counters', vp),
+                ('h2', vp), ('tf32_x3', i32)]
 
 
 class ScatterDesc(C.Structure):

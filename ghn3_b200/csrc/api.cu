@@ -1,6 +1,7 @@
 // C-ABI plumbing: error state, launch counter, and the composite Graphormer-stack entry point.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -60,11 +61,15 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
   const int x3 = (a->tf32_x3 != 0 && dt == GHN3_TF32) ? 1 : 0;
   const int act_dt = x3 ? GHN3_F32 : dt;      // storage dtype tag of the activations produced between GEMMs
   int rc;
+  const bool fuse_ln = a->ln_counters != nullptr && C <= 1024;
+  if (fuse_ln) GHN3_CUDA(cudaMemsetAsync(a->ln_counters, 0, sizeof(int32_t) * ((M + 127) / 128), stream));
   for (int l = 0; l < a->layers; ++l) {
     const ghn3_layer_weights& w = a->layers_host[l];
     ghn3_layernorm_args ln = {};
     ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = w.ln1_w; ln.beta = w.ln1_b; ln.out = a->h; ln.out_dtype = act_dt;
-    if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+    if (!fuse_ln || l == 0) {                  // otherwise produced by the previous layer's FFN2 epilogue
+      if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+    }
 
     ghn3_gemm_args qkv = linear(a->h, M, C, w.w_qkv, 3 * C, nullptr, a->qkv, dt, act_dt, GHN3_ACT_NONE, 0, x3);
     if ((rc = gemm_impl(&qkv, stream)) != GHN3_OK) return rc;
@@ -76,15 +81,27 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
     if ((rc = attention_impl(&at, stream)) != GHN3_OK) return rc;
 
     ghn3_gemm_args proj = linear(a->h, M, C, w.w_out, C, w.b_out, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1, x3);
+    if (fuse_ln) {                             // LN2 of this layer, written into h2 (h is this GEMM's A operand)
+      proj.ln_out = a->h2; proj.ln_gamma = w.ln2_w; proj.ln_beta = w.ln2_b;
+      proj.ln_counters = a->ln_counters; proj.ln_out_dtype = act_dt;
+    }
     if ((rc = gemm_impl(&proj, stream)) != GHN3_OK) return rc;
 
     ln.gamma = w.ln2_w; ln.beta = w.ln2_b;
-    if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+    if (!fuse_ln) {
+      if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
+    }
 
-    ghn3_gemm_args ff1 = linear(a->h, M, C, w.w_ff1, 4 * C, w.b_ff1, a->ff, dt, act_dt, GHN3_ACT_GELU, 0, x3);
+    ghn3_gemm_args ff1 = linear(fuse_ln ? a->h2 : a->h, M, C, w.w_ff1, 4 * C, w.b_ff1, a->ff, dt, act_dt, GHN3_ACT_GELU,
+                                0, x3);
     if ((rc = gemm_impl(&ff1, stream)) != GHN3_OK) return rc;
 
     ghn3_gemm_args ff2 = linear(a->ff, M, 4 * C, w.w_ff2, C, w.b_ff2, a->x, dt, GHN3_F32, GHN3_ACT_NONE, 1, x3);
+    if (fuse_ln && l + 1 < a->layers) {        // LN1 of the next layer
+      const ghn3_layer_weights& wn = a->layers_host[l + 1];
+      ff2.ln_out = a->h; ff2.ln_gamma = wn.ln1_w; ff2.ln_beta = wn.ln1_b;
+      ff2.ln_counters = a->ln_counters; ff2.ln_out_dtype = act_dt;
+    }
     if ((rc = gemm_impl(&ff2, stream)) != GHN3_OK) return rc;
   }
   if (a->ln_w != nullptr) {

@@ -148,6 +148,13 @@ struct GemmKernelArgs {
   int32_t b_dynamic;     // B is produced by an earlier kernel of the step: do not fetch it before pdl_wait()
   const int32_t* rowmap; // optional: output row of problem row m is rowmap[p.d_off + m] (d_off is then a table offset)
   int32_t n_tiles;       // grouped launches: length of `tiles` (the persistent kernel strides over it)
+  // fused LayerNorm of the finished rows (residual GEMMs of the Graphormer stack): the CTA that completes the last
+  // tile / K-split of a 128-row block normalises those rows of D (= the residual stream) into ln_out
+  void* ln_out;
+  const float* ln_gamma;
+  const float* ln_beta;
+  int32_t* ln_counters;
+  int32_t ln_out_dtype;
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -199,6 +206,57 @@ constexpr int gemm_threads() { return kX3 ? 320 : 192; }
 // rows per store instruction (measured: ~half of a small GEMM's run time), so each 32x32 block is transposed through
 // a per-warp shared-memory staging block and stored with lanes along columns: one contiguous 128-byte (fp32) or
 // 64-byte (bf16) row segment per warp instruction.
+// LayerNorm (eps 1e-5) of one fp32 row of `width` columns held in L2 (written by other CTAs: ld.cg), one warp per row.
+__device__ __forceinline__ void layernorm_row_from_l2(const float* __restrict__ xrow, int width, const float* gamma,
+                                                      const float* beta, void* out_row, int out_dtype, int lane) {
+  const int w4 = width >> 2;
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < w4) {
+      v[i] = __ldcg((const float4*)xrow + f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)width;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < w4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)width + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = lane + 32 * i;
+    if (f < w4) {
+      const float4 g = __ldg((const float4*)gamma + f);
+      const float4 b = __ldg((const float4*)beta + f);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out_dtype == GHN3_BF16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(y.x, y.y);
+        pk.y = pack_bf16x2(y.z, y.w);
+        ((uint2*)out_row)[f] = pk;
+      } else {
+        if (out_dtype == GHN3_TF32) {
+          y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w);
+        }
+        ((float4*)out_row)[f] = y;
+      }
+    }
+  }
+}
+
 // Per-tile epilogue inputs that do not depend on the accumulator (output row offsets through the optional row map,
 // column biases): fetched into the warp's staging block BEFORE waiting for the MMAs, so their global-memory latency
 // overlaps the main loop.
@@ -514,6 +572,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tcgen05_fence_after();
     epilogue_store_tile<BN>(args, p, mt, nt, tmem_base, stage, meta, q, lane, use_bias, atomic);
     if (threadIdx.x == 128) GHN3_TRACE(3);
+    if (args.ln_out != nullptr) {
+      // fused LayerNorm: count finished (tile, K-split) contributions per 128-row block; the last one normalises
+      __shared__ int s_last;
+      __threadfence();                                              // this warp's stores / atomics are visible
+      asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps
+      if (threadIdx.x == 64) {
+        const int total_kb = (args.k + BK - 1) / BK;
+        const int per = (total_kb + args.k_splits - 1) / max(args.k_splits, 1);
+        const int eff_splits = (total_kb + per - 1) / per;
+        const int target = (int)gridDim.x * eff_splits;
+        const int old = atomicAdd(args.ln_counters + mt, 1);
+        s_last = (old == target - 1) ? 1 : 0;
+        if (s_last) args.ln_counters[mt] = 0;                        // ready for the next launch
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        const int width = p.n;
+        const int esz = args.ln_out_dtype == GHN3_BF16 ? 2 : 4;
+        for (int rr = 0; rr < 32; ++rr) {
+          const int m = mt * kBlockM + q * 32 + rr;
+          if (m >= p.m) break;
+          layernorm_row_from_l2((const float*)args.d + p.d_off + (int64_t)m * p.ldd, width, args.ln_gamma, args.ln_beta,
+                                (uint8_t*)args.ln_out + (int64_t)m * width * esz, args.ln_out_dtype, lane);
+        }
+      }
+    }
   } else {
     // kX3 only: warps 6..9 split each landed fp32 tile into hi (in place) and lo (second buffer)
     if constexpr (kX3) {
@@ -978,6 +1063,16 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.b_dynamic = a->b_dynamic;
   ka.rowmap = a->rowmap;
   ka.n_tiles = a->n_tiles;
+  ka.ln_out = a->ln_out;
+  ka.ln_gamma = a->ln_gamma;
+  ka.ln_beta = a->ln_beta;
+  ka.ln_counters = a->ln_counters;
+  ka.ln_out_dtype = a->ln_out_dtype;
+  if (a->ln_out != nullptr) {
+    GHN3_REQUIRE(a->problems == nullptr && a->accumulate && a->out_dtype == GHN3_F32 && a->ln_counters != nullptr &&
+                     a->single.n % 4 == 0 && a->single.n <= 1024 && a->single.ldd == a->single.n,
+                 "ghn3_gemm: fused LayerNorm needs a single-problem residual GEMM over complete rows (n <= 1024)");
+  }
 
   if (swap) {
     if (tf32) return launch_gemm_persistent<true, 64, 6, true>(ma, mb, ka, a->n_tiles, stream);

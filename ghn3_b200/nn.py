@@ -32,6 +32,13 @@ from .weights import (EDGE_EMBED_ROWS, MAX_DEGREE, MAX_INPUT_DIST, N_PRIMITIVES,
 DTYPES = {'bf16': (ops.BF16, False), 'tf32': (ops.TF32, True), 'tf32x1': (ops.TF32, False)}
 
 
+# LayerNorm fused into the residual GEMMs (the CTA that completes a 128-row block normalises it). Implemented and
+# tested (tests/test_kernels_gpu.py::test_gemm_fused_layernorm) but OFF: measured 2.9 ms vs 1.03 ms for the Graphormer
+# stack on B200 -- one CTA normalising 128 x C values serially sits on the critical path, whereas the separate
+# LayerNorm launch (58 CTAs, ~3 us with programmatic dependent launch) does not.
+FUSE_LN = bool(int(__import__('os').environ.get('GHN3_FUSE_LN', '0')))
+
+
 def log(*a, **k):
     print(*a, **k)
 
@@ -446,11 +453,14 @@ class _Program:
         self.dec_in = E(max(n_dec, 1), C)
         self.emb = E(N, C, dtype=torch.float32) if want_emb else None
         self.h, self.qkv, self.ff = E(N, C), E(N, 3 * C), E(N, 4 * C)
+        self.h2 = E(N, C)
+        self.ln_counters = torch.zeros((N + 127) // 128 + 1, dtype=torch.int32, device=device)
         self.ghn = ghn
         self.ga = L.GraphormerArgs(hid=C, heads=H, layers=ghn.layers, dtype=dt, layers_host=w['layers'],
                                    ln_w=L.ptr(w['ln_w']), ln_b=L.ptr(w['ln_b']), total_nodes=N, x=L.ptr(self.x),
                                    h=L.ptr(self.h), qkv=L.ptr(self.qkv), ff=L.ptr(self.ff), dec_in=L.ptr(self.dec_in),
                                    dec_dtype=act, dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(self.emb),
+                                   ln_counters=L.ptr(self.ln_counters) if FUSE_LN else None, h2=L.ptr(self.h2),
                                    tf32_x3=int(x3))
         self.ops.append(('graphormer', 'graphormer_stack', self.ga))
         bufs = {}

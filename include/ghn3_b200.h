@@ -204,6 +204,15 @@ typedef struct {
                                 UMMA-M lanes and the activation rows become the N dimension (64 per tile), so all four
                                 epilogue warps work and the output is stored column-coalesced without staging.
                                 Tiles are then {problem, m / 64, n / 128 (or the b_group tile), 0}. */
+  /* Fused LayerNorm (eps 1e-5) for single-problem residual GEMMs whose output rows are complete rows of the
+   * residual stream (accumulate = 1, ldd == n): the CTA that finishes the last tile / K-split of a 128-row block
+   * writes LN(D rows) * gamma + beta into ln_out [m][n] (ln_out_dtype). ln_counters: device int32[ceil(m/128)],
+   * zero on entry, zero again on exit. Replaces the separate LayerNorm launches of ghn3/graphormer.py:239,241. */
+  void* ln_out;
+  const float* ln_gamma;
+  const float* ln_beta;
+  int32_t* ln_counters;
+  int32_t ln_out_dtype;
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);
@@ -279,6 +288,10 @@ typedef struct {
   void* dec_in; int32_t dec_dtype;         /* rows scattered by dst_row */
   const int32_t* dst_row;                  /* [total_nodes] or NULL (identity) */
   float* emb_f32;                          /* optional [total_nodes][C] */
+  int32_t* ln_counters;                    /* optional int32[ceil(total_nodes/128)] scratch: enables the LayerNorms
+                                              fused into the residual GEMMs (only the first and the final one are
+                                              then separate launches) */
+  void* h2;                                /* [total_nodes][C] in dtype, needed when ln_counters is given */
   int32_t tf32_x3;                         /* dtype TF32 only: activations stay un-rounded fp32, GEMMs use the
                                               3-term compensated tf32 mode (~fp32 accuracy) */
 } ghn3_graphormer_args;

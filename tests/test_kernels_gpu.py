@@ -522,3 +522,34 @@ def test_gemm_grouped_swap_ab(dtype, g):
         got = out[torch.from_numpy(perm).to(DEV)].float()
         assert _rel(got[:, :len(rows_w)], ref) < (6e-3 if dtype == ops.BF16 else 2e-5)
         assert bool((got[:, len(rows_w):] == -5.0).all())
+
+
+@pytest.mark.parametrize('dtype,x3', [(ops.BF16, False), (ops.TF32, True)])
+@pytest.mark.parametrize('splits', [0, 1, 4])
+def test_gemm_fused_layernorm(dtype, x3, splits):
+    """Residual GEMM + LayerNorm of the finished rows by the last-arriving CTA (graphormer.py:239-241)."""
+    import ctypes as C_
+    torch.manual_seed(31 + splits)
+    m, n, k = 457, 384, 1536
+    a = torch.randn(m, k, device=DEV)
+    b = torch.randn(n, k, device=DEV) / k ** 0.5
+    bias = torch.randn(n, device=DEV)
+    g, be = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+    a_in, b_in = (a, b) if x3 else (a.bfloat16(), b.bfloat16())
+    x = torch.randn(m, n, device=DEV)
+    x_ref = (x.double() + a_in.double() @ b_in.double().t() + bias.double()).float()
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (n,), g, be, 1e-5)
+    ln_out = torch.full((m, n), 7.0, device=DEV, dtype=torch.float32 if x3 else torch.bfloat16)
+    counters = torch.zeros(8, dtype=torch.int32, device=DEV)
+    for rep in range(2):                       # the counters must come back to zero
+        xx = x.clone()
+        ga = L.GemmArgs(a=L.ptr(a_in), a_rows=m, lda=k, b=L.ptr(b_in), b_rows=n, ldb=k, k=k, in_dtype=dtype,
+                        d=L.ptr(xx), out_dtype=ops.F32, bias=L.ptr(bias), act=0, accumulate=1, k_splits=splits,
+                        tf32_x3=int(x3), b_dynamic=1, ln_out=L.ptr(ln_out), ln_gamma=L.ptr(g), ln_beta=L.ptr(be),
+                        ln_counters=L.ptr(counters), ln_out_dtype=ops.F32 if x3 else ops.BF16)
+        ga.single = L.GemmProblem(a_row0=0, b_row0=0, m=m, n=n, d_off=0, ldd=n, bias_off=0)
+        L.call('gemm', ga, L.current_stream())
+        torch.cuda.synchronize()
+        assert _rel(xx, x_ref) < 2e-5
+        assert _rel(ln_out, ln_ref) < (1e-2 if not x3 else 2e-5)
+        assert int(counters.abs().sum()) == 0
