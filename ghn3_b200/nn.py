@@ -284,6 +284,8 @@ class GHN3(GHN):
                                       'parameters) is not implemented in the CUDA path yet')
         is_lst = isinstance(nets_torch, (list, tuple))
         nets = list(nets_torch) if is_lst else [nets_torch]
+        if len(nets) == 0:                                   # empty batch: nothing to predict
+            return ([], torch.empty(0, self.hid, device=device)) if return_embeddings else []
 
         if graphs is None:
             graphs = GraphBatch([Graph(net, ve_cutoff=50 if self.ve else 1) for net in nets], dense=True)

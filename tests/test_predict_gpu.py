@@ -161,3 +161,99 @@ def test_trace_on_the_fly_graphs_none():
 def test_xl_large_graphs(arch):
     """BASELINE.json config 4: the largest torchvision graph (N = 816) and a cyclic graph (Swin-V2), ghn3xlm16, bf16."""
     run_case('ghn3xlm16', [arch], 'bf16', check_logits=False)
+
+
+def _oracle_graph(g):
+    """ghn3_b200 Graph -> oracle graph dict (SPD by the oracle's own BFS)."""
+    n = g.n_nodes
+    adj = np.zeros((n, n), dtype=np.int64)
+    adj[g.edges1[:, 0], g.edges1[:, 1]] = 1
+    return {'n': n, 'ops': g.node_feat[:, 0].numpy(), 'A': O.spd_matrix(adj, max(int(g.ve_cutoff), 1)), 'adj1': adj,
+            'node_info': g.node_info}
+
+
+class SmallNet(torch.nn.Module):
+    """A user model that is not in torchvision: conv / bn / depthwise / 5x5 / linear head."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        self.features = nn.Sequential(
+            nn.Conv2d(3, 24, 5, padding=2), nn.BatchNorm2d(24), nn.ReLU(),
+            nn.Conv2d(24, 24, 3, padding=1, groups=24, bias=False), nn.BatchNorm2d(24), nn.ReLU(),
+            nn.MaxPool2d(2), nn.Conv2d(24, 40, 1), nn.ReLU(), nn.AdaptiveAvgPool2d(1))
+        self.classifier = nn.Linear(40, 10)
+
+    def forward(self, x):
+        return self.classifier(torch.flatten(self.features(x), 1))
+
+
+def test_custom_model_traced_on_the_fly_matches_oracle():
+    ghn, cfg = make_ghn('ghn3tiny', 'tf32')
+    sd = procedural_state_dict(cfg, 0)
+    torch.manual_seed(3)
+    model = SmallNet()
+    model.expected_input_sz = 32
+    ref = copy.deepcopy(model)
+    g = Graph(model, verbose=False)
+    model = model.to(DEV)
+    with torch.no_grad():
+        ghn(model, g)
+    O.predict(sd, cfg, ref, _oracle_graph(g))
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref.named_parameters()):
+        assert H.max_rel_err(p1, p2) < 1e-3, n1
+
+
+@pytest.mark.parametrize('flags', [dict(predict_class_layers=False), dict(bn_track_running_stats=False),
+                                   dict(weight_norm=False), dict(ve=False), dict(reduce_graph=True)])
+def test_forward_flags_match_oracle(flags):
+    """API flags of GHN3.forward / GHN3.__init__ (nn.py:186-209, 140-143) against the oracle."""
+    cfg = CONFIGS['ghn3tiny']
+    sd = procedural_state_dict(cfg, 0)
+    weight_norm, ve = flags.get('weight_norm', True), flags.get('ve', True)
+    ghn = GHN3(**cfg, weight_norm=weight_norm, ve=ve, compute_dtype='tf32')
+    ghn.load_state_dict(sd)
+    ghn = ghn.to(DEV).eval()
+    rec = H.graph_records()['resnet18']
+    model = H.build_model('resnet18').to(DEV)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    g = Graph.from_record(rec, ve_cutoff=50 if ve else 1)
+    fwd = {k: v for k, v in flags.items() if k in ('predict_class_layers', 'bn_track_running_stats', 'reduce_graph')}
+    with torch.no_grad():
+        ghn(model, g, **fwd)
+    ref = H.build_model('resnet18')
+    og = O.graph_from_record(rec, cutoff=50 if ve else 1)
+    emb = O.embed_graph(sd, cfg, ref, og)
+    O.decode_and_set(sd, cfg, ref, og['node_info'], emb, predict_class_layers=fwd.get('predict_class_layers', True),
+                     weight_norm=weight_norm)
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref.named_parameters()):
+        assert H.max_rel_err(p1, p2) < 1e-3, (flags, n1)
+    if flags.get('predict_class_layers') is False:
+        assert torch.equal(model.fc.weight, before['fc.weight']) and torch.equal(model.fc.bias, before['fc.bias'])
+    if flags.get('bn_track_running_stats') is False:
+        assert all(m.training and not m.track_running_stats for m in model.modules()
+                   if isinstance(m, torch.nn.BatchNorm2d))
+
+
+def test_ten_class_ghn_with_11x11_grid():
+    """CIFAR-style GHN config: num_classes=10, 11x11 decoder grid (9-row spatial table, nn.py:74,83-84)."""
+    cfg = dict(hid=32, layers=2, heads=8, max_shape=(32, 32, 11, 11), num_classes=10, layernorm=True)
+    sd = procedural_state_dict(cfg, 0)
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(sd)
+    ghn = ghn.to(DEV).eval()
+    for arch in ('resnet18', 'alexnet'):
+        rec = H.graph_records()[arch]
+        model = H.build_model(arch).to(DEV)
+        with torch.no_grad():
+            ghn(model, Graph.from_record(rec))
+        ref = H.build_model(arch)
+        O.predict(sd, cfg, ref, O.graph_from_record(rec))
+        for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref.named_parameters()):
+            assert H.max_rel_err(p1, p2) < 1e-3, (arch, n1)
+
+
+def test_empty_and_single_node_inputs():
+    ghn, cfg = make_ghn('ghn3tiny', 'bf16')
+    with torch.no_grad():
+        assert ghn([], []) == []
