@@ -709,13 +709,13 @@ __device__ __forceinline__ void epilogue_prepare_swapped(const GemmKernelArgs& a
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStagingBytes = 4 * (kStageBlock + kMetaBlock);
 
-template <int BN, int kStages>
+template <int BN, int kStages, bool kX3>
 constexpr int gemm_persistent_smem_bytes() {
-  return kStages * (kBlockM + BN) * kRowBytes + kStagingBytes + 1024 + 256;
+  return kStages * (kBlockM + BN) * kRowBytes * (kX3 ? 2 : 1) + kStagingBytes + 1024 + 256;
 }
 
-template <bool kTf32, int BN, int kStages, bool kSwap>
-__global__ void __launch_bounds__(192, 1)
+template <bool kTf32, int BN, int kStages, bool kSwap, bool kX3>
+__global__ void __launch_bounds__(gemm_threads<kX3>(), 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                                const GemmKernelArgs args) {
   constexpr int EB = kTf32 ? 4 : 2;
@@ -725,16 +725,20 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
   constexpr uint32_t B_BYTES = BN * kRowBytes;
   constexpr uint32_t kIdesc = make_idesc(kTf32, kBlockM, BN);
   static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
+  static_assert(!kX3 || (kTf32 && !kSwap), "the 3-term split is a tf32 mode of the un-swapped kernel");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + kStages * A_BYTES;
-  const uint32_t sStage = sB + kStages * B_BYTES;
+  const uint32_t sAlo = sB + kStages * B_BYTES;                      // only used when kX3
+  const uint32_t sBlo = sAlo + (kX3 ? kStages * A_BYTES : 0);
+  const uint32_t sStage = sBlo + (kX3 ? kStages * B_BYTES : 0);
   const uint32_t bar_base = sStage + kStagingBytes;
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + 8 * kStages;
-  const uint32_t tmem_full_bar = bar_base + 16 * kStages;        // 2 barriers
+  const uint32_t split_bar = bar_base + 16 * kStages;
+  const uint32_t tmem_full_bar = bar_base + 24 * kStages;        // 2 barriers
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;            // 2 barriers
   const uint32_t tmem_slot = tmem_empty_bar + 16;
   uint32_t* tmem_slot_ptr = (uint32_t*)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -750,6 +754,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(split_bar + 8 * s, 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar + 8 * b, 1);
@@ -817,19 +822,30 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(full_bar + 8 * s, ph);
+          mbar_wait((kX3 ? split_bar : full_bar) + 8 * s, ph);
           tcgen05_fence_after();
           const uint64_t da = make_smem_desc(sA + s * A_BYTES);
           const uint64_t db = make_smem_desc(sB + s * B_BYTES);
+          if constexpr (kX3) {
+            const uint64_t da_lo = make_smem_desc(sAlo + s * A_BYTES);
+            const uint64_t db_lo = make_smem_desc(sBlo + s * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < kMmaPerStage; ++k)
-            umma<kTf32>(acc, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kMmaPerStage; ++k) {
+              umma<true>(acc, da_lo + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              umma<true>(acc, da + 2 * k, db_lo + 2 * k, kIdesc, 1u);
+              umma<true>(acc, da + 2 * k, db + 2 * k, kIdesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kMmaPerStage; ++k)
+              umma<kTf32>(acc, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
           tcgen05_commit(empty_bar + 8 * s);
         }
         tcgen05_commit(tmem_full_bar + 8 * ab);
       }
     }
-  } else {
+  } else if (warp < 6) {
     const int q = warp & 3;
     float* stage = (float*)(smem_raw + (sStage - smem_u32(smem_raw)) + q * kStageBlock);
     uint8_t* meta = smem_raw + (sStage - smem_u32(smem_raw)) + 4 * kStageBlock + q * kMetaBlock;
@@ -862,6 +878,38 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * ab);
+    }
+  } else {
+    // kX3 only: warps 6..9 split every landed fp32 stage into hi (in place) and lo, for all tiles of this CTA
+    if constexpr (kX3) {
+      const int t = threadIdx.x - 192;
+      uint32_t it = 0;
+      for (int tt = blockIdx.x; tt < n_tiles; tt += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          float4* a_hi = (float4*)(smem_raw + (sA + s * A_BYTES - smem_u32(smem_raw)));
+          float4* a_lo = (float4*)(smem_raw + (sAlo + s * A_BYTES - smem_u32(smem_raw)));
+          float4* b_hi = (float4*)(smem_raw + (sB + s * B_BYTES - smem_u32(smem_raw)));
+          float4* b_lo = (float4*)(smem_raw + (sBlo + s * B_BYTES - smem_u32(smem_raw)));
+          auto split4 = [](float4* hi, float4* lo, int idx) {
+            float4 v = hi[idx], h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            hi[idx] = h;
+            lo[idx] = l;
+          };
+#pragma unroll 4
+          for (int idx = t; idx < (int)(A_BYTES / 16); idx += 128) split4(a_hi, a_lo, idx);
+#pragma unroll 4
+          for (int idx = t; idx < (int)(B_BYTES / 16); idx += 128) split4(b_hi, b_lo, idx);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(split_bar + 8 * s);
+        }
+      }
     }
   }
 
@@ -962,19 +1010,19 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmK
 static long long* g_gemm_trace = nullptr;
 void set_gemm_trace(long long* p) { g_gemm_trace = p; }
 
-template <bool kTf32, int BN, int kStages, bool kSwap>
+template <bool kTf32, int BN, int kStages, bool kSwap, bool kX3>
 static int launch_gemm_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelArgs& ka, int n_tiles,
                                   cudaStream_t stream) {
-  constexpr int smem = gemm_persistent_smem_bytes<BN, kStages>();
+  constexpr int smem = gemm_persistent_smem_bytes<BN, kStages, kX3>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap>,
+    GHN3_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap, kX3>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const dim3 grid((unsigned)std::min(n_tiles, num_sms()));
-  GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap>, grid, dim3(192), (size_t)smem, stream, ma, mb,
+  GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap, kX3>, grid, dim3(gemm_threads<kX3>()), (size_t)smem, stream, ma, mb,
                        ka));
   GHN3_LAUNCH_CHECK("gemm_tcgen05_persistent_kernel");
   return GHN3_OK;
@@ -1075,14 +1123,15 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   }
 
   if (swap) {
-    if (tf32) return launch_gemm_persistent<true, 64, 6, true>(ma, mb, ka, a->n_tiles, stream);
-    return launch_gemm_persistent<false, 64, 6, true>(ma, mb, ka, a->n_tiles, stream);
+    if (tf32) return launch_gemm_persistent<true, 64, 6, true, false>(ma, mb, ka, a->n_tiles, stream);
+    return launch_gemm_persistent<false, 64, 6, true, false>(ma, mb, ka, a->n_tiles, stream);
   }
   // grouped launches with enough tiles run on the persistent kernel (one CTA per SM, double-buffered accumulator)
   static const bool no_persistent = getenv("GHN3_NO_PERSISTENT") != nullptr;
-  if (a->problems != nullptr && !x3 && bn == 128 && a->n_tiles >= 2 * num_sms() && !no_persistent) {
-    if (tf32) return launch_gemm_persistent<true, 128, 5, false>(ma, mb, ka, a->n_tiles, stream);
-    return launch_gemm_persistent<false, 128, 5, false>(ma, mb, ka, a->n_tiles, stream);
+  if (a->problems != nullptr && bn == 128 && a->n_tiles >= 2 * num_sms() && !no_persistent) {
+    if (x3) return launch_gemm_persistent<true, 128, 3, false, true>(ma, mb, ka, a->n_tiles, stream);
+    if (tf32) return launch_gemm_persistent<true, 128, 5, false, false>(ma, mb, ka, a->n_tiles, stream);
+    return launch_gemm_persistent<false, 128, 5, false, false>(ma, mb, ka, a->n_tiles, stream);
   }
 
   if (x3) {
