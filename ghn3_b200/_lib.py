@@ -130,11 +130,60 @@ class SumsqArgs(C.Structure):
     _fields_ = [('ptrs', vp), ('numels', vp), ('n', i32), ('out', vp)]
 
 
+# ---- training path (adjoint kernels) ----
+EW_COPY, EW_GELU, EW_GELU_BWD, EW_RELU_BWD, EW_ADD = 0, 1, 2, 3, 4
+
+
+class TransposeArgs(C.Structure):
+    _fields_ = [('src', vp), ('src_dtype', i32), ('ld_src', i64), ('rows', i32), ('cols', i32), ('group', i32),
+                ('group_stride', i32), ('dst', vp), ('dst_dtype', i32), ('ld_dst', i64)]
+
+
+class ElementwiseArgs(C.Structure):
+    _fields_ = [('op', i32), ('n', i64), ('a', vp), ('a_dtype', i32), ('b', vp), ('b_dtype', i32), ('out', vp),
+                ('out_dtype', i32)]
+
+
+class ColsumArgs(C.Structure):
+    _fields_ = [('src', vp), ('src_dtype', i32), ('ld', i64), ('rows', i32), ('cols', i32), ('group', i32),
+                ('group_stride', i32), ('dst', vp)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [('rows', i32), ('hid', i32), ('x', vp), ('gamma', vp), ('dy', vp), ('dy_dtype', i32), ('dy_row', vp),
+                ('dx', vp), ('accumulate', i32), ('dgamma', vp), ('dbeta', vp)]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [('n_graphs', i32), ('hid', i32), ('heads', i32), ('max_nodes', i32), ('total_nodes', i32),
+                ('lut_size', i32), ('node_off', vp), ('mat_off', vp), ('qkv', vp), ('out', vp), ('d_out', vp),
+                ('dtype', i32), ('pair', vp), ('lut', vp), ('d_qkv', vp), ('d_lut', vp), ('lse', vp), ('delta', vp)]
+
+
+class ScatterBwdArgs(C.Structure):
+    _fields_ = [('descs', vp), ('n_descs', i32), ('n_chunks', i64), ('chunk_desc', vp), ('grads', vp), ('d_src', vp)]
+
+
+class NodeFeaturesBwdArgs(C.Structure):
+    _fields_ = [('total_nodes', i32), ('hid', i32), ('op', vp), ('shape_idx', vp), ('deg_in', vp), ('deg_out', vp),
+                ('dist0', vp), ('dx', vp), ('d_embed_op', vp), ('d_embed_ch', vp), ('d_embed_sp', vp),
+                ('d_cent_in', vp), ('d_cent_out', vp), ('d_dist_embed', vp)]
+
+
+class EdgeLutBwdArgs(C.Structure):
+    _fields_ = [('hid', i32), ('heads', i32), ('vmax', i32), ('edge_embed', vp), ('w1', vp), ('b1', vp), ('w2', vp),
+                ('d_lut', vp), ('workspace', vp), ('d_edge_embed', vp), ('d_w1', vp), ('d_b1', vp), ('d_w2', vp),
+                ('d_b2', vp)]
+
+
 assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
            'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
+TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
+                 'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd']
+SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None
 
@@ -150,12 +199,12 @@ def load(build_if_missing=True):
         from . import build as _build
         _build.build()
     lib = C.CDLL(LIB_PATH)
-    for s in SYMBOLS:
+    for s in SYMBOLS_ALL:
         if not hasattr(lib, s):
             raise RuntimeError('ghn3_b200: %s does not export %s' % (LIB_PATH, s))
     lib.ghn3_last_error.restype = C.c_char_p
     lib.ghn3_launch_count.restype = C.c_int64
-    for s in SYMBOLS[3:15]:
+    for s in SYMBOLS[3:15] + TRAIN_SYMBOLS:
         getattr(lib, s).restype = C.c_int
         getattr(lib, s).argtypes = [C.c_void_p, C.c_void_p]
     lib.ghn3_run_sequence.restype = C.c_int

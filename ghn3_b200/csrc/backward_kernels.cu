@@ -1,0 +1,699 @@
+// Backward kernels of the GHN-3 training path (reference: ghn3/trainer.py:238-411 runs autograd through
+// GHN3.forward(keep_grads=True), ghn3/nn.py:186-349). Each kernel is the hand-written adjoint of one forward kernel
+// of this library; the linear layers reuse the tcgen05 GEMM on explicitly transposed operands (ghn3_transpose).
+// All gradients of GHN parameters are accumulated in fp32.
+#include "common.cuh"
+
+namespace ghn3 {
+
+__device__ __forceinline__ float ld_f(const void* p, int64_t i, int dt) {
+  return dt == GHN3_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st_f(void* p, int64_t i, int dt, float v) {
+  if (dt == GHN3_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else if (dt == GHN3_TF32) ((float*)p)[i] = round_tf32(v);
+  else ((float*)p)[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dst[c][r] = src[row(r)][c]: 32 x 32 tiles through shared memory, dtype conversion on the way
+__global__ void __launch_bounds__(256) transpose_kernel(const ghn3_transpose_args a) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < a.rows && c < a.cols) {
+      const int64_t sr = a.group > 0 ? (int64_t)(r / a.group) * a.group_stride + r % a.group : r;
+      v = ld_f(a.src, sr * a.ld_src + c, a.src_dtype);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < a.cols && r < a.rows) st_f(a.dst, (int64_t)c * a.ld_dst + r, a.dst_dtype, tile[tx][ty + 8 * i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752440f)) + u * 0.39894228040143267794f * __expf(-0.5f * u * u);
+}
+
+__global__ void __launch_bounds__(256) elementwise_kernel(const ghn3_elementwise_args a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    switch (a.op) {
+      case GHN3_EW_GELU: v = gelu_f(ld_f(a.a, i, a.a_dtype)); break;
+      case GHN3_EW_GELU_BWD: v = ld_f(a.a, i, a.a_dtype) * gelu_grad(ld_f(a.b, i, a.b_dtype)); break;
+      case GHN3_EW_RELU_BWD: v = ld_f(a.b, i, a.b_dtype) > 0.f ? ld_f(a.a, i, a.a_dtype) : 0.f; break;
+      case GHN3_EW_ADD: v = ld_f(a.a, i, a.a_dtype) + ld_f(a.b, i, a.b_dtype); break;
+      default: v = ld_f(a.a, i, a.a_dtype); break;      // GHN3_EW_COPY
+    }
+    st_f(a.out, i, a.out_dtype, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dst[col(c)] += sum_r src[r][c]
+__global__ void __launch_bounds__(256) colsum_kernel(const ghn3_colsum_args a) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * 256;
+  const int r1 = min(r0 + 256, a.rows);
+  float acc = 0.f;
+  if (c < a.cols)
+    for (int r = r0 + ty; r < r1; r += 8) acc += ld_f(a.src, (int64_t)r * a.ld + c, a.src_dtype);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < a.cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    const int64_t dc = a.group > 0 ? (int64_t)(c / a.group) * a.group_stride + c % a.group : c;
+    atomicAdd(a.dst + dc, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm backward (eps 1e-5): one warp per row, per-block shared accumulators for dgamma / dbeta
+constexpr int kLnMaxT = 32;       // hid <= 1024
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm_bwd_args a) {
+  extern __shared__ float ln_smem[];
+  const int C = a.hid;
+  float* sG = ln_smem;
+  float* sB = ln_smem + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ln_smem[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invC = 1.f / (float)C;
+  for (int row = blockIdx.x * 8 + warp; row < a.rows; row += gridDim.x * 8) {
+    const int64_t dyr = a.dy_row ? a.dy_row[row] : row;
+    if (dyr < 0) continue;                     // no gradient reaches this row through this LayerNorm
+    const float* x = a.x + (int64_t)row * C;
+    float xv[kLnMaxT], gv[kLnMaxT];
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < kLnMaxT; ++t) {
+      const int c = lane + 32 * t;
+      xv[t] = c < C ? x[c] : 0.f;
+      sum += xv[t];
+    }
+    const float mean = warp_sum(sum) * invC;
+    float sq = 0.f;
+#pragma unroll
+    for (int t = 0; t < kLnMaxT; ++t) {
+      const int c = lane + 32 * t;
+      const float d = c < C ? xv[t] - mean : 0.f;
+      sq += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * invC + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < kLnMaxT; ++t) {
+      const int c = lane + 32 * t;
+      if (c < C) {
+        const float dy = ld_f(a.dy, dyr * C + c, a.dy_dtype);
+        const float xh = (xv[t] - mean) * rstd;
+        xv[t] = xh;
+        const float g = dy * a.gamma[c];
+        gv[t] = g;
+        s1 += g;
+        s2 += g * xh;
+        atomicAdd(sG + c, dy * xh);
+        atomicAdd(sB + c, dy);
+      } else {
+        gv[t] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+    float* dx = a.dx + (int64_t)row * C;
+#pragma unroll
+    for (int t = 0; t < kLnMaxT; ++t) {
+      const int c = lane + 32 * t;
+      if (c < C) {
+        const float v = rstd * (gv[t] - s1 - xv[t] * s2);
+        dx[c] = a.accumulate ? dx[c] + v : v;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (sG[c] != 0.f) atomicAdd(a.dgamma + c, sG[c]);
+    if (sB[c] != 0.f) atomicAdd(a.dbeta + c, sB[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Attention backward, fp32 math on CUDA cores. Softmax statistics are recomputed (no state saved by the forward).
+//   S = Q K^T d^-1/2 + lut[h][pair];  P = softmax(S);  O = P V
+//   delta_i = dO_i . O_i;  dP = dO V^T;  dS = P o (dP - delta);  dQ = dS K d^-1/2;  dK = dS^T Q d^-1/2;  dV = P^T dO
+//   dlut[h][pair(i,j)] += dS_ij
+constexpr int kBwdKT = 128;     // keys (kernel A) / queries (kernel B) staged per tile
+constexpr int kBwdWarps = 8;
+constexpr int kBwdPerWarp = 2;  // queries (A) / keys (B) per warp
+constexpr int kBwdRows = kBwdWarps * kBwdPerWarp;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) attention_bwd_dq_kernel(const ghn3_attention_bwd_args a) {
+  extern __shared__ float bw_smem[];
+  constexpr int DP = D + 1;
+  float* sK = bw_smem;                         // [KT][DP]
+  float* sV = sK + kBwdKT * DP;                // [KT][DP]
+  float* sBias = sV + kBwdKT * DP;             // [rows][KT]
+  uint16_t* sPair = (uint16_t*)(sBias + kBwdRows * kBwdKT);   // [rows][KT]
+  float* sLut = (float*)(sPair + kBwdRows * kBwdKT);          // [lut_size]
+  float* sHist = sLut + a.lut_size;                           // [lut_size]
+
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int n0 = a.node_off[g];
+  const int n = a.node_off[g + 1] - n0;
+  const int q0 = blockIdx.x * kBwdRows;
+  if (q0 >= n) return;
+  const int ld = (n + 15) & ~15;
+  const int C = a.hid, C3 = 3 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qkv = (const T*)a.qkv + (int64_t)n0 * C3;
+  const T* dout = (const T*)a.d_out + (int64_t)n0 * C;
+  const T* out = (const T*)a.out + (int64_t)n0 * C;
+  const uint16_t* pair = a.pair + a.mat_off[g];
+  const float scale = rsqrtf((float)D);
+
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) {
+    sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
+    sHist[i] = 0.f;
+  }
+
+  float q[kBwdPerWarp][D], dO[kBwdPerWarp][D], dq[kBwdPerWarp][D];
+  float m[kBwdPerWarp], l[kBwdPerWarp], delta[kBwdPerWarp];
+  int qi[kBwdPerWarp];
+#pragma unroll
+  for (int t = 0; t < kBwdPerWarp; ++t) {
+    qi[t] = q0 + warp * kBwdPerWarp + t;
+    const bool ok = qi[t] < n;
+    const int64_t r = ok ? qi[t] : 0;
+    float dl = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      q[t][d] = ok ? to_float(qkv[r * C3 + h * D + d]) * scale : 0.f;
+      dO[t][d] = ok ? to_float(dout[r * C + h * D + d]) : 0.f;
+      dq[t][d] = 0.f;
+      dl += dO[t][d] * (ok ? to_float(out[r * C + h * D + d]) : 0.f);
+    }
+    delta[t] = dl;
+    m[t] = -INFINITY;
+    l[t] = 0.f;
+  }
+
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k0 = 0; k0 < n; k0 += kBwdKT) {
+      const int kt = min(kBwdKT, n - k0);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < kt * D; idx += blockDim.x) {
+        const int j = idx / D, d = idx - j * D;
+        const T* row = qkv + (int64_t)(k0 + j) * C3 + h * D + d;
+        sK[j * DP + d] = to_float(row[C]);
+        sV[j * DP + d] = to_float(row[2 * C]);
+      }
+      for (int idx = threadIdx.x; idx < kBwdRows * kBwdKT; idx += blockDim.x) {
+        const int r = idx / kBwdKT, j = idx - r * kBwdKT;
+        uint16_t p = 0;
+        if (q0 + r < n && j < kt) p = pair[(int64_t)(q0 + r) * ld + k0 + j];
+        sPair[idx] = p;
+        sBias[idx] = sLut[p];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < kBwdPerWarp; ++t) {
+        if (qi[t] >= n) continue;
+        const int r = warp * kBwdPerWarp + t;
+        if (pass == 0) {
+          // running max / sum of exp
+          float mx = m[t];
+          float sv[kBwdKT / 32];
+#pragma unroll
+          for (int u = 0; u < kBwdKT / 32; ++u) {
+            const int j = lane + 32 * u;
+            float s = -INFINITY;
+            if (j < kt) {
+              s = sBias[r * kBwdKT + j];
+#pragma unroll
+              for (int d = 0; d < D; ++d) s = fmaf(q[t][d], sK[j * DP + d], s);
+            }
+            sv[u] = s;
+            mx = fmaxf(mx, s);
+          }
+          mx = warp_max(mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int u = 0; u < kBwdKT / 32; ++u) sum += (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - mx);
+          sum = warp_sum(sum);
+          l[t] = l[t] * __expf(m[t] - mx) + sum;
+          m[t] = mx;
+        } else {
+          const float lse = m[t] + __logf(l[t]);
+#pragma unroll
+          for (int u = 0; u < kBwdKT / 32; ++u) {
+            const int j = lane + 32 * u;
+            if (j < kt) {
+              float s = sBias[r * kBwdKT + j], dp = 0.f;
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                s = fmaf(q[t][d], sK[j * DP + d], s);
+                dp = fmaf(dO[t][d], sV[j * DP + d], dp);
+              }
+              const float p = __expf(s - lse);
+              const float ds = p * (dp - delta[t]);
+#pragma unroll
+              for (int d = 0; d < D; ++d) dq[t][d] = fmaf(ds, sK[j * DP + d], dq[t][d]);
+              if (a.d_lut != nullptr) atomicAdd(sHist + sPair[r * kBwdKT + j], ds);
+            }
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int t = 0; t < kBwdPerWarp; ++t) {
+    if (qi[t] >= n) continue;
+    const int64_t row = n0 + qi[t];
+    T* dst = (T*)a.d_qkv + row * C3 + h * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float v = warp_sum(dq[t][d]) * scale;
+      if (lane == 0) dst[d] = from_float<T>(v);
+    }
+    if (lane == 0) {
+      a.lse[(int64_t)h * a.total_nodes + row] = m[t] + __logf(l[t]);
+      a.delta[(int64_t)h * a.total_nodes + row] = delta[t];
+    }
+  }
+  __syncthreads();
+  if (a.d_lut != nullptr)
+    for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x)
+      if (sHist[i] != 0.f) atomicAdd(a.d_lut + (int64_t)h * a.lut_size + i, sHist[i]);
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) attention_bwd_dkv_kernel(const ghn3_attention_bwd_args a) {
+  extern __shared__ float bw_smem[];
+  constexpr int DP = D + 1;
+  float* sQ = bw_smem;                         // [QT][DP]   (pre-scaled by d^-1/2)
+  float* sdO = sQ + kBwdKT * DP;               // [QT][DP]
+  float* sBias = sdO + kBwdKT * DP;            // [keys][QT]
+  float* sLse = sBias + kBwdRows * kBwdKT;     // [QT]
+  float* sDelta = sLse + kBwdKT;               // [QT]
+  float* sLut = sDelta + kBwdKT;               // [lut_size]
+
+  const int g = blockIdx.z, h = blockIdx.y;
+  const int n0 = a.node_off[g];
+  const int n = a.node_off[g + 1] - n0;
+  const int j0 = blockIdx.x * kBwdRows;
+  if (j0 >= n) return;
+  const int ld = (n + 15) & ~15;
+  const int C = a.hid, C3 = 3 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qkv = (const T*)a.qkv + (int64_t)n0 * C3;
+  const T* dout = (const T*)a.d_out + (int64_t)n0 * C;
+  const uint16_t* pair = a.pair + a.mat_off[g];
+  const float scale = rsqrtf((float)D);
+
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
+
+  float k[kBwdPerWarp][D], v[kBwdPerWarp][D], dk[kBwdPerWarp][D], dv[kBwdPerWarp][D];
+  int kj[kBwdPerWarp];
+#pragma unroll
+  for (int t = 0; t < kBwdPerWarp; ++t) {
+    kj[t] = j0 + warp * kBwdPerWarp + t;
+    const bool ok = kj[t] < n;
+    const int64_t r = ok ? kj[t] : 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      k[t][d] = ok ? to_float(qkv[r * C3 + C + h * D + d]) : 0.f;
+      v[t][d] = ok ? to_float(qkv[r * C3 + 2 * C + h * D + d]) : 0.f;
+      dk[t][d] = 0.f;
+      dv[t][d] = 0.f;
+    }
+  }
+
+  for (int i0 = 0; i0 < n; i0 += kBwdKT) {
+    const int it = min(kBwdKT, n - i0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < it * D; idx += blockDim.x) {
+      const int i = idx / D, d = idx - i * D;
+      sQ[i * DP + d] = to_float(qkv[(int64_t)(i0 + i) * C3 + h * D + d]) * scale;
+      sdO[i * DP + d] = to_float(dout[(int64_t)(i0 + i) * C + h * D + d]);
+    }
+    for (int i = threadIdx.x; i < it; i += blockDim.x) {
+      sLse[i] = a.lse[(int64_t)h * a.total_nodes + n0 + i0 + i];
+      sDelta[i] = a.delta[(int64_t)h * a.total_nodes + n0 + i0 + i];
+    }
+    for (int idx = threadIdx.x; idx < kBwdKT * kBwdRows; idx += blockDim.x) {
+      const int i = idx / kBwdRows, r = idx - i * kBwdRows;       // 16 consecutive threads read 32 contiguous bytes
+      float b = 0.f;
+      if (i < it && j0 + r < n) b = sLut[pair[(int64_t)(i0 + i) * ld + j0 + r]];
+      sBias[r * kBwdKT + i] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kBwdPerWarp; ++t) {
+      if (kj[t] >= n) continue;
+      const int r = warp * kBwdPerWarp + t;
+#pragma unroll
+      for (int u = 0; u < kBwdKT / 32; ++u) {
+        const int i = lane + 32 * u;
+        if (i < it) {
+          float s = sBias[r * kBwdKT + i], dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            s = fmaf(sQ[i * DP + d], k[t][d], s);
+            dp = fmaf(sdO[i * DP + d], v[t][d], dp);
+          }
+          const float p = __expf(s - sLse[i]);
+          const float ds = p * (dp - sDelta[i]);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            dv[t][d] = fmaf(p, sdO[i * DP + d], dv[t][d]);
+            dk[t][d] = fmaf(ds, sQ[i * DP + d], dk[t][d]);       // sQ already carries d^-1/2
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kBwdPerWarp; ++t) {
+    if (kj[t] >= n) continue;
+    T* dst = (T*)a.d_qkv + (int64_t)(n0 + kj[t]) * C3 + h * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float vk = warp_sum(dk[t][d]);
+      const float vv = warp_sum(dv[t][d]);
+      if (lane == 0) {
+        dst[C + d] = from_float<T>(vk);
+        dst[2 * C + d] = from_float<T>(vv);
+      }
+    }
+  }
+}
+
+template <typename T, int D>
+static int launch_attention_bwd(const ghn3_attention_bwd_args* a, cudaStream_t stream) {
+  constexpr int DP = D + 1;
+  const size_t smem_a = sizeof(float) * (2 * kBwdKT * DP + kBwdRows * kBwdKT + 2 * a->lut_size) +
+                        sizeof(uint16_t) * kBwdRows * kBwdKT;
+  const size_t smem_b = sizeof(float) * (2 * kBwdKT * DP + kBwdRows * kBwdKT + 2 * kBwdKT + a->lut_size);
+  GHN3_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "ghn3_attention_bwd: look-up table too large");
+  GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+  GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  const dim3 grid((unsigned)ceil_div(a->max_nodes, kBwdRows), (unsigned)a->heads, (unsigned)a->n_graphs);
+  attention_bwd_dq_kernel<T, D><<<grid, 256, smem_a, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("attention_bwd_dq_kernel");
+  attention_bwd_dkv_kernel<T, D><<<grid, 256, smem_b, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("attention_bwd_dkv_kernel");
+  return GHN3_OK;
+}
+
+int attention_bwd_impl(const ghn3_attention_bwd_args* a, cudaStream_t stream) {
+  GHN3_REQUIRE(a != nullptr, "ghn3_attention_bwd: null args");
+  GHN3_REQUIRE(a->heads > 0 && a->hid % a->heads == 0, "ghn3_attention_bwd: hid must be divisible by heads");
+  GHN3_REQUIRE(a->lse != nullptr && a->delta != nullptr, "ghn3_attention_bwd: lse / delta workspaces are required");
+  if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
+  const int D = a->hid / a->heads;
+  const bool bf = a->dtype == GHN3_BF16;
+#define GHN3_ATTN_BWD_CASE(DV) \
+  if (D == DV) return bf ? launch_attention_bwd<__nv_bfloat16, DV>(a, stream) : launch_attention_bwd<float, DV>(a, stream);
+  GHN3_ATTN_BWD_CASE(4)
+  GHN3_ATTN_BWD_CASE(8)
+  GHN3_ATTN_BWD_CASE(16)
+  GHN3_ATTN_BWD_CASE(24)
+  GHN3_ATTN_BWD_CASE(32)
+#undef GHN3_ATTN_BWD_CASE
+  set_error("ghn3_attention_bwd: head dim %d is not supported (4, 8, 16, 24, 32)", D);
+  return GHN3_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adjoint of scatter_kernel: every target element sends grad * d(finish)/dv back to the source element it was read
+// from (tiled copies add up). Same descriptor table and index arithmetic as the forward kernel.
+__device__ __forceinline__ uint32_t fdiv_b(uint32_t n, uint32_t mul, uint32_t sh) {
+  return mul ? (__umulhi(n, mul) >> sh) : n;
+}
+
+__global__ void __launch_bounds__(256) scatter_bwd_kernel(const ghn3_scatter_desc* __restrict__ descs,
+                                                          const int32_t* __restrict__ chunk_desc,
+                                                          const float* const* __restrict__ grads,
+                                                          float* const* __restrict__ d_src) {
+  const int di = __ldg(chunk_desc + blockIdx.x);
+  const float* grad = grads[di];
+  float* ds = d_src[di];
+  if (grad == nullptr || ds == nullptr) return;
+  const ghn3_scatter_desc d = descs[di];
+  const uint32_t base = (uint32_t)(((int64_t)blockIdx.x - d.chunk0) * GHN3_SCATTER_CHUNK);
+  const uint32_t end = (uint32_t)min((int64_t)base + GHN3_SCATTER_CHUNK, d.numel);
+  const int mode = d.mode;
+  for (uint32_t e = base + threadIdx.x; e < end; e += 256) {
+    uint32_t r = fdiv_b(e, d.m_t3, d.s_t3);
+    const int x = (int)(e - r * d.t3);
+    uint32_t r2 = fdiv_b(r, d.m_t2, d.s_t2);
+    const int y = (int)(r - r2 * d.t2);
+    const uint32_t a = fdiv_b(r2, d.m_t1, d.s_t1);
+    const uint32_t b = r2 - a * d.t1;
+    const uint32_t am = a - fdiv_b(a, d.m_so, d.s_so) * d.so;
+    const uint32_t bm = b - fdiv_b(b, d.m_si, d.s_si) * d.si;
+    const int64_t col = (int64_t)am * d.ca + bm;
+    const float gval = grad[e];
+    if (mode == 3) {
+      const float sy = fmaxf(((float)y + 0.5f) * ((float)d.kh_src / (float)d.t2) - 0.5f, 0.f);
+      const float sx = fmaxf(((float)x + 0.5f) * ((float)d.kw_src / (float)d.t3) - 0.5f, 0.f);
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, d.kh_src - 1), x1 = min(x0 + 1, d.kw_src - 1);
+      const float ly = sy - (float)y0, lx = sx - (float)x0;
+      const int64_t rb = (int64_t)a * d.ra;
+      const float gs = gval * d.scale;
+      atomicAdd(ds + (rb + y0 * d.kw_src + x0) * d.ld + col, gs * (1.f - ly) * (1.f - lx));
+      atomicAdd(ds + (rb + y0 * d.kw_src + x1) * d.ld + col, gs * (1.f - ly) * lx);
+      atomicAdd(ds + (rb + y1 * d.kw_src + x0) * d.ld + col, gs * ly * (1.f - lx));
+      atomicAdd(ds + (rb + y1 * d.kw_src + x1) * d.ld + col, gs * ly * lx);
+    } else {
+      const int64_t row = (int64_t)a * d.ra + (int64_t)(y + d.cy) * d.kw_src + (x + d.cx);
+      const int64_t si = row * d.ld + col;
+      float dv;
+      if (mode == 1) {
+        const float s = 1.0f / (1.0f + expf(-(0.5f * d.src[si])));
+        dv = s * (1.f - s);                       // d/dv 2*sigmoid(v/2)
+      } else if (mode == 2) {
+        const float t = tanhf(0.2f * d.src[si]);
+        dv = 0.2f * (1.f - t * t);
+      } else {
+        dv = d.scale;
+      }
+      atomicAdd(ds + si, gval * dv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adjoint of node_features_kernel: scatter-add of dx rows into the six embedding tables
+__global__ void __launch_bounds__(256) node_features_bwd_kernel(const ghn3_node_features_bwd_args a) {
+  const int node = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (node >= a.total_nodes) return;
+  const int C = a.hid, Q = C >> 2;
+  const int op = a.op[node];
+  const int4 si = *(const int4*)(a.shape_idx + 4 * (int64_t)node);
+  const int din = a.deg_in[node], dout = a.deg_out[node], d0 = a.dist0[node];
+  for (int c = lane; c < C; c += 32) {
+    const float g = a.dx[(int64_t)node * C + c];
+    const int q = c / Q, cc = c - q * Q;
+    const int sidx = q == 0 ? si.x : (q == 1 ? si.y : (q == 2 ? si.z : si.w));
+    float* stab = q < 2 ? a.d_embed_ch : a.d_embed_sp;
+    atomicAdd(a.d_embed_op + (int64_t)op * C + c, g);
+    atomicAdd(stab + (int64_t)sidx * Q + cc, g);
+    atomicAdd(a.d_cent_in + (int64_t)din * C + c, g);
+    atomicAdd(a.d_cent_out + (int64_t)dout * C + c, g);
+    atomicAdd(a.d_dist_embed + (int64_t)d0 * C + c, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adjoint of the edge-bias look-up table (edge_lut_stage1/2). P = stage-1 projections [2][V][C] (recomputed by the
+// caller with the forward kernel), dP zero-initialised by the entry point.
+__global__ void __launch_bounds__(256) edge_lut_bwd_stage2(int C, int V, int H, const float* __restrict__ P,
+                                                           const float* __restrict__ b1, const float* __restrict__ W2,
+                                                           const float* __restrict__ dlut, float* __restrict__ dP,
+                                                           float* __restrict__ db1, float* __restrict__ dW2,
+                                                           float* __restrict__ db2) {
+  extern __shared__ float lb_smem[];
+  float* sW2 = lb_smem;              // [H][C] gradient accumulator
+  float* sB1 = sW2 + H * C;          // [C]
+  float* sB2 = sB1 + C;              // [H]
+  for (int i = threadIdx.x; i < H * C + C + H; i += blockDim.x) lb_smem[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ab = blockIdx.x * 8 + warp; ab < V * V; ab += gridDim.x * 8) {
+    const int av = ab / V, bv = ab % V;
+    const float* pa = P + (int64_t)av * C;
+    const float* pb = P + (int64_t)(V + bv) * C;
+    const float dl_lane = lane < H ? dlut[(int64_t)lane * V * V + ab] : 0.f;     // H <= 32
+    if (lane < H && dl_lane != 0.f) atomicAdd(sB2 + lane, dl_lane);
+    for (int c = lane; c < C; c += 32) {
+      const float t = fmaxf((pa[c] + pb[c]) + b1[c], 0.f);
+      float dt = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const float dl = __shfl_sync(0xffffffffu, dl_lane, h);
+        dt = fmaf(dl, W2[(int64_t)h * C + c], dt);
+        if (t > 0.f) atomicAdd(sW2 + h * C + c, dl * t);
+      }
+      if (t > 0.f && dt != 0.f) {
+        atomicAdd(sB1 + c, dt);
+        atomicAdd(dP + (int64_t)av * C + c, dt);
+        atomicAdd(dP + (int64_t)(V + bv) * C + c, dt);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * C; i += blockDim.x)
+    if (sW2[i] != 0.f) atomicAdd(dW2 + i, sW2[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    if (sB1[i] != 0.f) atomicAdd(db1 + i, sB1[i]);
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    if (sB2[i] != 0.f) atomicAdd(db2 + i, sB2[i]);
+}
+
+// dW1[c][side*C + k] += sum_v dP[side][v][c] * E[v+2][k]
+__global__ void __launch_bounds__(256) edge_lut_bwd_w1(int C, int V, const float* __restrict__ E,
+                                                       const float* __restrict__ dP, float* __restrict__ dW1) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (int64_t)C * 2 * C) return;
+  const int c = (int)(o / (2 * C)), sk = (int)(o % (2 * C));
+  const int side = sk / C, k = sk - side * C;
+  float acc = 0.f;
+  for (int v = 0; v < V; ++v) acc = fmaf(dP[((int64_t)side * V + v) * C + c], E[(int64_t)(v + 2) * C + k], acc);
+  dW1[o] += acc;
+}
+
+// dE[v+2][k] += sum_side sum_c dP[side][v][c] * W1[c][side*C + k]
+__global__ void __launch_bounds__(256) edge_lut_bwd_embed(int C, int V, const float* __restrict__ W1,
+                                                          const float* __restrict__ dP, float* __restrict__ dE) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= V * C) return;
+  const int v = o / C, k = o - v * C;
+  float acc = 0.f;
+  for (int side = 0; side < 2; ++side)
+    for (int c = 0; c < C; ++c)
+      acc = fmaf(dP[((int64_t)side * V + v) * C + c], W1[(int64_t)c * 2 * C + side * C + k], acc);
+  dE[(int64_t)(v + 2) * C + k] += acc;
+}
+
+}  // namespace ghn3
+
+using namespace ghn3;
+
+extern "C" int ghn3_transpose(const ghn3_transpose_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->src != nullptr && a->dst != nullptr, "ghn3_transpose: null args");
+  if (a->rows <= 0 || a->cols <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->ld_dst >= a->rows && a->ld_src >= a->cols, "ghn3_transpose: leading dimensions too small");
+  const dim3 grid((unsigned)ceil_div(a->cols, 32), (unsigned)ceil_div(a->rows, 32));
+  GHN3_REQUIRE(grid.y < 65536, "ghn3_transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("transpose_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_elementwise(const ghn3_elementwise_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->a != nullptr && a->out != nullptr, "ghn3_elementwise: null args");
+  GHN3_REQUIRE(a->op >= GHN3_EW_COPY && a->op <= GHN3_EW_ADD, "ghn3_elementwise: bad op");
+  GHN3_REQUIRE(a->op == GHN3_EW_COPY || a->op == GHN3_EW_GELU || a->b != nullptr, "ghn3_elementwise: second operand missing");
+  if (a->n <= 0) return GHN3_OK;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->n, 256), (int64_t)num_sms() * 16);
+  elementwise_kernel<<<blocks, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("elementwise_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_colsum(const ghn3_colsum_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->src != nullptr && a->dst != nullptr, "ghn3_colsum: null args");
+  if (a->rows <= 0 || a->cols <= 0) return GHN3_OK;
+  const dim3 grid((unsigned)ceil_div(a->cols, 32), (unsigned)ceil_div(a->rows, 256));
+  GHN3_REQUIRE(grid.y < 65536, "ghn3_colsum: too many rows");
+  colsum_kernel<<<grid, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("colsum_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_layernorm_bwd: null args");
+  GHN3_REQUIRE(a->hid > 0 && a->hid <= 32 * kLnMaxT, "ghn3_layernorm_bwd: hid must be <= 1024");
+  GHN3_REQUIRE(a->x && a->gamma && a->dy && a->dx && a->dgamma && a->dbeta, "ghn3_layernorm_bwd: null pointer");
+  if (a->rows <= 0) return GHN3_OK;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 8), (int64_t)num_sms() * 2);
+  layernorm_bwd_kernel<<<blocks, 256, sizeof(float) * 2 * a->hid, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("layernorm_bwd_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_attention_bwd(const ghn3_attention_bwd_args* a, ghn3_stream_t stream) {
+  return attention_bwd_impl(a, (cudaStream_t)stream);
+}
+
+extern "C" int ghn3_scatter_bwd(const ghn3_scatter_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_scatter_bwd: null args");
+  if (a->n_descs <= 0 || a->n_chunks <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->chunk_desc != nullptr && a->grads != nullptr && a->d_src != nullptr && a->descs != nullptr,
+               "ghn3_scatter_bwd: descriptor, chunk, gradient and source-gradient tables are required");
+  GHN3_REQUIRE(a->n_chunks < (int64_t)2147483647, "ghn3_scatter_bwd: too many chunks");
+  scatter_bwd_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(a->descs, a->chunk_desc, a->grads, a->d_src);
+  GHN3_LAUNCH_CHECK("scatter_bwd_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_node_features_bwd(const ghn3_node_features_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->dx != nullptr, "ghn3_node_features_bwd: null args");
+  GHN3_REQUIRE(a->hid > 0 && a->hid % 4 == 0, "ghn3_node_features_bwd: hid must be a multiple of 4");
+  if (a->total_nodes <= 0) return GHN3_OK;
+  node_features_bwd_kernel<<<(unsigned)ceil_div(a->total_nodes, 8), 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("node_features_bwd_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_edge_lut_bwd(const ghn3_edge_lut_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->d_lut != nullptr && a->workspace != nullptr, "ghn3_edge_lut_bwd: null args");
+  GHN3_REQUIRE(a->heads > 0 && a->heads <= 32, "ghn3_edge_lut_bwd: at most 32 heads");
+  const int C = a->hid, V = a->vmax + 1, H = a->heads;
+  // workspace: P [2][V][C] | dP [2][V][C]
+  float* P = a->workspace;
+  float* dP = P + (int64_t)2 * V * C;
+  ghn3_edge_lut_args f = {};
+  f.hid = C; f.heads = H; f.vmax = a->vmax;
+  f.edge_embed = a->edge_embed; f.w1 = a->w1; f.b1 = a->b1; f.w2 = a->w2; f.b2 = nullptr; f.workspace = P; f.lut = nullptr;
+  int rc = ghn3_edge_lut(&f, stream_);          // lut == NULL: stage 1 only
+  if (rc != GHN3_OK) return rc;
+  GHN3_CUDA(cudaMemsetAsync(dP, 0, sizeof(float) * 2 * V * C, stream));
+  const size_t smem = sizeof(float) * ((size_t)H * C + C + H);
+  GHN3_REQUIRE(smem <= 160 * 1024, "ghn3_edge_lut_bwd: heads * hid too large");
+  GHN3_CUDA(cudaFuncSetAttribute(edge_lut_bwd_stage2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div((int64_t)V * V, 8), num_sms());
+  edge_lut_bwd_stage2<<<blocks, 256, smem, stream>>>(C, V, H, P, a->b1, a->w2, a->d_lut, dP, a->d_b1, a->d_w2, a->d_b2);
+  GHN3_LAUNCH_CHECK("edge_lut_bwd_stage2");
+  edge_lut_bwd_w1<<<(unsigned)ceil_div((int64_t)C * 2 * C, 256), 256, 0, stream>>>(C, V, a->edge_embed, dP, a->d_w1);
+  GHN3_LAUNCH_CHECK("edge_lut_bwd_w1");
+  edge_lut_bwd_embed<<<(unsigned)ceil_div((int64_t)V * C, 256), 256, 0, stream>>>(C, V, a->w1, dP, a->d_edge_embed);
+  GHN3_LAUNCH_CHECK("edge_lut_bwd_embed");
+  return GHN3_OK;
+}

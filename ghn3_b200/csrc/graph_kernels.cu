@@ -298,6 +298,7 @@ extern "C" int ghn3_edge_lut(const ghn3_edge_lut_args* a, ghn3_stream_t stream_)
   const int V = a->vmax + 1, C = a->hid;
   edge_lut_stage1<<<(unsigned)ceil_div(2 * V * C, 8), 256, 0, stream>>>(C, V, a->edge_embed, a->w1, a->workspace);
   GHN3_LAUNCH_CHECK("edge_lut_stage1");
+  if (a->lut == nullptr) return GHN3_OK;       // projections only (used by ghn3_edge_lut_bwd)
   if (a->heads <= 8) {
     edge_lut_stage2<8><<<(unsigned)ceil_div(V * V, 8), 256, 0, stream>>>(C, V, a->heads, a->workspace, a->b1, a->w2, a->b2, a->lut);
   } else if (a->heads <= 16) {

@@ -257,3 +257,80 @@ def convert(src, dst_dtype):
     L.check(L.load().ghn3_convert_f32(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(src.numel()),
                                       C.c_int32(dst_dtype), C.c_void_p(L.current_stream())), 'ghn3_convert_f32')
     return dst
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training path: thin wrappers of the adjoint kernels (see include/ghn3_b200.h, "Training path")
+def _dt(t):
+    return BF16 if t.dtype == torch.bfloat16 else F32
+
+
+def transpose(src, dst_dtype=None, group=0, group_stride=0, rows=None, pad=8, out=None):
+    """dst[c, r] = src[row(r), c]; the destination row stride is rounded up to `pad` elements (TMA alignment).
+    Returns the [cols, rows] view of the padded buffer."""
+    _require_cuda(src, 'src')
+    assert src.dim() == 2 and src.stride(1) == 1
+    rows = src.shape[0] if rows is None else rows
+    cols = src.shape[1]
+    dd = _dt(src) if dst_dtype is None else dst_dtype
+    ld = (rows + pad - 1) // pad * pad
+    if out is None:
+        out = torch.zeros(cols, ld, dtype=TORCH_DTYPE[dd], device=src.device)
+    a = L.TransposeArgs(src=L.ptr(src), src_dtype=_dt(src), ld_src=src.stride(0), rows=rows, cols=cols, group=group,
+                        group_stride=group_stride, dst=L.ptr(out), dst_dtype=dd, ld_dst=out.stride(0))
+    L.call('transpose', a, L.current_stream())
+    return out[:, :rows]
+
+
+def elementwise(op, a, b=None, out=None, out_dtype=None):
+    _require_cuda(a, 'a')
+    od = _dt(a) if out_dtype is None else out_dtype
+    if out is None:
+        out = torch.empty(a.shape, dtype=TORCH_DTYPE[od], device=a.device)
+    args = L.ElementwiseArgs(op=op, n=a.numel(), a=L.ptr(a), a_dtype=_dt(a), b=L.ptr(b),
+                             b_dtype=_dt(b) if b is not None else F32, out=L.ptr(out), out_dtype=od)
+    L.call('elementwise', args, L.current_stream())
+    return out
+
+
+def colsum(src, dst, group=0, group_stride=0):
+    _require_cuda(src, 'src')
+    a = L.ColsumArgs(src=L.ptr(src), src_dtype=_dt(src), ld=src.stride(0), rows=src.shape[0], cols=src.shape[1],
+                     group=group, group_stride=group_stride, dst=L.ptr(dst))
+    L.call('colsum', a, L.current_stream())
+    return dst
+
+
+def layernorm_bwd(x, gamma, dy, dx, dgamma, dbeta, accumulate=False, dy_row=None):
+    _require_cuda(x, 'x')
+    a = L.LayerNormBwdArgs(rows=x.shape[0], hid=x.shape[1], x=L.ptr(x), gamma=L.ptr(gamma), dy=L.ptr(dy),
+                           dy_dtype=_dt(dy), dy_row=L.ptr(dy_row), dx=L.ptr(dx), accumulate=int(accumulate),
+                           dgamma=L.ptr(dgamma), dbeta=L.ptr(dbeta))
+    L.call('layernorm_bwd', a, L.current_stream())
+    return dx
+
+
+def attention_bwd(qkv, out, d_out, pack, lut, hid, heads, d_lut=None):
+    _require_cuda(qkv, 'qkv')
+    M = qkv.shape[0]
+    d_qkv = torch.empty_like(qkv)
+    ws = torch.empty(2, heads, M, dtype=torch.float32, device=qkv.device)
+    a = L.AttentionBwdArgs(n_graphs=pack.n_graphs, hid=hid, heads=heads, max_nodes=pack.max_nodes, total_nodes=M,
+                           lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']), mat_off=L.ptr(pack.d['mat_off']),
+                           qkv=L.ptr(qkv), out=L.ptr(out), d_out=L.ptr(d_out), dtype=_dt(qkv), pair=L.ptr(pack.pair),
+                           lut=L.ptr(lut), d_qkv=L.ptr(d_qkv), d_lut=L.ptr(d_lut), lse=L.ptr(ws[0]),
+                           delta=L.ptr(ws[1]))
+    L.call('attention_bwd', a, L.current_stream())
+    return d_qkv
+
+
+def edge_lut_bwd(edge_embed, w1, b1, w2, d_lut, vmax, grads):
+    """grads: dict of zero-initialised fp32 tensors edge_embed, w1, b1, w2, b2 that receive the gradients (+=)."""
+    C_, H = w1.shape[0], w2.shape[0]
+    ws = torch.empty(4 * (vmax + 1) * C_, dtype=torch.float32, device=w1.device)
+    a = L.EdgeLutBwdArgs(hid=C_, heads=H, vmax=vmax, edge_embed=L.ptr(edge_embed), w1=L.ptr(w1), b1=L.ptr(b1),
+                         w2=L.ptr(w2), d_lut=L.ptr(d_lut), workspace=L.ptr(ws), d_edge_embed=L.ptr(grads['edge_embed']),
+                         d_w1=L.ptr(grads['w1']), d_b1=L.ptr(grads['b1']), d_w2=L.ptr(grads['w2']),
+                         d_b2=L.ptr(grads['b2']))
+    L.call('edge_lut_bwd', a, L.current_stream())
+    return grads

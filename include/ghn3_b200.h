@@ -362,6 +362,116 @@ typedef struct {
 } ghn3_relu_transpose_args;
 int ghn3_relu_transpose(const ghn3_relu_transpose_args* args, ghn3_stream_t stream);
 
+/* ===============================================================================================================
+ * Training path: adjoints of the kernels above, used by GHN3.forward(keep_grads=True) so that
+ * autograd can flow from the target networks' loss into the GHN parameters (reference: ghn3/trainer.py:238-411,
+ * ghn3/nn.py:526-545). Gradients of GHN parameters are fp32 and are ACCUMULATED (+=) into caller-zeroed buffers
+ * unless stated otherwise.
+ * ============================================================================================================= */
+
+/* dst[c][r] = src[row(r)][c], row(r) = (r / group) * group_stride + r % group when group > 0, else r.
+ * src/dst dtypes are GHN3_BF16 / GHN3_TF32 / GHN3_F32 storage tags. Produces the K-major operands of the dgrad /
+ * wgrad GEMMs (W^T, X^T, dY^T). */
+typedef struct {
+  const void* src; int32_t src_dtype; int64_t ld_src;
+  int32_t rows, cols;
+  int32_t group, group_stride;
+  void* dst; int32_t dst_dtype; int64_t ld_dst;
+} ghn3_transpose_args;
+int ghn3_transpose(const ghn3_transpose_args* args, ghn3_stream_t stream);
+
+enum ghn3_elementwise_op {
+  GHN3_EW_COPY = 0,       /* out = a (dtype conversion) */
+  GHN3_EW_GELU = 1,       /* out = gelu(a), exact erf form (ghn3/nn.py:142) */
+  GHN3_EW_GELU_BWD = 2,   /* out = a * gelu'(b) */
+  GHN3_EW_RELU_BWD = 3,   /* out = a * (b > 0) */
+  GHN3_EW_ADD = 4         /* out = a + b */
+};
+typedef struct {
+  int32_t op;
+  int64_t n;
+  const void* a; int32_t a_dtype;
+  const void* b; int32_t b_dtype;
+  void* out; int32_t out_dtype;
+} ghn3_elementwise_args;
+int ghn3_elementwise(const ghn3_elementwise_args* args, ghn3_stream_t stream);
+
+/* dst[col(c)] += sum_r src[r][c] (bias gradients); col(c) uses the same (group, group_stride) mapping as above. */
+typedef struct {
+  const void* src; int32_t src_dtype; int64_t ld;
+  int32_t rows, cols;
+  int32_t group, group_stride;
+  float* dst;
+} ghn3_colsum_args;
+int ghn3_colsum(const ghn3_colsum_args* args, ghn3_stream_t stream);
+
+/* LayerNorm backward (eps 1e-5): dx (+)= dLN/dx . dy, dgamma += sum dy * xhat, dbeta += sum dy.
+ * dy_row (optional): the gradient of row r is row dy_row[r] of dy (< 0: no gradient) -- the adjoint of the row
+ * scatter of ghn3_layernorm (final LayerNorm -> decoder input rows). */
+typedef struct {
+  int32_t rows, hid;
+  const float* x;            /* forward input [rows][C] */
+  const float* gamma;
+  const void* dy; int32_t dy_dtype;
+  const int32_t* dy_row;
+  float* dx;                 /* [rows][C] fp32 */
+  int32_t accumulate;        /* 1: dx += ..., 0: dx = ... (rows without gradient are left untouched) */
+  float* dgamma; float* dbeta;
+} ghn3_layernorm_bwd_args;
+int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* args, ghn3_stream_t stream);
+
+/* Attention backward (adjoint of ghn3_attention): given qkv, the forward output and d_out, writes d_qkv [M][3C]
+ * (same dtype) and accumulates the edge-bias gradient d_lut[h][pair(i,j)] += dS_ij (the bias is shared by all
+ * layers, ghn3/graphormer.py:126-130). Softmax statistics are recomputed; lse / delta are [H][total_nodes] fp32
+ * workspaces. */
+typedef struct {
+  int32_t n_graphs, hid, heads, max_nodes, total_nodes;
+  int32_t lut_size;
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  const void* qkv;
+  const void* out;           /* forward attention output [M][C] */
+  const void* d_out;         /* [M][C] */
+  int32_t dtype;             /* storage of qkv / out / d_out / d_qkv: GHN3_BF16, else fp32 */
+  const uint16_t* pair;
+  const float* lut;
+  void* d_qkv;               /* out [M][3C] */
+  float* d_lut;              /* += [H][lut_size], may be NULL */
+  float* lse; float* delta;  /* workspaces [H][total_nodes] */
+} ghn3_attention_bwd_args;
+int ghn3_attention_bwd(const ghn3_attention_bwd_args* args, ghn3_stream_t stream);
+
+/* Adjoint of ghn3_scatter: grads[i] is the gradient of the i-th target tensor (NULL: none), d_src[i] the fp32
+ * gradient buffer parallel to descs[i].src (same indexing); contributions are added atomically. */
+typedef struct {
+  const ghn3_scatter_desc* descs;
+  int32_t n_descs;
+  int64_t n_chunks;
+  const int32_t* chunk_desc;        /* required */
+  const float* const* grads;        /* device [n_descs] */
+  float* const* d_src;              /* device [n_descs] */
+} ghn3_scatter_bwd_args;
+int ghn3_scatter_bwd(const ghn3_scatter_bwd_args* args, ghn3_stream_t stream);
+
+/* Adjoint of ghn3_node_features: scatter-add of dx rows into the embedding-table gradients. */
+typedef struct {
+  int32_t total_nodes, hid;
+  const int32_t* op; const int32_t* shape_idx; const int32_t* deg_in; const int32_t* deg_out; const int32_t* dist0;
+  const float* dx;
+  float* d_embed_op; float* d_embed_ch; float* d_embed_sp; float* d_cent_in; float* d_cent_out; float* d_dist_embed;
+} ghn3_node_features_bwd_args;
+int ghn3_node_features_bwd(const ghn3_node_features_bwd_args* args, ghn3_stream_t stream);
+
+/* Adjoint of ghn3_edge_lut. workspace: 4*(vmax+1)*C floats. */
+typedef struct {
+  int32_t hid, heads, vmax;
+  const float* edge_embed; const float* w1; const float* b1; const float* w2;
+  const float* d_lut;        /* [H][(vmax+1)^2] */
+  float* workspace;
+  float* d_edge_embed; float* d_w1; float* d_b1; float* d_w2; float* d_b2;
+} ghn3_edge_lut_bwd_args;
+int ghn3_edge_lut_bwd(const ghn3_edge_lut_bwd_args* args, ghn3_stream_t stream);
+
 /* Runs a prebuilt sequence of the entry points above with ONE call (the host side of `ghn(model)` is then a single
  * FFI crossing per prediction): ops[i].args points to the argument struct of the entry point named by ops[i].op. */
 enum ghn3_opcode {
