@@ -176,13 +176,46 @@ class EdgeLutBwdArgs(C.Structure):
                 ('d_b2', vp)]
 
 
+class FcBwdArgs(C.Structure):
+    _fields_ = [('problems', vp), ('n_problems', i32), ('max_m', i32), ('rowmap', vp), ('dh0', vp), ('dtype', i32),
+                ('dec_in', vp), ('fc_w', vp), ('hid', i32), ('n_out', i32), ('grid_positions', i32), ('d_fc_w', vp),
+                ('d_fc_b', vp), ('d_dec_in', vp)]
+
+
+class ReluTransposeBwdArgs(C.Structure):
+    _fields_ = [('src', vp), ('d_src', vp), ('ld', i64), ('src_bs', i64), ('d_rt', vp), ('rows', i32), ('cols', i32),
+                ('batch', i32)]
+
+
+class GraphormerTrainArgs(C.Structure):
+    _fields_ = [('fwd', GraphormerArgs), ('xs', vp), ('xm', vp), ('h1', vp), ('qkv', vp), ('ao', vp), ('h2', vp),
+                ('u', vp), ('g', vp)]
+
+
+class LayerWeightsT(C.Structure):
+    _fields_ = [('w_qkv_t', vp), ('w_out_t', vp), ('w_ff1_t', vp), ('w_ff2_t', vp)]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [('ln1_w', vp), ('ln1_b', vp), ('w_qkv', vp), ('w_out', vp), ('b_out', vp), ('ln2_w', vp),
+                ('ln2_b', vp), ('w_ff1', vp), ('b_ff1', vp), ('w_ff2', vp), ('b_ff2', vp)]
+
+
+class GraphormerBwdArgs(C.Structure):
+    _fields_ = [('saved', C.POINTER(GraphormerTrainArgs)), ('layers_t_host', C.POINTER(LayerWeightsT)),
+                ('grads_host', C.POINTER(LayerGrads)), ('d_ln_w', vp), ('d_ln_b', vp), ('d_dec_in', vp),
+                ('d_dec_dtype', i32), ('d_lut', vp), ('dx', vp), ('dxa', vp), ('dh', vp), ('dhf', vp), ('dqkv', vp),
+                ('dff', vp), ('ta', vp), ('tb', vp), ('m_pad', i32), ('lse', vp), ('delta', vp)]
+
+
 assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
            'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
-                 'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd']
+                 'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
+                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd']
 SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None

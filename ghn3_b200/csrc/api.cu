@@ -136,6 +136,18 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
       case GHN3_OP_GEMM_SIMT: rc = ghn3_gemm_simt((const ghn3_gemm_simt_args*)ops[i].args, stream); break;
       case GHN3_OP_SCATTER: rc = ghn3_scatter((const ghn3_scatter_args*)ops[i].args, stream); break;
       case GHN3_OP_RELU_TRANSPOSE: rc = ghn3_relu_transpose((const ghn3_relu_transpose_args*)ops[i].args, stream); break;
+      case GHN3_OP_GRAPHORMER_TRAIN_FWD: rc = ghn3_graphormer_train_fwd((const ghn3_graphormer_train_args*)ops[i].args, stream); break;
+      case GHN3_OP_GRAPHORMER_BWD: rc = ghn3_graphormer_bwd((const ghn3_graphormer_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_TRANSPOSE: rc = ghn3_transpose((const ghn3_transpose_args*)ops[i].args, stream); break;
+      case GHN3_OP_ELEMENTWISE: rc = ghn3_elementwise((const ghn3_elementwise_args*)ops[i].args, stream); break;
+      case GHN3_OP_COLSUM: rc = ghn3_colsum((const ghn3_colsum_args*)ops[i].args, stream); break;
+      case GHN3_OP_LAYERNORM_BWD: rc = ghn3_layernorm_bwd((const ghn3_layernorm_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_ATTENTION_BWD: rc = ghn3_attention_bwd((const ghn3_attention_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_SCATTER_BWD: rc = ghn3_scatter_bwd((const ghn3_scatter_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_NODE_FEATURES_BWD: rc = ghn3_node_features_bwd((const ghn3_node_features_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_EDGE_LUT_BWD: rc = ghn3_edge_lut_bwd((const ghn3_edge_lut_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_FC_BWD: rc = ghn3_fc_bwd((const ghn3_fc_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_RELU_TRANSPOSE_BWD: rc = ghn3_relu_transpose_bwd((const ghn3_relu_transpose_bwd_args*)ops[i].args, stream); break;
       default:
         ghn3::set_error("ghn3_run_sequence: unknown op %d at index %d", ops[i].op, i);
         return GHN3_ERR_BAD_ARG;

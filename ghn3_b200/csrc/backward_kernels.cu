@@ -594,6 +594,122 @@ __global__ void __launch_bounds__(256) edge_lut_bwd_embed(int C, int V, const fl
   dE[(int64_t)(v + 2) * C + k] += acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decoder fc stage backward (forward: one GEMM problem per decoder-grid position, reference ghn3/nn.py:738-745).
+// Works on the ORIGINAL fp32 parameter layout fc.weight[(j*S*S + pos)][c], fc.bias[j*S*S + pos]; the (node, position)
+// rows of dh0 are found through the forward row map.
+//   d_w[(j, pos)][c] += sum_k dh0[row(k)][j] * x[a_row0 + k][c];  d_b[(j, pos)] += sum_k dh0[row(k)][j]
+__global__ void __launch_bounds__(256) fc_wgrad_kernel(const ghn3_fc_bwd_args a) {
+  __shared__ float sG[16][65];
+  __shared__ float sX[16][65];
+  const ghn3_gemm_problem p = a.problems[blockIdx.z];
+  const int C = a.hid, J = a.n_out, SS = a.grid_positions;
+  const int pos = p.b_row0 / J;
+  const int j0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tj = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  for (int k0 = 0; k0 < p.m; k0 += 16) {
+    const int kt = min(16, p.m - k0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+      const int kk = idx >> 6, e = idx & 63;
+      float g = 0.f, x = 0.f;
+      if (kk < kt) {
+        const int64_t row = a.rowmap[p.d_off + k0 + kk];
+        if (j0 + e < J) g = ld_f(a.dh0, row * J + j0 + e, a.dtype);
+        if (c0 + e < C) x = ld_f(a.dec_in, (int64_t)(p.a_row0 + k0 + kk) * C + c0 + e, a.dtype);
+      }
+      sG[kk][e] = g;
+      sX[kk][e] = x;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < kt; ++kk) {
+      float g[4], x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { g[i] = sG[kk][tj * 4 + i]; x[i] = sX[kk][tc * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(g[i], x[j], acc[i][j]);
+      if (blockIdx.y == 0 && threadIdx.x < 64) bsum += sG[kk][threadIdx.x];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + tj * 4 + i;
+    if (j >= J) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int c = c0 + tc * 4 + jj;
+      if (c < C && acc[i][jj] != 0.f) atomicAdd(a.d_fc_w + ((int64_t)j * SS + pos) * C + c, acc[i][jj]);
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 64 && j0 + threadIdx.x < J && bsum != 0.f)
+    atomicAdd(a.d_fc_b + (int64_t)(j0 + threadIdx.x) * SS + pos, bsum);
+}
+
+//   d_x[a_row0 + k][c] += sum_j dh0[row(k)][j] * w[(j, pos)][c]
+__global__ void __launch_bounds__(256) fc_dgrad_kernel(const ghn3_fc_bwd_args a) {
+  __shared__ float sW[32][64];
+  __shared__ float sG[16][33];
+  const ghn3_gemm_problem p = a.problems[blockIdx.z];
+  const int k0 = blockIdx.y * 16;
+  if (k0 >= p.m) return;
+  const int kt = min(16, p.m - k0);
+  const int C = a.hid, J = a.n_out, SS = a.grid_positions;
+  const int pos = p.b_row0 / J;
+  const int c0 = blockIdx.x * 64;
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < J; j0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+      const int jj = idx >> 6, e = idx & 63;
+      float w = 0.f;
+      if (j0 + jj < J && c0 + e < C) w = a.fc_w[((int64_t)(j0 + jj) * SS + pos) * C + c0 + e];
+      sW[jj][e] = w;
+    }
+    for (int idx = threadIdx.x; idx < 16 * 32; idx += 256) {
+      const int kk = idx >> 5, jj = idx & 31;
+      float g = 0.f;
+      if (kk < kt && j0 + jj < J) g = ld_f(a.dh0, (int64_t)a.rowmap[p.d_off + k0 + kk] * J + j0 + jj, a.dtype);
+      sG[kk][jj] = g;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float g = sG[tr][jj];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(g, sW[jj][tc * 4 + i], acc[i]);
+    }
+  }
+  if (tr < kt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + tc * 4 + i;
+      if (c < C && acc[i] != 0.f) atomicAdd(a.d_dec_in + (int64_t)(p.a_row0 + k0 + tr) * C + c, acc[i]);
+    }
+  }
+}
+
+// Adjoint of relu_transpose_kernel: d_src[z*src_bs + r*ld + c] += (src > 0) * d_rt[(z*cols + c)*rows + r]
+__global__ void __launch_bounds__(256) relu_transpose_bwd_kernel(const ghn3_relu_transpose_bwd_args a) {
+  const int64_t total = (int64_t)a.batch * a.rows * a.cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % a.cols);
+    const int r = (int)((i / a.cols) % a.rows);
+    const int64_t z = i / ((int64_t)a.cols * a.rows);
+    const int64_t si = z * a.src_bs + (int64_t)r * a.ld + c;
+    if (a.src[si] > 0.f) a.d_src[si] += a.d_rt[(z * a.cols + c) * a.rows + r];
+  }
+}
+
 }  // namespace ghn3
 
 using namespace ghn3;
@@ -695,5 +811,32 @@ extern "C" int ghn3_edge_lut_bwd(const ghn3_edge_lut_bwd_args* a, ghn3_stream_t 
   GHN3_LAUNCH_CHECK("edge_lut_bwd_w1");
   edge_lut_bwd_embed<<<(unsigned)ceil_div((int64_t)V * C, 256), 256, 0, stream>>>(C, V, a->w1, dP, a->d_edge_embed);
   GHN3_LAUNCH_CHECK("edge_lut_bwd_embed");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_fc_bwd(const ghn3_fc_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_fc_bwd: null args");
+  if (a->n_problems <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->problems && a->rowmap && a->dh0 && a->dec_in && a->fc_w && a->d_fc_w && a->d_fc_b && a->d_dec_in,
+               "ghn3_fc_bwd: null pointer");
+  GHN3_REQUIRE(a->n_problems < 65536 && a->max_m > 0, "ghn3_fc_bwd: too many problems / max_m missing");
+  const dim3 gw((unsigned)ceil_div(a->n_out, 64), (unsigned)ceil_div(a->hid, 64), (unsigned)a->n_problems);
+  fc_wgrad_kernel<<<gw, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("fc_wgrad_kernel");
+  const dim3 gd((unsigned)ceil_div(a->hid, 64), (unsigned)ceil_div(a->max_m, 16), (unsigned)a->n_problems);
+  fc_dgrad_kernel<<<gd, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("fc_dgrad_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_relu_transpose_bwd(const ghn3_relu_transpose_bwd_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr && a->src && a->d_src && a->d_rt, "ghn3_relu_transpose_bwd: null args");
+  const int64_t total = (int64_t)a->batch * a->rows * a->cols;
+  if (total <= 0) return GHN3_OK;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)num_sms() * 16);
+  relu_transpose_bwd_kernel<<<blocks, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("relu_transpose_bwd_kernel");
   return GHN3_OK;
 }

@@ -279,9 +279,7 @@ class GHN3(GHN):
         device = self.embed.weight.device
         if device.type != 'cuda':
             raise RuntimeError('ghn3_b200: the GHN must be on a CUDA device (got %s); there is no CPU path' % device)
-        if keep_grads or (keep_grads is None and self.training):
-            raise NotImplementedError('ghn3_b200: keep_grads=True (training the GHN through the predicted '
-                                      'parameters) is not implemented in the CUDA path yet')
+        keep_grads = self.training if keep_grads is None else bool(keep_grads)       # nn.py:525
         is_lst = isinstance(nets_torch, (list, tuple))
         nets = list(nets_torch) if is_lst else [nets_torch]
         if len(nets) == 0:                                   # empty batch: nothing to predict
@@ -297,7 +295,11 @@ class GHN3(GHN):
 
         w = self._device_weights()
         bp = self._batch_plan(graphs, nets, predict_class_layers, reduce_graph)
-        emb = self._run(w, graphs.pack, bp, return_embeddings)
+        if keep_grads:
+            from .train import forward_keep_grads
+            emb = forward_keep_grads(self, nets, graphs, w, bp, return_embeddings)
+        else:
+            emb = self._run(w, graphs.pack, bp, return_embeddings)
 
         if bn_track_running_stats is None:
             bn_track_running_stats = self.training
@@ -427,10 +429,12 @@ class _Program:
     The kernel sequence of one batch plan with every argument struct prebuilt and every workspace buffer allocated
     once; per call only the graph-pack pointers and (if they moved) the target-parameter addresses are patched.
     """
-    OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6}
+    OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6,
+          'graphormer_train_fwd': 7}
 
-    def __init__(self, ghn, w, bp, device, want_emb):
+    def __init__(self, ghn, w, bp, device, want_emb, train=False):
         self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
+        self.train = train
         dt, x3, act = w['dtype'], w['x3'], w['act']
         tdt = ops.TORCH_DTYPE[dt]
         C, H = ghn.hid, ghn.heads
@@ -443,7 +447,11 @@ class _Program:
         self.keep = []
         self.ops = []            # (stage label, op code, ctypes args struct)
         # ---- node features ----
-        self.x = E(N, C, dtype=torch.float32)
+        if train:                # residual stream of every layer is kept for the backward pass
+            self.xs = E(ghn.layers + 1, N, C, dtype=torch.float32)
+            self.x = self.xs[0]
+        else:
+            self.x = E(N, C, dtype=torch.float32)
         t = w['tables']
         self.nf = L.NodeFeaturesArgs(total_nodes=N, hid=C, shape_idx=L.ptr(st['shape_idx']),
                                      embed_op=L.ptr(t['embed_op']), embed_ch=L.ptr(t['embed_ch']),
@@ -464,8 +472,18 @@ class _Program:
                                    dec_dtype=act, dst_row=L.ptr(st['dst_row']), emb_f32=L.ptr(self.emb),
                                    ln_counters=L.ptr(self.ln_counters) if FUSE_LN else None, h2=L.ptr(self.h2),
                                    tf32_x3=int(x3))
-        self.ops.append(('graphormer', 'graphormer_stack', self.ga))
+        if train:
+            Lh = ghn.layers
+            self.sv = dict(xm=E(Lh, N, C, dtype=torch.float32), h1=E(Lh, N, C), qkv=E(Lh, N, 3 * C), ao=E(Lh, N, C),
+                           h2=E(Lh, N, C), u=E(Lh, N, 4 * C), g=E(Lh, N, 4 * C))
+            self.ta = L.GraphormerTrainArgs(fwd=self.ga, xs=L.ptr(self.xs),
+                                            **{k_: L.ptr(v_) for k_, v_ in self.sv.items()})
+            self.ga = self.ta.fwd            # the struct was copied by value: patch THIS copy in bind_pack
+            self.ops.append(('graphormer', 'graphormer_train_fwd', self.ta))
+        else:
+            self.ops.append(('graphormer', 'graphormer_stack', self.ga))
         bufs = {}
+        self.rts = []
 
         def gemm_args(a, b, bias, act_, out, out_dtype, problems=None, tiles=None, **kw):
             g = L.GemmArgs(a=L.ptr(a), a_rows=a.shape[0], lda=a.stride(0), b=L.ptr(b), b_rows=b.shape[0],
@@ -503,6 +521,7 @@ class _Program:
                     # relu + transpose of the (ms x i') block into a K-major operand, then a tensor-core GEMM
                     rt = E(cnt * ii, ms0)
                     self.keep.append(rt)
+                    self.rts.append(rt)
                     ta = L.ReluTransposeArgs(src=self.wout.data_ptr() + woff * 4, ld=ii, src_bs=ld, dst=L.ptr(rt),
                                              dst_dtype=act, rows=ms0, cols=ii, batch=cnt)
                     self.ops.append(('heads_1d', 'relu_transpose', ta))
@@ -553,6 +572,7 @@ class _Program:
             self.seq[i].op = self.OP[name]
             self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
         self.bound_pack = None
+        self.bwd = None
 
     def bind_pack(self, pack):
         if pack is self.bound_pack:
@@ -599,6 +619,21 @@ class _Program:
             desc['scale'] = 1.0
         self.desc_dev.copy_(torch.from_numpy(desc.view(np.uint8).reshape(-1)))
         self.last_ptrs = ptrs
+
+    def point_descriptors_at(self, pred, out_meta, weight_norm):
+        """Training path: the scatter writes into slices of the flat buffer `pred` (one slice per parameter)."""
+        n = self.n_desc
+        if n == 0:
+            return
+        base = pred.data_ptr()
+        offs = np.array([out_meta['slices'][oi][0] for oi in out_meta['desc_out']], dtype=np.uint64) * np.uint64(4)
+        desc = self.desc_host
+        desc['dst'] = np.uint64(base) + offs + self.bp.desc_dst_shift
+        if not weight_norm:
+            desc['mode'] = np.where(desc['mode'] == 3, 3, 0)
+            desc['scale'] = 1.0
+        self.desc_dev.copy_(torch.from_numpy(desc.view(np.uint8).reshape(-1)))
+        self.last_ptrs = None
 
     def run(self, prof=None):
         stream = L.current_stream()

@@ -309,6 +309,7 @@ class BatchPlan:
         wout_elems = 0
         i = 0
         self.cls_heads = []              # (wout_off, ld, i_need, n_nodes, clsw_out_off)
+        self.segments = []               # (o', i', first row, rows, wout offset): one per column class (training path)
         clsw_elems = 0
         while i < len(conv):
             o, ii = conv[i][1].o_need, conv[i][1].i_need
@@ -340,6 +341,7 @@ class BatchPlan:
                 row += cnt * P
                 k = m
             seg_rows = row - seg_row0
+            self.segments.append((o, ii, seg_row0, seg_rows, seg_base))
             if ii == ms1:
                 c2_probs.append((seg_row0, 0, seg_rows, o * ms1, seg_base, ld, 0))
             elif ii <= 128:

@@ -1,0 +1,423 @@
+"""
+Training path of the B200-native GHN-3: `ghn(nets, graphs, keep_grads=True)` (reference ghn3/nn.py:186-349 with the
+keep_grads branch of `_set_params`, nn.py:526-545) and the adjoint program that carries the target networks' loss
+gradient back into the GHN parameters (what autograd does for the reference under ghn3/trainer.py:238-411).
+
+The forward pass is the prediction program with a Graphormer stack that keeps its activations
+(ghn3_graphormer_train_fwd) and a scatter into one flat buffer whose slices become the target networks' parameters
+(tensors with a grad_fn). The backward pass is one hand-written kernel sequence (include/ghn3_b200.h, "Training
+path"): scatter^T -> decoders^T -> Graphormer^T -> node features^T / edge-bias LUT^T. There is no autograd tape inside
+the GHN and no CPU path.
+"""
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .plan import SRC_CLSB, SRC_CLSW, SRC_D1, SRC_TOK, SRC_WOUT
+
+OPC = {'graphormer_bwd': 8, 'transpose': 9, 'elementwise': 10, 'colsum': 11, 'layernorm_bwd': 12,
+       'attention_bwd': 13, 'scatter_bwd': 14, 'node_features_bwd': 15, 'edge_lut_bwd': 16, 'fc_bwd': 17,
+       'relu_transpose_bwd': 18, 'gemm': 3, 'gemm_simt': 4}
+
+
+def _pad8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# transposed weight copies (operands of the dgrad GEMMs); rebuilt whenever the device weights are
+def transposed_weights(ghn, w):
+    wt = w.get('T')
+    if wt is not None:
+        return wt
+    act = w['act']
+    T = lambda t: ops.transpose(t, dst_dtype=act)       # [cols, rows] view, row stride padded to 8 elements
+    layers = (L.LayerWeightsT * ghn.layers)()
+    keep = []
+    for l, t in enumerate(w['layers_keep']):
+        d = dict(w_qkv_t=T(t['w_qkv']), w_out_t=T(t['w_out']), w_ff1_t=T(t['w_ff1']), w_ff2_t=T(t['w_ff2']))
+        keep.append(d)
+        for k, v in d.items():
+            setattr(layers[l], k, v.data_ptr())
+    wt = {'layers': layers, 'keep': keep, 'c0_wT': T(w['c0_w']), 'd1_w0T': T(w['d1_w0']), 'd1_w1T': T(w['d1_w1']),
+          'cls_wT': T(w['cls_w'])}
+    w['T'] = wt
+    return wt
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _Backward:
+    """The adjoint kernel sequence of one training program (built once per batch plan and weight version)."""
+
+    def __init__(self, prog, ghn):
+        self.prog, self.ghn = prog, ghn
+        bp, w, dev = prog.bp, prog.w, prog.device
+        act = w['act']
+        adt = ops.TORCH_DTYPE[act]
+        in_dt, x3 = w['dtype'], int(w['x3'])
+        C, H = ghn.hid, ghn.heads
+        ms0, ms1, S, _ = ghn.max_shape
+        ncls, mc = ghn.num_classes, bp.max_ch
+        N = bp.total_nodes
+        wt = transposed_weights(ghn, w)
+        self.keep = []
+        self.ops = []
+        self.zero = []                     # buffers cleared at the start of every backward pass
+        Z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
+        E = lambda *shape, dtype=adt: torch.empty(*shape, dtype=dtype, device=dev)
+
+        # ---- fp32 gradient of every GHN parameter: one flat buffer, views per parameter ----
+        params = list(ghn.parameters())
+        offs = np.concatenate([[0], np.cumsum([(p.numel() + 3) // 4 * 4 for p in params])]).astype(np.int64)
+        self.params = params
+        self.gflat = Z(int(offs[-1]))
+        self.gviews = [self.gflat[int(o):int(o) + p.numel()].view(p.shape) for o, p in zip(offs[:-1], params)]
+        gof = {id(p): v for p, v in zip(params, self.gviews)}
+        G = lambda p: gof[id(p)]
+        self.zero.append(self.gflat)
+
+        def add(name, args):
+            self.ops.append((name, args))
+            return args
+
+        def transpose(src, rows, cols, ld_src, dst, src_dtype=None, group=0, group_stride=0):
+            """dst [cols, pad8(rows)] <- src [rows(mapped), cols]; returns the padded row stride."""
+            ld = _pad8(rows)
+            add('transpose', L.TransposeArgs(src=src if isinstance(src, int) else src.data_ptr(),
+                                             src_dtype=src_dtype, ld_src=ld_src, rows=rows, cols=cols, group=group,
+                                             group_stride=group_stride, dst=dst.data_ptr(), dst_dtype=act, ld_dst=ld))
+            return ld
+
+        def ew(op, n, a, a_dt, b, b_dt, out, out_dt):
+            P = lambda t: t if isinstance(t, int) or t is None else t.data_ptr()
+            add('elementwise', L.ElementwiseArgs(op=op, n=n, a=P(a), a_dtype=a_dt, b=P(b), b_dtype=b_dt, out=P(out),
+                                                 out_dtype=out_dt))
+
+        def colsum(src, src_dt, rows, cols, ld, dst, group=0, group_stride=0):
+            P = lambda t: t if isinstance(t, int) else t.data_ptr()
+            add('colsum', L.ColsumArgs(src=P(src), src_dtype=src_dt, ld=ld, rows=rows, cols=cols, group=group,
+                                       group_stride=group_stride, dst=P(dst)))
+
+        def gemm(a, m, lda, b, n, ldb, k, d, out_dtype, accumulate=0, b_dynamic=1, rowmap=None, ldd=None):
+            P = lambda t: t if isinstance(t, int) else t.data_ptr()
+            g = L.GemmArgs(a=P(a), a_rows=m, lda=lda, b=P(b), b_rows=n, ldb=ldb, k=k, in_dtype=in_dt, d=P(d),
+                           out_dtype=out_dtype, bias=None, act=ops.ACT_NONE, accumulate=accumulate, tf32_x3=x3,
+                           b_dynamic=b_dynamic, rowmap=L.ptr(rowmap))
+            g.single = L.GemmProblem(a_row0=0, b_row0=0, m=m, n=n, d_off=0, ldd=n if ldd is None else ldd, bias_off=-1)
+            add('gemm', g)
+
+        el = 2 if act == ops.BF16 else 4
+        F32 = ops.F32
+        n_dec = bp.n_conv + bp.n_1d
+        self.ddec = Z(max(n_dec, 1), C)
+        self.zero.append(self.ddec)
+
+        # ---- source-gradient buffers of the scatter ----
+        dbufs = {}
+        if bp.conv_total_rows > 0:
+            self.dwout = Z(bp.wout_elems)
+            dbufs[SRC_WOUT] = self.dwout
+            self.zero.append(self.dwout)
+            if bp.clsw_elems:
+                self.dclsw = Z(bp.clsw_elems)
+                dbufs[SRC_CLSW] = self.dclsw
+                self.zero.append(self.dclsw)
+        if bp.n_1d > 0:
+            self.dd1 = Z(bp.n_1d, 2 * mc)
+            dbufs[SRC_D1] = self.dd1
+            self.zero.append(self.dd1)
+            if bp.n_clsb:
+                self.dclsb = Z(2 * bp.n_clsb, ncls)
+                dbufs[SRC_CLSB] = self.dclsb
+                self.zero.append(self.dclsb)
+        n_desc = prog.n_desc
+        self.n_desc = n_desc
+        if n_desc:
+            dsrc = np.zeros(n_desc, dtype=np.int64)
+            for i in range(n_desc):
+                b_ = int(bp.desc_src_buf[i])
+                if b_ in dbufs:
+                    dsrc[i] = dbufs[b_].data_ptr() + int(bp.desc_src_off[i]) * 4
+            self.dsrc_dev = torch.from_numpy(dsrc).to(dev)
+            self.grad_ptrs = torch.zeros(n_desc, dtype=torch.int64, device=dev)
+            self.grad_ptrs_host = torch.zeros(n_desc, dtype=torch.int64).pin_memory()
+            add('scatter_bwd', L.ScatterBwdArgs(descs=L.ptr(prog.desc_dev), n_descs=n_desc, n_chunks=bp.n_chunks,
+                                                chunk_desc=L.ptr(prog.st['chunk_desc']), grads=L.ptr(self.grad_ptrs),
+                                                d_src=L.ptr(self.dsrc_dev)))
+
+        # ---- 1-D decoder (+ classification-bias head) ----
+        dec1, bcl = ghn.decoder_1d, ghn.bias_class[1]
+        if bp.n_1d > 0:
+            n1 = bp.n_1d
+            n1p = _pad8(n1)
+            if bp.n_clsb:
+                rows = 2 * bp.n_clsb
+                d1blk = prog.d1.data_ptr() + (n1 - bp.n_clsb) * 2 * mc * 4
+                dd1blk = self.dd1.data_ptr() + (n1 - bp.n_clsb) * 2 * mc * 4
+                colsum(self.dclsb, F32, rows, ncls, ncls, G(bcl.bias))
+                # dWbc[cls][k] = sum_row dY[row][cls] * relu(d1[row][k])
+                add('gemm_simt', L.GemmSimtArgs(a=d1blk, sam=1, sak=mc, b=L.ptr(self.dclsb), sbn=1, sbk=ncls,
+                                                bias=None, d=G(bcl.weight).data_ptr(), sdm=1, sdn=mc, m=mc, n=ncls,
+                                                k=rows, relu_a=1, act=ops.ACT_NONE, batch=1))
+                tmp = E(rows, mc, dtype=torch.float32)
+                self.keep.append(tmp)
+                add('gemm_simt', L.GemmSimtArgs(a=L.ptr(self.dclsb), sam=ncls, sak=1, b=L.ptr(w['bc_w']), sbn=1,
+                                                sbk=mc, bias=None, d=L.ptr(tmp), sdm=mc, sdn=1, m=rows, n=mc, k=ncls,
+                                                relu_a=0, act=ops.ACT_NONE, batch=1))
+                ew(L.EW_RELU_BWD, rows * mc, tmp, F32, d1blk, F32, dd1blk, F32)
+            dd1a = E(n1, 2 * mc)
+            tA, tB = E(2 * max(mc, C), n1p), E(2 * C, n1p)
+            dhid = E(n1, 2 * C)
+            self.keep += [dd1a, tA, tB, dhid]
+            d_in = prog.dec_in.data_ptr() + bp.n_conv * C * el
+            ew(L.EW_COPY, n1 * 2 * mc, self.dd1, F32, None, 0, dd1a, act)
+            colsum(self.dd1, F32, n1, 2 * mc, 2 * mc, G(dec1.fc[2].bias))
+            transpose(self.dd1, n1, 2 * mc, 2 * mc, tA, src_dtype=F32)
+            transpose(prog.hid1, n1, 2 * C, 2 * C, tB, src_dtype=act)
+            gemm(tA, 2 * mc, n1p, tB, 2 * C, n1p, n1, G(dec1.fc[2].weight), F32, accumulate=1)
+            gemm(dd1a, n1, 2 * mc, wt['d1_w1T'], 2 * C, wt['d1_w1T'].stride(0), 2 * mc, dhid, act, b_dynamic=0)
+            ew(L.EW_RELU_BWD, n1 * 2 * C, dhid, act, prog.hid1, act, dhid, act)
+            colsum(dhid, act, n1, 2 * C, 2 * C, G(dec1.fc[0].bias))
+            transpose(dhid, n1, 2 * C, 2 * C, tA, src_dtype=act)
+            transpose(d_in, n1, C, C, tB, src_dtype=act)
+            gemm(tA, 2 * C, n1p, tB, C, n1p, n1, G(dec1.fc[0].weight), F32, accumulate=1)
+            gemm(dhid, n1, 2 * C, wt['d1_w0T'], C, wt['d1_w0T'].stride(0), 2 * C,
+                 self.ddec.data_ptr() + bp.n_conv * C * 4, F32, b_dynamic=0)
+
+        # ---- conv decoder ----
+        dec = ghn.decoder
+        R = bp.conv_total_rows
+        if R > 0:
+            # class heads first: they add into dwout
+            clp = dec.class_layer_predictor[1]
+            for hi, (woff, ld, ii, cnt, coff) in enumerate(bp.cls_heads):
+                n2 = cnt * ii
+                n2p, nclsp = _pad8(n2), _pad8(ncls)
+                tO, A2, rtT = E(n2, nclsp), E(ncls, n2p), E(ms0, n2p)
+                drt = E(n2, ms0, dtype=torch.float32)
+                self.keep += [tO, A2, rtT, drt]
+                dout = self.dclsw.data_ptr() + coff * 4
+                transpose(dout, ncls, n2, n2, tO, src_dtype=F32)                 # dOut^T  [n2][ncls]
+                colsum(tO, act, n2, ncls, nclsp, G(clp.bias))
+                transpose(tO, n2, ncls, nclsp, A2, src_dtype=act)                # dOut    [ncls][n2] (padded stride)
+                transpose(prog.rts[hi], n2, ms0, ms0, rtT, src_dtype=act)        # rt^T    [ms0][n2]
+                gemm(A2, ncls, n2p, rtT, ms0, n2p, n2, G(clp.weight), F32, accumulate=1)
+                gemm(tO, n2, nclsp, wt['cls_wT'], ms0, wt['cls_wT'].stride(0), ncls, drt, F32, b_dynamic=0)
+                add('relu_transpose_bwd', L.ReluTransposeBwdArgs(src=prog.wout.data_ptr() + woff * 4,
+                                                                 d_src=self.dwout.data_ptr() + woff * 4, ld=ii,
+                                                                 src_bs=ld, d_rt=L.ptr(drt), rows=ms0, cols=ii,
+                                                                 batch=cnt))
+            max_elems = max(_pad8(rows) * o * ii for (o, ii, _, rows, _) in bp.segments)
+            max_a2 = max(rows * _pad8(o * ii) for (o, ii, _, rows, _) in bp.segments)
+            max_ld = max(_pad8(o * ii) for (o, ii, _, _, _) in bp.segments)
+            max_rows = max(_pad8(rows) for (_, _, _, rows, _) in bp.segments)
+            taT, a2 = E(max_elems), E(max_a2)
+            tW = E(8 * C * max_ld)
+            h1T = E(8 * C * max(max_rows, _pad8(R)))
+            self.dh1, self.dh0 = E(R, 8 * C), E(R, 4 * C)
+            self.keep += [taT, a2, tW, h1T]
+            rowmaps = {}
+            c2w, c2b = dec.conv[2].weight, dec.conv[2].bias
+            for (o, ii, row0, rows, base) in bp.segments:
+                ld = o * ii
+                ldp, rp = _pad8(ld), _pad8(rows)
+                grp = 0 if ii == ms1 else ii
+                dseg = self.dwout.data_ptr() + base * 4
+                transpose(dseg, rows, ld, ld, taT, src_dtype=F32)                # dwout^T [ld][rows]
+                transpose(taT, ld, rows, rp, a2, src_dtype=act)                  # dwout   [rows][ld] (padded stride)
+                transpose(w['c2_w'], ld, 8 * C, 8 * C, tW, src_dtype=act, group=grp, group_stride=ms1)
+                gemm(a2, rows, ldp, tW, 8 * C, ldp, ld, self.dh1.data_ptr() + row0 * 8 * C * el, act)
+                transpose(prog.h1.data_ptr() + row0 * 8 * C * el, rows, 8 * C, 8 * C, h1T, src_dtype=act)
+                rm = None
+                if grp:
+                    if ii not in rowmaps:
+                        m_ = np.arange(ms0 * ii, dtype=np.int64)
+                        rowmaps[ii] = torch.from_numpy(((m_ // ii) * ms1 + m_ % ii).astype(np.int32)).to(dev)
+                    rm = rowmaps[ii]
+                gemm(taT, ld, rp, h1T, 8 * C, rp, rows, G(c2w), F32, accumulate=1, rowmap=rm, ldd=8 * C)
+                colsum(dseg, F32, rows, ld, ld, G(c2b), group=grp, group_stride=ms1)
+            self.keep.append(rowmaps)
+            rp = _pad8(R)
+            h0T = E(4 * C * rp)
+            self.keep.append(h0T)
+            ew(L.EW_RELU_BWD, R * 8 * C, self.dh1, act, prog.h1, act, self.dh1, act)
+            colsum(self.dh1, act, R, 8 * C, 8 * C, G(dec.conv[0].bias))
+            transpose(self.dh1, R, 8 * C, 8 * C, h1T, src_dtype=act)
+            transpose(prog.h0, R, 4 * C, 4 * C, h0T, src_dtype=act)
+            gemm(h1T, 8 * C, rp, h0T, 4 * C, rp, R, G(dec.conv[0].weight), F32, accumulate=1)
+            gemm(self.dh1, R, 8 * C, wt['c0_wT'], 4 * C, wt['c0_wT'].stride(0), 8 * C, self.dh0, act, b_dynamic=0)
+            ew(L.EW_RELU_BWD, R * 4 * C, self.dh0, act, prog.h0, act, self.dh0, act)
+            fcw = dec.fc[0].weight
+            if not (fcw.is_contiguous() and fcw.dtype == torch.float32):
+                raise RuntimeError('ghn3_b200: decoder.fc.0.weight must be a contiguous fp32 tensor for training')
+            add('fc_bwd', L.FcBwdArgs(problems=L.ptr(prog.st['fc_problems']), n_problems=len(bp.fc_problems),
+                                      max_m=int(bp.fc_problems['m'].max()), rowmap=L.ptr(prog.st['fc_rowmap']),
+                                      dh0=L.ptr(self.dh0), dtype=act if act == ops.BF16 else F32,
+                                      dec_in=L.ptr(prog.dec_in), fc_w=fcw.data_ptr(), hid=C, n_out=4 * C,
+                                      grid_positions=S * S, d_fc_w=G(fcw).data_ptr(),
+                                      d_fc_b=G(dec.fc[0].bias).data_ptr(), d_dec_in=L.ptr(self.ddec)))
+
+        # ---- Graphormer stack ----
+        mp = _pad8(N)
+        self.lgr = (L.LayerGrads * ghn.layers)()
+        for l, layer in enumerate(ghn.gnn):
+            lg = self.lgr[l]
+            lg.ln1_w, lg.ln1_b = G(layer.ln1.weight).data_ptr(), G(layer.ln1.bias).data_ptr()
+            lg.w_qkv = G(layer.attn.to_qkv.weight).data_ptr()
+            lg.w_out, lg.b_out = G(layer.attn.to_out[0].weight).data_ptr(), G(layer.attn.to_out[0].bias).data_ptr()
+            lg.ln2_w, lg.ln2_b = G(layer.ln2.weight).data_ptr(), G(layer.ln2.bias).data_ptr()
+            lg.w_ff1, lg.b_ff1 = G(layer.ff.net[0].weight).data_ptr(), G(layer.ff.net[0].bias).data_ptr()
+            lg.w_ff2, lg.b_ff2 = G(layer.ff.net[3].weight).data_ptr(), G(layer.ff.net[3].bias).data_ptr()
+        self.dx = E(N, C, dtype=torch.float32)
+        ws = dict(dxa=E(N, C), dh=E(N, C), dhf=E(N, C, dtype=torch.float32), dqkv=E(N, 3 * C), dff=E(N, 4 * C),
+                  ta=E(4 * C, mp), tb=E(4 * C, mp), lse=E(H, N, dtype=torch.float32),
+                  delta=E(H, N, dtype=torch.float32))
+        self.keep.append(ws)
+        self.wt = wt
+        self.d_lut = None                      # allocated when the pack (cutoff) is known
+        self.gb = L.GraphormerBwdArgs(saved=ct.pointer(prog.ta), layers_t_host=wt['layers'], grads_host=self.lgr,
+                                      d_ln_w=G(ghn.ln.weight).data_ptr(), d_ln_b=G(ghn.ln.bias).data_ptr(),
+                                      d_dec_in=L.ptr(self.ddec), d_dec_dtype=F32, d_lut=None, dx=L.ptr(self.dx),
+                                      m_pad=mp, **{k: L.ptr(v) for k, v in ws.items()})
+        add('graphormer_bwd', self.gb)
+        # ---- node features, edge-bias look-up table ----
+        g0 = ghn.gnn[0]
+        nf = prog.nf
+        self.nfb = L.NodeFeaturesBwdArgs(total_nodes=N, hid=C, shape_idx=nf.shape_idx, dx=L.ptr(self.dx),
+                                         d_embed_op=G(ghn.embed.weight).data_ptr(),
+                                         d_embed_ch=G(ghn.shape_enc.embed_channel.weight).data_ptr(),
+                                         d_embed_sp=G(ghn.shape_enc.embed_spatial.weight).data_ptr(),
+                                         d_cent_in=G(g0.centrality_embed_in.weight).data_ptr(),
+                                         d_cent_out=G(g0.centrality_embed_out.weight).data_ptr(),
+                                         d_dist_embed=G(g0.input_dist_embed.weight).data_ptr())
+        add('node_features_bwd', self.nfb)
+        li = w['lut_inputs']
+        self.lut_ws = None
+        self.lb = L.EdgeLutBwdArgs(hid=C, heads=H, vmax=0, edge_embed=L.ptr(li[0]), w1=L.ptr(li[1]), b1=L.ptr(li[2]),
+                                   w2=L.ptr(li[3]), d_lut=None, workspace=None,
+                                   d_edge_embed=G(g0.attn.edge_embed.embed.weight).data_ptr(),
+                                   d_w1=G(g0.attn.proj_e[0].weight).data_ptr(),
+                                   d_b1=G(g0.attn.proj_e[0].bias).data_ptr(),
+                                   d_w2=G(g0.attn.proj_e[2].weight).data_ptr(),
+                                   d_b2=G(g0.attn.proj_e[2].bias).data_ptr())
+        add('edge_lut_bwd', self.lb)
+        self.seq = (L.SeqOp * len(self.ops))()
+        for i, (name, args) in enumerate(self.ops):
+            self.seq[i].op = OPC[name]
+            self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def run(self, out_grads, out_index):
+        """out_grads: gradients of the program outputs (one per predicted PARAMETER, None allowed);
+        out_index[i] = (output index, byte shift, has_grad_path) of descriptor i. Returns the GHN parameter grads."""
+        prog = self.prog
+        pack = prog.bound_pack
+        dev = prog.device
+        vmax = pack.cutoff
+        lut_size = (vmax + 1) ** 2
+        if self.d_lut is None or self.d_lut.shape[1] != lut_size:
+            self.d_lut = torch.zeros(self.ghn.heads, lut_size, dtype=torch.float32, device=dev)
+            self.lut_ws = torch.empty(4 * (vmax + 1) * self.ghn.hid, dtype=torch.float32, device=dev)
+            self.gb.d_lut = self.d_lut.data_ptr()
+            self.lb.d_lut, self.lb.workspace, self.lb.vmax = self.d_lut.data_ptr(), self.lut_ws.data_ptr(), vmax
+        nfb, nf = self.nfb, prog.nf
+        nfb.op, nfb.deg_in, nfb.deg_out, nfb.dist0 = nf.op, nf.deg_in, nf.deg_out, nf.dist0
+        for t in self.zero:
+            t.zero_()
+        self.d_lut.zero_()
+        live = []
+        if self.n_desc:
+            host = self.grad_ptrs_host
+            for i, (oi, shift, has_path) in enumerate(out_index):
+                g = out_grads[oi] if has_path else None
+                if g is None:
+                    host[i] = 0
+                    continue
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.float().contiguous()
+                live.append(g)
+                host[i] = g.data_ptr() + shift
+            self.grad_ptrs.copy_(host, non_blocking=True)
+        stream = L.current_stream()
+        L.check(L.load().ghn3_run_sequence(self.seq, len(self.ops), ct.c_void_p(stream)), 'ghn3_run_sequence (backward)')
+        self.live = live
+        return self.gviews
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _PredictFn(torch.autograd.Function):
+    """(GHN parameters) -> (predicted target parameters): forward = the prediction program, backward = _Backward."""
+
+    @staticmethod
+    def forward(ctx, ghn, prog, pack, out_meta, out_index, *params):
+        prog.bind_pack(pack)
+        total = out_meta['total']
+        pred = torch.empty(total, dtype=torch.float32, device=prog.device)
+        prog.point_descriptors_at(pred, out_meta, ghn.weight_norm)
+        if prog.bp.n_tok_elems:
+            prog.tok.normal_(mean=0.0, std=0.02)
+        prog.run(getattr(ghn, '_profile', None))
+        prog.step_id = getattr(prog, 'step_id', 0) + 1
+        ctx.ghn, ctx.prog, ctx.out_index, ctx.step_id = ghn, prog, out_index, prog.step_id
+        outs = tuple(pred[o:o + n].view(shape) for (o, n, shape) in out_meta['slices'])
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        prog, ghn = ctx.prog, ctx.ghn
+        if prog.step_id != ctx.step_id:
+            raise RuntimeError('ghn3_b200: backward() called after another forward pass of the same (GHN, batch) '
+                               'program; its saved activations have been overwritten')
+        if prog.bwd is None:
+            prog.bwd = _Backward(prog, ghn)
+        gviews = prog.bwd.run(grads, ctx.out_index)
+        return (None, None, None, None, None) + tuple(gviews)
+
+
+def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
+    """GHN3.forward(keep_grads=True): predicted parameters are tensors with a grad_fn, set on the target modules the
+    way the reference does (ghn3/nn.py:526-545)."""
+    from .nn import _Program
+    device = ghn.embed.weight.device
+    prog = getattr(bp, 'train_program', None)
+    if prog is None or prog.w is not w or prog.device != device or prog.want_emb != bool(return_embeddings):
+        prog = _Program(ghn, w, bp, device, bool(return_embeddings), train=True)
+        bp.train_program = prog
+    meta = getattr(bp, 'out_meta', None)
+    if meta is None:
+        # one output per predicted PARAMETER (a ViT pos_embedding is written by two descriptors)
+        index, slices, keys, off = [], [], {}, 0
+        for (module, attr, shape, view) in bp.desc_targets:
+            key = (id(module), attr)
+            if key not in keys:
+                p = getattr(module, attr)
+                full = tuple(p) if isinstance(p, (list, tuple)) else tuple(p.shape)
+                n = int(np.prod(full))
+                keys[key] = len(slices)
+                slices.append((off, n, full))
+                off += (n + 3) // 4 * 4
+            index.append(keys[key])
+        meta = {'slices': slices, 'total': max(off, 4), 'desc_out': index,
+                'targets': [(m, a) for (m, a, _, v) in bp.desc_targets]}
+        shifts = [int(s) for s in bp.desc_dst_shift]
+        meta['out_index'] = [(index[i], shifts[i], bp.desc_targets[i][3] != 'tok') for i in range(len(index))]
+        bp.out_meta = meta
+    outs = _PredictFn.apply(ghn, prog, graphs.pack, meta, meta['out_index'], *list(ghn.parameters()))
+    done = set()
+    for (module, attr), oi in zip(meta['targets'], meta['desc_out']):
+        key = (id(module), attr)
+        if key in done:
+            continue
+        done.add(key)
+        t = outs[oi]
+        cur = module.__dict__.get(attr, module._parameters.get(attr) if hasattr(module, '_parameters') else None)
+        if isinstance(cur, (list, tuple)):                 # light modules keep shapes, not parameters (nn.py:527-533)
+            setattr(module, attr, t)
+        else:
+            module.__dict__[attr] = t                      # nn.py:536-539
+            module._parameters[attr] = t
+    ghn.last_program = prog
+    return prog.emb

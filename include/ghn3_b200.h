@@ -472,11 +472,87 @@ typedef struct {
 } ghn3_edge_lut_bwd_args;
 int ghn3_edge_lut_bwd(const ghn3_edge_lut_bwd_args* args, ghn3_stream_t stream);
 
+/* Decoder fc stage backward (adjoint of the per-position grouped GEMM + ReLU of ghn3/nn.py:738-745; dh0 is the
+ * gradient AFTER the ReLU mask). Gradients go straight to the ORIGINAL parameter layout of decoder.fc.0
+ * (weight [(j*S*S + pos)][C], bias [j*S*S + pos]) and to the decoder-input rows, all accumulated atomically. */
+typedef struct {
+  const ghn3_gemm_problem* problems;  /* device: the forward fc problems (a_row0, b_row0 = pos*n_out, m, d_off) */
+  int32_t n_problems;
+  int32_t max_m;                      /* max problems[].m (sizes the launch) */
+  const int32_t* rowmap;              /* forward row map: h0 row of problems[p].d_off + k */
+  const void* dh0; int32_t dtype;     /* [R][n_out], GHN3_BF16 or fp32 storage; also the dtype of dec_in */
+  const void* dec_in;                 /* [n_dec][C] */
+  const float* fc_w;                  /* original fp32 weight */
+  int32_t hid, n_out, grid_positions; /* C, 4C, S*S */
+  float* d_fc_w; float* d_fc_b; float* d_dec_in;
+} ghn3_fc_bwd_args;
+int ghn3_fc_bwd(const ghn3_fc_bwd_args* args, ghn3_stream_t stream);
+
+/* Adjoint of ghn3_relu_transpose: d_src[z*src_bs + r*ld + c] += (src > 0) * d_rt[(z*cols + c)*rows + r]. */
+typedef struct {
+  const float* src; float* d_src; int64_t ld; int64_t src_bs;
+  const float* d_rt;
+  int32_t rows, cols, batch;
+} ghn3_relu_transpose_bwd_args;
+int ghn3_relu_transpose_bwd(const ghn3_relu_transpose_bwd_args* args, ghn3_stream_t stream);
+
+/* Graphormer stack, training flavour. ghn3_graphormer_train_fwd computes the same function as ghn3_graphormer_stack
+ * (fwd.x is ignored: the input node features are xs[0]) but keeps every activation of every layer;
+ * ghn3_graphormer_bwd consumes them. Buffers are [layers][total_nodes][width] (xs: layers+1), contiguous. */
+typedef struct {
+  ghn3_graphormer_args fwd;  /* weights, batch description, decoder-input outputs; workspaces h/qkv/ff unused */
+  float* xs;                 /* [L+1][M][C] fp32 residual stream: xs[l] = input of layer l, xs[L] = stack output */
+  float* xm;                 /* [L][M][C]   fp32 residual stream after the attention block */
+  void* h1;                  /* [L][M][C]   LN1 output                (activation dtype) */
+  void* qkv;                 /* [L][M][3C] */
+  void* ao;                  /* [L][M][C]   attention output */
+  void* h2;                  /* [L][M][C]   LN2 output */
+  void* u;                   /* [L][M][4C]  FFN pre-activation */
+  void* g;                   /* [L][M][4C]  GELU(u) */
+} ghn3_graphormer_train_args;
+int ghn3_graphormer_train_fwd(const ghn3_graphormer_train_args* args, ghn3_stream_t stream);
+
+typedef struct {             /* transposed copies of the layer's GEMM weights, GEMM input dtype */
+  const void* w_qkv_t;       /* [C][3C] */
+  const void* w_out_t;       /* [C][C]  */
+  const void* w_ff1_t;       /* [C][4C] */
+  const void* w_ff2_t;       /* [4C][C] */
+} ghn3_layer_weights_t;
+
+typedef struct {             /* fp32 gradient accumulators (+=), shapes of the corresponding parameters */
+  float* ln1_w; float* ln1_b; float* w_qkv; float* w_out; float* b_out;
+  float* ln2_w; float* ln2_b; float* w_ff1; float* b_ff1; float* w_ff2; float* b_ff2;
+} ghn3_layer_grads;
+
+typedef struct {
+  const ghn3_graphormer_train_args* saved;   /* HOST pointer */
+  const ghn3_layer_weights_t* layers_t_host; /* HOST array [layers] */
+  const ghn3_layer_grads* grads_host;        /* HOST array [layers] */
+  float* d_ln_w; float* d_ln_b;              /* final LayerNorm (+=) */
+  const void* d_dec_in; int32_t d_dec_dtype; /* gradient wrt the decoder-input rows [n_dec][C] */
+  float* d_lut;                              /* [H][lut_size] (+=) */
+  float* dx;                                 /* [M][C] fp32: on return the gradient wrt the node features xs[0] */
+  /* workspaces */
+  void* dxa;                 /* [M][C]  activation dtype */
+  void* dh;                  /* [M][C]  activation dtype */
+  float* dhf;                /* [M][C]  fp32 */
+  void* dqkv;                /* [M][3C] activation dtype */
+  void* dff;                 /* [M][4C] activation dtype */
+  void* ta; void* tb;        /* [4C][m_pad] activation dtype (transposed operands of the wgrad GEMMs) */
+  int32_t m_pad;             /* multiple of 8, >= total_nodes */
+  float* lse; float* delta;  /* [H][M] */
+} ghn3_graphormer_bwd_args;
+int ghn3_graphormer_bwd(const ghn3_graphormer_bwd_args* args, ghn3_stream_t stream);
+
 /* Runs a prebuilt sequence of the entry points above with ONE call (the host side of `ghn(model)` is then a single
  * FFI crossing per prediction): ops[i].args points to the argument struct of the entry point named by ops[i].op. */
 enum ghn3_opcode {
   GHN3_OP_NODE_FEATURES = 1, GHN3_OP_GRAPHORMER = 2, GHN3_OP_GEMM = 3, GHN3_OP_GEMM_SIMT = 4, GHN3_OP_SCATTER = 5,
-  GHN3_OP_RELU_TRANSPOSE = 6
+  GHN3_OP_RELU_TRANSPOSE = 6,
+  /* training path */
+  GHN3_OP_GRAPHORMER_TRAIN_FWD = 7, GHN3_OP_GRAPHORMER_BWD = 8, GHN3_OP_TRANSPOSE = 9, GHN3_OP_ELEMENTWISE = 10,
+  GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
+  GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18
 };
 typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
 int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);

@@ -1,0 +1,146 @@
+"""Training path on the B200: gradients of the GHN parameters through ghn(model, keep_grads=True) vs autograd through
+the CPU oracle (the reference's keep_grads branch, ghn3/nn.py:526-545 + ghn3/trainer.py:321-345) on the same weights,
+graphs and loss."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from ghn3_b200 import GHN3, Graph
+from ghn3_b200.weights import CONFIGS, procedural_state_dict
+from oracle import ghn3_oracle as O
+from tests import helpers as H
+
+DEV = 'cuda'
+# gradients are compared per tensor as max|a-b| / max|b|; bf16 operands in every dgrad / wgrad GEMM
+GTOL = {'tf32': 3e-3, 'bf16': 6e-2}
+
+
+def _loss_weights(tensors, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(t.shape, generator=g) for t in tensors]
+
+
+def _cuda_grads(cfg_name, dtype, archs, recs, all_R):
+    cfg = CONFIGS[cfg_name]
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    models = [H.build_model(a).to(DEV) for a in archs]
+    graphs = [Graph.from_record(r) for r in recs]
+    out = ghn(models if len(models) > 1 else models[0], graphs if len(graphs) > 1 else graphs[0], keep_grads=True)
+    out = out if isinstance(out, list) else [out]
+    loss = 0.
+    for model, arch, Rs in zip(out, archs, all_R):
+        mods = dict(model.named_modules())
+        # the oracle recorded (module of ITS model, attr, weight): address the same module by name here
+        for (omod, key, r) in Rs:
+            name = getattr(omod, '_ghn3_name', None)
+            t = getattr(mods[name], key)
+            assert t.grad_fn is not None or t.requires_grad, (arch, name, key)
+            loss = loss + (t * r.to(DEV)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return {k: p.grad for k, p in ghn.named_parameters()}, float(loss)
+
+
+def _run(cfg_name, archs, dtype):
+    cfg = CONFIGS[cfg_name]
+    recs = [H.graph_records()[a] for a in archs]
+    sd_grads, all_R, ref_loss = _oracle_grads_named(cfg, archs, recs)
+    grads, loss = _cuda_grads(cfg_name, dtype, archs, recs, all_R)
+    if not any(a.startswith('vit') for a in archs):      # ViT class-token rows are fresh random draws (nn.py:446)
+        assert abs(loss - ref_loss) <= 5 * GTOL[dtype] * max(1.0, abs(ref_loss)), (loss, ref_loss)
+    worst, bad = {}, {}
+    for k, ref in sd_grads.items():
+        g = grads[k]
+        assert g is not None, k
+        g = g.float().cpu()
+        denom = float(ref.abs().max())
+        if k.endswith('proj_e.2.bias'):
+            # softmax is shift invariant: the exact gradient of the per-head bias offset is 0 and both sides hold
+            # rounding noise only; measure it against the scale of the neighbouring weight gradient
+            denom = float(sd_grads[k.replace('.bias', '.weight')].abs().max())
+            err = float((g - ref).abs().max()) / denom
+            if not err < (0.15 if dtype == 'bf16' else GTOL[dtype]):
+                bad[k] = err
+            continue
+        if denom == 0.0:
+            assert float(g.abs().max()) == 0.0, k
+            continue
+        if dtype == 'bf16':
+            # bf16 activations move ReLU / GELU kinks of ~1% of the hidden units relative to the fp32 oracle; with
+            # the random loss weights used here that shows up as ~6-9% relative L2 noise on EVERY tensor (cosine
+            # 0.996-0.998, measured with tools/grad_check.py), so the bf16 path is held to a direction + norm bound
+            # and the exact adjoint arithmetic is pinned by the tf32 (error-compensated) path at 3e-3
+            l2 = float((g - ref).norm() / ref.norm())
+            cos = float((g * ref).sum() / (g.norm() * ref.norm()))
+            worst[k] = l2
+            if not (l2 < 0.15 and cos > 0.985):
+                bad[k] = (l2, cos)
+        else:
+            err = float((g - ref).abs().max()) / denom
+            worst[k] = err
+            if not err < GTOL[dtype]:
+                bad[k] = err
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    print(cfg_name, archs, dtype, 'worst:', top)
+    assert not bad, bad
+
+
+def _oracle_grads_named(cfg, archs, recs):
+    sd = {k: v.clone().requires_grad_(True) for k, v in procedural_state_dict(cfg, 0).items()}
+    loss = 0.
+    all_R = []
+    for arch, rec in zip(archs, recs):
+        model = H.build_model(arch)
+        for n, m in model.named_modules():
+            m.__dict__['_ghn3_name'] = n
+        out = O.predict_keep_grads(sd, cfg, model, O.graph_from_record(rec))
+        R = _loss_weights([t for _, _, t in out])
+        all_R.append([(m, key, r) for (m, key, _), r in zip(out, R)])
+        loss = loss + sum((t * r).sum() for (_, _, t), r in zip(out, R))
+    loss.backward()
+    return {k: v.grad for k, v in sd.items()}, all_R, float(loss)
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+@pytest.mark.parametrize('arch', ['resnet18', 'squeezenet1_1', 'mobilenet_v3_small', 'vit_b_32'])
+def test_tiny_gradients(arch, dtype):
+    _run('ghn3tiny', [arch], dtype)
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+def test_tiny_gradients_batch_of_graphs(dtype):
+    """meta-batch of unequal graphs: the loss is a sum over models, gradients add up (trainer.py:308-327)."""
+    _run('ghn3tiny', ['resnet18', 'alexnet', 'squeezenet1_1'], dtype)
+
+
+def test_tm8_gradients_resnet50():
+    _run('ghn3tm8', ['resnet50'], 'bf16')
+
+
+def test_second_step_after_weight_update():
+    """the device weight copies, their transposes and the LUT follow an in-place optimizer update"""
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    opt = torch.optim.SGD(ghn.parameters(), lr=1e-2)
+    rec = H.graph_records()['resnet18']
+    graph = Graph.from_record(rec)
+    losses = []
+    for step in range(3):
+        model = H.build_model('resnet18').to(DEV)
+        model = ghn(model, graph, keep_grads=True)
+        torch.manual_seed(0)
+        x = torch.randn(4, 3, 64, 64, device=DEV)
+        y = model(x)
+        loss = torch.nn.functional.cross_entropy(y, torch.tensor([1, 2, 3, 4], device=DEV))
+        opt.zero_grad()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ghn.parameters())
+        opt.step()
+        losses.append(float(loss))
+    assert losses[2] < losses[0], losses
