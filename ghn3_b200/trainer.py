@@ -1,0 +1,165 @@
+"""
+One GHN training step on the B200 path -- the GHN branch of the reference's `Trainer.update`
+(ghn3/trainer.py:238-411) with the same argument meaning:
+
+    trainer = Trainer(ghn, opt='adamw', opt_args={'lr': 4e-4, 'weight_decay': 1e-2}, grad_clip=5, predparam_wd=3e-5)
+    metrics = trainer.update(images, targets, graphs=graph_batch)       # graph_batch.nets = the target networks
+
+What differs from the reference, by design:
+  * no autocast / GradScaler: the GHN computes in bf16 or error-compensated tf32 with fp32 accumulation and fp32
+    gradients (`GHN3(compute_dtype=...)`), so the fp16 range workarounds (trainer.py:343-379) have nothing to do;
+  * data parallelism is not DistributedDataParallel: the hand-written backward pass all-reduces its one flat
+    gradient buffer itself (ghn3_b200.train.GradSync), overlapping the decoder gradients with the Graphormer adjoint;
+  * metrics are kept on the device and averaged across ranks with ONE packed all-reduce per step instead of the
+    4-5 `.item()` + all_gather round trips (trainer.py:381-388, ddp_utils.py:84-93).
+"""
+import torch
+import torch.nn as nn
+
+from .train import enable_grad_sync
+
+
+def is_ddp():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_meta_batch(n_items, rank, world_size):
+    """Indices of the meta-batch items owned by `rank`: contiguous equal shares (reference train_ghn_ddp.py:92 gives
+    every rank meta_batch_size // world_size graphs)."""
+    if n_items % world_size != 0:
+        raise ValueError('meta batch size %d must be divisible by the number of ranks %d (train_ghn_ddp.py:92)'
+                         % (n_items, world_size))
+    per = n_items // world_size
+    return list(range(rank * per, (rank + 1) * per))
+
+
+class AvgMeter:
+    def __init__(self):
+        self.sum, self.cnt = 0.0, 0
+
+    def update(self, val, n=1):
+        self.sum += float(val) * n
+        self.cnt += n
+
+    @property
+    def avg(self):
+        return self.sum / max(self.cnt, 1)
+
+
+class Trainer:
+    def __init__(self, model, opt='adamw', opt_args=None, scheduler=None, n_batches=None, grad_clip=5,
+                 device='cuda', log_interval=100, label_smoothing=0, predparam_wd=0, verbose=False, **unused):
+        self.criterion = nn.CrossEntropyLoss(label_smoothing=label_smoothing)
+        self.n_batches, self.grad_clip, self.device = n_batches, grad_clip, device
+        self.log_interval, self.predparam_wd, self.verbose = log_interval, predparam_wd, verbose
+        self.ddp = is_ddp()
+        model.to(device)
+        self._model = model
+        if self.ddp:
+            enable_grad_sync(model)
+        opt_args = dict(opt_args or {})
+        params = [p for p in model.parameters() if p.requires_grad]
+        if isinstance(opt, str):
+            name = opt.lower()
+            if name == 'sgd':
+                opt_args.setdefault('momentum', 0.9)
+                self._optimizer = torch.optim.SGD(params, **opt_args)
+            elif name == 'adam':
+                self._optimizer = torch.optim.Adam(params, **opt_args)
+            elif name == 'adamw':
+                self._optimizer = torch.optim.AdamW(params, **opt_args)
+            else:
+                raise NotImplementedError(opt)
+        else:
+            self._optimizer = opt
+        self._scheduler = scheduler
+        self._step = 0
+        self.skipped_updates = 0
+        self.reset_metrics()
+
+    def reset_metrics(self, epoch=0):
+        self._step = 0
+        self.metrics = {'loss': AvgMeter(), 'top1': AvgMeter(), 'top5': AvgMeter()}
+        if self.predparam_wd > 0:
+            self.metrics['loss_predwd'] = AvgMeter()
+
+    def scheduler_step(self):
+        if self._scheduler is not None:
+            self._scheduler.step()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def update(self, images, targets, graphs=None, models=None, loss_fn=None):
+        """
+        One step (reference trainer.py:238-411). `graphs.nets` (or `models`) are the target networks of this rank's
+        share of the meta-batch. `loss_fn(models) -> scalar` replaces the image forward (used by the GHN-only
+        benchmark); by default every network runs on `images` and the cross-entropy losses are averaged.
+        Returns self.metrics.
+        """
+        ghn = self._model
+        if not ghn.training:
+            ghn.train()
+        self._optimizer.zero_grad(set_to_none=True)
+        if models is None:
+            models = list(getattr(graphs, 'nets', None) or [])
+        if not models:
+            raise ValueError('Trainer.update needs the target networks (graphs.nets or models=...)')
+        models = ghn(models, graphs, bn_track_running_stats=True, keep_grads=True, reduce_graph=True)
+        models = models if isinstance(models, (list, tuple)) else [models]
+        loss_predwd = None
+        if self.predparam_wd > 0:
+            total = 0
+            for m in models:
+                for p in m.parameters():
+                    total = total + torch.norm(p, p='fro')
+            loss_predwd = self.predparam_wd * total
+        logits = None
+        if loss_fn is not None:
+            loss = loss_fn(models)
+        else:
+            targets = targets.to(self.device, non_blocking=True)
+            images = images.to(self.device, non_blocking=True)
+            loss, logits = 0, []
+            for model in models:
+                out = model(images)
+                y = out[0] if isinstance(out, tuple) else out
+                loss = loss + self.criterion(y, targets)
+                logits.append(y.detach())
+            logits = torch.stack(logits)
+        if loss_predwd is not None:
+            loss = loss + loss_predwd
+        loss = loss / len(models)                                   # mean over this rank's models (trainer.py:327)
+        loss.backward()                                             # GHN adjoint + gradient all-reduce inside
+        if self.grad_clip > 0:
+            nn.utils.clip_grad_norm_([p for g in self._optimizer.param_groups for p in g['params']], self.grad_clip)
+        self._optimizer.step()
+
+        # metrics: one packed device tensor, one all-reduce, one host read
+        vals = [loss.detach().float()]
+        if loss_predwd is not None:
+            vals.append(loss_predwd.detach().float() if torch.is_tensor(loss_predwd) else torch.tensor(0.0))
+        if logits is not None:
+            tg = targets.view(1, -1).expand(len(logits), -1).reshape(-1)
+            lg = logits.reshape(-1, logits.shape[-1])
+            top = lg.topk(min(5, lg.shape[-1]), 1).indices
+            hit = top.eq(tg.view(-1, 1))
+            vals += [hit[:, :1].any(1).float().mean() * 100, hit.any(1).float().mean() * 100]
+        packed = torch.stack([v.to(self.device) for v in vals])
+        if self.ddp:
+            import torch.distributed as dist
+            dist.all_reduce(packed)
+            packed = packed / dist.get_world_size()
+        host = packed.tolist()
+        if host[0] != host[0]:
+            raise RuntimeError('the loss is NaN at step %d, unable to proceed' % self._step)
+        n = 1 if logits is None else logits.shape[0] * logits.shape[1]
+        self.metrics['loss'].update(host[0], n)
+        i = 1
+        if loss_predwd is not None:
+            self.metrics['loss_predwd'].update(host[i], n)
+            i += 1
+        if logits is not None:
+            self.metrics['top1'].update(host[i], n)
+            self.metrics['top5'].update(host[i + 1], n)
+        self._step += 1
+        return self.metrics

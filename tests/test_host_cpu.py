@@ -201,3 +201,38 @@ dist.destroy_process_group()
                         '--master-addr', '127.0.0.1', '--master-port', '29531', str(script)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_training_exchange_two_ranks_gloo(tmp_path):
+    """world_size-2 run of the training path's host logic: contiguous meta-batch shares (train_ghn_ddp.py:92) and the
+    two-region flat-gradient average of ghn3_b200.train.GradSync (sum + divide on gloo, AVG on NCCL)."""
+    script = tmp_path / 'w.py'
+    script.write_text('''
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from ghn3_b200.train import GradSync
+from ghn3_b200.trainer import shard_meta_batch
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = shard_meta_batch(8, rank, world)
+assert mine == list(range(rank * 4, rank * 4 + 4))
+try:
+    shard_meta_batch(7, rank, world)
+    raise SystemExit('expected ValueError')
+except ValueError:
+    pass
+sync = GradSync()
+assert not sync.avg and sync.world == 2
+flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+works = [sync.start(flat[:6]), sync.start(flat[6:])]
+sync.finish(works, flat)
+assert torch.allclose(flat, torch.arange(10, dtype=torch.float32) * 1.5), flat
+if rank == 0:
+    print('OK')
+dist.destroy_process_group()
+''' % REPO)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29532', str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
