@@ -214,6 +214,8 @@ class GHN3(GHN):
         return super().load_state_dict(*args, **kwargs)
 
     def _device_weights(self):
+        """Device copies of the weights in the compute dtype. Built once; when the parameters change IN PLACE
+        (optimizer step, load_state_dict) the same buffers are refreshed, so prebuilt programs stay valid."""
         sig = self._weights_signature()
         if self._dev is not None and self._dev['sig'] == sig:
             return self._dev
@@ -223,12 +225,35 @@ class GHN3(GHN):
         if not self.layernorm:
             raise NotImplementedError('ghn3_b200: layernorm=False GHNs are not supported by the CUDA path')
         self.fix_embed_layers()
+        if self._dev is not None and self._dev['compute_dtype'] == self.compute_dtype and self._dev['ptrs'] == \
+                [p.data_ptr() for p in self._param_list]:
+            for fn in self._dev['refresh']:
+                fn()
+            self._dev['sig'] = sig
+            return self._dev
         dt, x3 = DTYPES[self.compute_dtype]
         C, S = self.hid, self.max_shape[2]
-        f = lambda p: p.detach().contiguous().float()
-        cv = (lambda p: f(p)) if x3 else (lambda p: ops.convert(f(p), dt))      # x3 keeps the fp32 master weights
+        refresh = []
+
+        def f(p):
+            """fp32 view of a parameter: aliases its storage when possible, otherwise a copy that is refreshed."""
+            d = p.detach()
+            if d.dtype == torch.float32 and d.is_contiguous():
+                return d
+            buf = d.contiguous().float()
+            refresh.append(lambda: buf.copy_(p.detach()))
+            return buf
+
+        def cv(p):
+            if x3:                                         # x3 keeps the fp32 master weights
+                return f(p)
+            buf = ops.convert(f(p), dt)
+            refresh.append(lambda: ops.convert(p.detach().float().contiguous(), dt, out=buf))
+            return buf
+
         g0 = self.gnn[0]
-        w = {'sig': sig, 'dtype': dt, 'x3': x3, 'act': ops.F32 if x3 else dt}
+        w = {'sig': sig, 'dtype': dt, 'x3': x3, 'act': ops.F32 if x3 else dt, 'compute_dtype': self.compute_dtype,
+             'ptrs': [p.data_ptr() for p in self._param_list], 'refresh': refresh}
         w['tables'] = {'embed_op': f(self.embed.weight), 'embed_ch': f(self.shape_enc.embed_channel.weight),
                        'embed_sp': f(self.shape_enc.embed_spatial.weight),
                        'cent_in': f(g0.centrality_embed_in.weight), 'cent_out': f(g0.centrality_embed_out.weight),
@@ -236,6 +261,11 @@ class GHN3(GHN):
         self._lut_cache = {}
         w['lut_inputs'] = (f(g0.attn.edge_embed.embed.weight), f(g0.attn.proj_e[0].weight), f(g0.attn.proj_e[0].bias),
                            f(g0.attn.proj_e[2].weight), f(g0.attn.proj_e[2].bias))
+
+        def refresh_luts():
+            for vmax, lut in self._lut_cache.items():
+                ops.edge_lut(*w['lut_inputs'], vmax=vmax, out=lut)
+        refresh.append(refresh_luts)
         layers = (L.LayerWeights * self.layers)()
         keep = []
         for l, layer in enumerate(self.gnn):
@@ -251,10 +281,16 @@ class GHN3(GHN):
         dec = self.decoder
         # fc weight repacked position-major: [c*S*S + p][k] -> [p][c][k], so one decoder-grid position is one
         # contiguous [4C, C] block and a crop window is a set of row ranges (nn.py:738-745)
-        fc_w = f(dec.fc[0].weight).view(4 * C, S * S, C).permute(1, 0, 2).contiguous().view(S * S * 4 * C, C)
-        w['fc_w'] = fc_w if x3 else ops.convert(fc_w, dt)
-        del fc_w
-        w['fc_b'] = f(dec.fc[0].bias).view(4 * C, S * S).t().contiguous().view(-1)
+        repack_w = lambda: f(dec.fc[0].weight).view(4 * C, S * S, C).permute(1, 0, 2).contiguous().view(S * S * 4 * C, C)
+        repack_b = lambda: f(dec.fc[0].bias).view(4 * C, S * S).t().contiguous().view(-1)
+        if x3:
+            w['fc_w'] = repack_w()
+            refresh.append(lambda: w['fc_w'].copy_(repack_w()))
+        else:
+            w['fc_w'] = ops.convert(repack_w(), dt)
+            refresh.append(lambda: ops.convert(repack_w(), dt, out=w['fc_w']))
+        w['fc_b'] = repack_b()
+        refresh.append(lambda: w['fc_b'].copy_(repack_b()))
         w['c0_w'], w['c0_b'] = cv(dec.conv[0].weight), f(dec.conv[0].bias)
         w['c2_w'], w['c2_b'] = cv(dec.conv[2].weight), f(dec.conv[2].bias)
         w['cls_w'], w['cls_b'] = cv(dec.class_layer_predictor[1].weight), f(dec.class_layer_predictor[1].bias)

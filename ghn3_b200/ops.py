@@ -170,12 +170,12 @@ def node_features(op, shape_idx, pack, tables, hid):
     return x
 
 
-def edge_lut(edge_embed, w1, b1, w2, b2, vmax=50):
+def edge_lut(edge_embed, w1, b1, w2, b2, vmax=50, out=None):
     _require_cuda(edge_embed, 'edge_embed')
     C_, H = w1.shape[0], w2.shape[0]
     V = vmax + 1
     ws = torch.empty(2 * V * C_, dtype=torch.float32, device=w1.device)
-    lut = torch.empty(H, V * V, dtype=torch.float32, device=w1.device)
+    lut = torch.empty(H, V * V, dtype=torch.float32, device=w1.device) if out is None else out
     a = L.EdgeLutArgs(hid=C_, heads=H, vmax=vmax, edge_embed=L.ptr(edge_embed), w1=L.ptr(w1), b1=L.ptr(b1),
                       w2=L.ptr(w2), b2=L.ptr(b2), workspace=L.ptr(ws), lut=L.ptr(lut))
     L.call('edge_lut', a, L.current_stream())
@@ -250,10 +250,11 @@ def scatter(descs_dev, n_descs, n_chunks, chunk_desc=None):
     L.call('scatter', a, L.current_stream())
 
 
-def convert(src, dst_dtype):
+def convert(src, dst_dtype, out=None):
     _require_cuda(src, 'src')
     src = src.contiguous()
-    dst = torch.empty(src.shape, dtype=TORCH_DTYPE[dst_dtype], device=src.device)
+    dst = torch.empty(src.shape, dtype=TORCH_DTYPE[dst_dtype], device=src.device) if out is None else out
+    assert dst.numel() == src.numel() and dst.is_contiguous()
     L.check(L.load().ghn3_convert_f32(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(src.numel()),
                                       C.c_int32(dst_dtype), C.c_void_p(L.current_stream())), 'ghn3_convert_f32')
     return dst

@@ -34,7 +34,13 @@ def transposed_weights(ghn, w):
     if wt is not None:
         return wt
     act = w['act']
-    T = lambda t: ops.transpose(t, dst_dtype=act)       # [cols, rows] view, row stride padded to 8 elements
+
+    def T(t):
+        """[cols, rows] view of a buffer whose row stride is padded to 8 elements; refreshed with the weights."""
+        view = ops.transpose(t, dst_dtype=act)
+        base = view._base if view._base is not None else view
+        w['refresh'].append(lambda: ops.transpose(t, dst_dtype=act, out=base))
+        return view
     layers = (L.LayerWeightsT * ghn.layers)()
     keep = []
     for l, t in enumerate(w['layers_keep']):
@@ -351,6 +357,18 @@ class _Backward:
         lib = L.load()
         nd = self.n_decoder_ops
         sync = getattr(self.ghn, '_grad_sync', None)
+        prof = getattr(self.ghn, '_profile_bwd', None)
+        if prof is not None:                       # per-op device times (tools/profile_train.py); no exchange
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            prof.append(('start', ev))
+            for name, args in self.ops:
+                L.call(name, args, stream)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                prof.append((name, ev))
+            self.live = live
+            return self.gviews
         L.check(lib.ghn3_run_sequence(self.seq, nd, ct.c_void_p(stream)), 'ghn3_run_sequence (decoder backward)')
         works = []
         if sync is not None and self.early_elems:
