@@ -187,6 +187,20 @@ class ReluTransposeBwdArgs(C.Structure):
                 ('batch', i32)]
 
 
+class ExpandSeg(C.Structure):
+    _fields_ = [('src_off', i64), ('row0', i32), ('rows', i32), ('ld', i32), ('group', i32), ('tile0', i32),
+                ('tiles_c', i32)]
+
+
+class ExpandArgs(C.Structure):
+    _fields_ = [('segs', vp), ('n_segs', i32), ('n_tiles', i32), ('src', vp), ('group_stride', i32), ('x', vp),
+                ('ld_x', i64), ('xt', vp), ('ld_xt', i64), ('dtype', i32), ('d_bias', vp)]
+
+
+class MemsetArgs(C.Structure):
+    _fields_ = [('ptr', vp), ('bytes', i64)]
+
+
 class GraphormerTrainArgs(C.Structure):
     _fields_ = [('fwd', GraphormerArgs), ('xs', vp), ('xm', vp), ('h1', vp), ('qkv', vp), ('ao', vp), ('h2', vp),
                 ('u', vp), ('g', vp)]
@@ -215,7 +229,7 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
-                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd']
+                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols']
 SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None

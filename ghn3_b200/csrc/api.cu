@@ -148,6 +148,16 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
       case GHN3_OP_EDGE_LUT_BWD: rc = ghn3_edge_lut_bwd((const ghn3_edge_lut_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_FC_BWD: rc = ghn3_fc_bwd((const ghn3_fc_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_RELU_TRANSPOSE_BWD: rc = ghn3_relu_transpose_bwd((const ghn3_relu_transpose_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_EXPAND_COLS: rc = ghn3_expand_cols((const ghn3_expand_args*)ops[i].args, stream); break;
+      case GHN3_OP_MEMSET: {
+        const ghn3_memset_args* m = (const ghn3_memset_args*)ops[i].args;
+        rc = GHN3_OK;
+        if (m->bytes > 0 && cudaMemsetAsync(m->ptr, 0, (size_t)m->bytes, (cudaStream_t)stream) != cudaSuccess) {
+          ghn3::set_error("ghn3_run_sequence: cudaMemsetAsync failed at index %d", i);
+          rc = GHN3_ERR_CUDA;
+        }
+        break;
+      }
       default:
         ghn3::set_error("ghn3_run_sequence: unknown op %d at index %d", ops[i].op, i);
         return GHN3_ERR_BAD_ARG;

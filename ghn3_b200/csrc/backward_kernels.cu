@@ -159,11 +159,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
 //   dlut[h][pair(i,j)] += dS_ij
 constexpr int kBwdKT = 128;     // keys (kernel A) / queries (kernel B) staged per tile
 constexpr int kBwdWarps = 8;
-constexpr int kBwdPerWarp = 2;  // queries (A) / keys (B) per warp
+constexpr int kBwdPerWarp = 1;  // queries (A) / keys (B) per warp (register budget: 2 CTAs per SM)
 constexpr int kBwdRows = kBwdWarps * kBwdPerWarp;
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256) attention_bwd_dq_kernel(const ghn3_attention_bwd_args a) {
+__global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
   float* sK = bw_smem;                         // [KT][DP]
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) attention_bwd_dq_kernel(const ghn3_attent
 }
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256) attention_bwd_dkv_kernel(const ghn3_attention_bwd_args a) {
+__global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
   float* sQ = bw_smem;                         // [QT][DP]   (pre-scaled by d^-1/2)
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) attention_bwd_dkv_kernel(const ghn3_atten
       sDelta[i] = a.delta[(int64_t)h * a.total_nodes + n0 + i0 + i];
     }
     for (int idx = threadIdx.x; idx < kBwdKT * kBwdRows; idx += blockDim.x) {
-      const int i = idx / kBwdRows, r = idx - i * kBwdRows;       // 16 consecutive threads read 32 contiguous bytes
+      const int i = idx / kBwdRows, r = idx - i * kBwdRows;       // kBwdRows consecutive threads read contiguous bytes
       float b = 0.f;
       if (i < it && j0 + r < n) b = sLut[pair[(int64_t)(i0 + i) * ld + j0 + r]];
       sBias[r * kBwdKT + i] = b;
@@ -710,6 +710,56 @@ __global__ void __launch_bounds__(256) relu_transpose_bwd_kernel(const ghn3_relu
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Decoder conv.2 backward, operand preparation: the compact per-class gradients dwout_c [rows_c][o'*i'] are expanded
+// into the full max_shape column space, x[row0 + r][col(c)] and xt[col(c)][row0 + r] with col(c) = (c / i') * ms1 +
+// c % i' (zeros elsewhere, set by the caller), so that ONE dgrad GEMM and ONE wgrad GEMM cover every column class;
+// the zeros cost tensor-core flops, not HBM passes over the 1.8 GB weight gradient. Also accumulates the bias
+// gradient d_bias[col(c)] += sum_r dwout_c[r][c].
+__global__ void __launch_bounds__(256) expand_kernel(const ghn3_expand_args a) {
+  __shared__ float tile[32][33];
+  __shared__ int s_seg;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = a.n_segs;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.segs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    s_seg = lo;
+  }
+  __syncthreads();
+  const ghn3_expand_seg sg = a.segs[s_seg];
+  const int lt = blockIdx.x - sg.tile0;
+  const int r0 = (lt / sg.tiles_c) * 32, c0 = (lt % sg.tiles_c) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = a.src + sg.src_off;
+  auto col = [&](int c) -> int64_t {
+    return sg.group > 0 ? (int64_t)(c / sg.group) * a.group_stride + c % sg.group : c;
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < sg.rows && c < sg.ld) {
+      v = src[(int64_t)r * sg.ld + c];
+      st_f(a.x, (int64_t)(sg.row0 + r) * a.ld_x + col(c), a.dtype, v);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < sg.ld && r < sg.rows) st_f(a.xt, col(c) * a.ld_xt + sg.row0 + r, a.dtype, tile[tx][ty + 8 * i]);
+  }
+  if (a.d_bias != nullptr && ty == 0 && c0 + tx < sg.ld) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) t += tile[r][tx];
+    if (t != 0.f) atomicAdd(a.d_bias + col(c0 + tx), t);
+  }
+}
+
 }  // namespace ghn3
 
 using namespace ghn3;
@@ -838,5 +888,15 @@ extern "C" int ghn3_relu_transpose_bwd(const ghn3_relu_transpose_bwd_args* a, gh
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)num_sms() * 16);
   relu_transpose_bwd_kernel<<<blocks, 256, 0, stream>>>(*a);
   GHN3_LAUNCH_CHECK("relu_transpose_bwd_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_expand_cols(const ghn3_expand_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_expand_cols: null args");
+  if (a->n_segs <= 0 || a->n_tiles <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->segs && a->src && a->x && a->xt, "ghn3_expand_cols: null pointer");
+  expand_kernel<<<(unsigned)a->n_tiles, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("expand_kernel");
   return GHN3_OK;
 }

@@ -20,7 +20,7 @@ from .plan import SRC_CLSB, SRC_CLSW, SRC_D1, SRC_TOK, SRC_WOUT
 
 OPC = {'graphormer_bwd': 8, 'transpose': 9, 'elementwise': 10, 'colsum': 11, 'layernorm_bwd': 12,
        'attention_bwd': 13, 'scatter_bwd': 14, 'node_features_bwd': 15, 'edge_lut_bwd': 16, 'fc_bwd': 17,
-       'relu_transpose_bwd': 18, 'gemm': 3, 'gemm_simt': 4}
+       'relu_transpose_bwd': 18, 'expand_cols': 19, 'memset': 20, 'gemm': 3, 'gemm_simt': 4}
 
 
 def _pad8(n):
@@ -48,8 +48,8 @@ def transposed_weights(ghn, w):
         keep.append(d)
         for k, v in d.items():
             setattr(layers[l], k, v.data_ptr())
-    wt = {'layers': layers, 'keep': keep, 'c0_wT': T(w['c0_w']), 'd1_w0T': T(w['d1_w0']), 'd1_w1T': T(w['d1_w1']),
-          'cls_wT': T(w['cls_w'])}
+    wt = {'layers': layers, 'keep': keep, 'c0_wT': T(w['c0_w']), 'c2_wT': T(w['c2_w']), 'd1_w0T': T(w['d1_w0']),
+          'd1_w1T': T(w['d1_w1']), 'cls_wT': T(w['cls_w'])}
     w['T'] = wt
     return wt
 
@@ -155,6 +155,7 @@ class _Backward:
             self.dsrc_dev = torch.from_numpy(dsrc).to(dev)
             self.grad_ptrs = torch.zeros(n_desc, dtype=torch.int64, device=dev)
             self.grad_ptrs_host = torch.zeros(n_desc, dtype=torch.int64).pin_memory()
+            self.grad_ptrs_np = self.grad_ptrs_host.numpy()
             add('scatter_bwd', L.ScatterBwdArgs(descs=L.ptr(prog.desc_dev), n_descs=n_desc, n_chunks=bp.n_chunks,
                                                 chunk_desc=L.ptr(prog.st['chunk_desc']), grads=L.ptr(self.grad_ptrs),
                                                 d_src=L.ptr(self.dsrc_dev)))
@@ -221,36 +222,31 @@ class _Backward:
                                                                  d_src=self.dwout.data_ptr() + woff * 4, ld=ii,
                                                                  src_bs=ld, d_rt=L.ptr(drt), rows=ms0, cols=ii,
                                                                  batch=cnt))
-            max_elems = max(_pad8(rows) * o * ii for (o, ii, _, rows, _) in bp.segments)
-            max_a2 = max(rows * _pad8(o * ii) for (o, ii, _, rows, _) in bp.segments)
-            max_ld = max(_pad8(o * ii) for (o, ii, _, _, _) in bp.segments)
-            max_rows = max(_pad8(rows) for (_, _, _, rows, _) in bp.segments)
-            taT, a2 = E(max_elems), E(max_a2)
-            tW = E(8 * C * max_ld)
-            h1T = E(8 * C * max(max_rows, _pad8(R)))
-            self.dh1, self.dh0 = E(R, 8 * C), E(R, 4 * C)
-            self.keep += [taT, a2, tW, h1T]
-            rowmaps = {}
-            c2w, c2b = dec.conv[2].weight, dec.conv[2].bias
-            for (o, ii, row0, rows, base) in bp.segments:
+            # conv.2: the per-class compact gradients are expanded into the full ms0*ms1 column space (zeros elsewhere,
+            # written once: the expanded positions are the same every step), then ONE dgrad and ONE wgrad GEMM
+            KF = ms0 * ms1
+            rp = _pad8(R)
+            self.X = torch.zeros(R, KF, dtype=adt, device=dev)
+            self.XT = torch.zeros(KF, rp, dtype=adt, device=dev)
+            segs, tile0 = (L.ExpandSeg * len(bp.segments))(), 0
+            for i_, (o, ii, row0, rows, base) in enumerate(bp.segments):
                 ld = o * ii
-                ldp, rp = _pad8(ld), _pad8(rows)
-                grp = 0 if ii == ms1 else ii
-                dseg = self.dwout.data_ptr() + base * 4
-                transpose(dseg, rows, ld, ld, taT, src_dtype=F32)                # dwout^T [ld][rows]
-                transpose(taT, ld, rows, rp, a2, src_dtype=act)                  # dwout   [rows][ld] (padded stride)
-                transpose(w['c2_w'], ld, 8 * C, 8 * C, tW, src_dtype=act, group=grp, group_stride=ms1)
-                gemm(a2, rows, ldp, tW, 8 * C, ldp, ld, self.dh1.data_ptr() + row0 * 8 * C * el, act)
-                transpose(prog.h1.data_ptr() + row0 * 8 * C * el, rows, 8 * C, 8 * C, h1T, src_dtype=act)
-                rm = None
-                if grp:
-                    if ii not in rowmaps:
-                        m_ = np.arange(ms0 * ii, dtype=np.int64)
-                        rowmaps[ii] = torch.from_numpy(((m_ // ii) * ms1 + m_ % ii).astype(np.int32)).to(dev)
-                    rm = rowmaps[ii]
-                gemm(taT, ld, rp, h1T, 8 * C, rp, rows, G(c2w), F32, accumulate=1, rowmap=rm, ldd=8 * C)
-                colsum(dseg, F32, rows, ld, ld, G(c2b), group=grp, group_stride=ms1)
-            self.keep.append(rowmaps)
+                tc = (ld + 31) // 32
+                segs[i_] = L.ExpandSeg(src_off=base, row0=row0, rows=rows, ld=ld, group=0 if ii == ms1 else ii,
+                                       tile0=tile0, tiles_c=tc)
+                tile0 += ((rows + 31) // 32) * tc
+            self.segs_dev = torch.from_numpy(np.frombuffer(bytes(segs), dtype=np.uint8).copy()).to(dev)
+            c2w, c2b = dec.conv[2].weight, dec.conv[2].bias
+            add('expand_cols', L.ExpandArgs(segs=L.ptr(self.segs_dev), n_segs=len(bp.segments), n_tiles=tile0,
+                                            src=L.ptr(self.dwout), group_stride=ms1, x=L.ptr(self.X), ld_x=KF,
+                                            xt=L.ptr(self.XT), ld_xt=rp, dtype=act, d_bias=G(c2b).data_ptr()))
+            h1T = E(8 * C * rp)
+            self.dh1, self.dh0 = E(R, 8 * C), E(R, 4 * C)
+            self.keep.append(h1T)
+            c2T = wt['c2_wT']
+            gemm(self.X, R, KF, c2T, 8 * C, c2T.stride(0), KF, self.dh1, act, b_dynamic=0)
+            transpose(prog.h1, R, 8 * C, 8 * C, h1T, src_dtype=act)
+            gemm(self.XT, KF, rp, h1T, 8 * C, rp, R, G(c2w), F32)
             rp = _pad8(R)
             h0T = E(4 * C * rp)
             self.keep.append(h0T)
@@ -316,15 +312,20 @@ class _Backward:
                                    d_w2=G(g0.attn.proj_e[2].weight).data_ptr(),
                                    d_b2=G(g0.attn.proj_e[2].bias).data_ptr())
         add('edge_lut_bwd', self.lb)
+        # the buffers that accumulate atomically are cleared by memset ops at the head of the sequence
+        head = [('memset', L.MemsetArgs(ptr=t.data_ptr(), bytes=t.numel() * t.element_size())) for t in self.zero]
+        self.ops = head + self.ops
+        self.n_decoder_ops += len(head)
         self.seq = (L.SeqOp * len(self.ops))()
         for i, (name, args) in enumerate(self.ops):
             self.seq[i].op = OPC[name]
             self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
 
     # ------------------------------------------------------------------------------------------------------------
-    def run(self, out_grads, out_index):
+    def run(self, out_grads, out_index, flat_grad=None, slices=None):
         """out_grads: gradients of the program outputs (one per predicted PARAMETER, None allowed);
-        out_index[i] = (output index, byte shift, has_grad_path) of descriptor i. Returns the GHN parameter grads."""
+        out_index[i] = (output index, byte shift, has_grad_path) of descriptor i; flat_grad: gradient of the flat
+        buffer all outputs are slices of (slices[oi] = (offset, numel, shape)). Returns the GHN parameter grads."""
         prog = self.prog
         pack = prog.bound_pack
         dev = prog.device
@@ -337,22 +338,39 @@ class _Backward:
             self.lb.d_lut, self.lb.workspace, self.lb.vmax = self.d_lut.data_ptr(), self.lut_ws.data_ptr(), vmax
         nfb, nf = self.nfb, prog.nf
         nfb.op, nfb.deg_in, nfb.deg_out, nfb.dist0 = nf.op, nf.deg_in, nf.deg_out, nf.dist0
-        for t in self.zero:
-            t.zero_()
         self.d_lut.zero_()
         live = []
         if self.n_desc:
-            host = self.grad_ptrs_host
+            host = self.grad_ptrs_np
+            flat_ptr = 0
+            if flat_grad is not None:
+                if flat_grad.dtype != torch.float32 or not flat_grad.is_contiguous():
+                    flat_grad = flat_grad.float().contiguous()
+                live.append(flat_grad)
+                flat_ptr = flat_grad.data_ptr()
+            cache = {}
             for i, (oi, shift, has_path) in enumerate(out_index):
-                g = out_grads[oi] if has_path else None
-                if g is None:
+                if not has_path:
                     host[i] = 0
                     continue
-                if g.dtype != torch.float32 or not g.is_contiguous():
-                    g = g.float().contiguous()
-                live.append(g)
-                host[i] = g.data_ptr() + shift
-            self.grad_ptrs.copy_(host, non_blocking=True)
+                g = cache.get(oi, False)
+                if g is False:
+                    g = out_grads[oi]
+                    if g is not None and flat_ptr:                # both routes carry gradient: add them
+                        o, n, shape = slices[oi]
+                        g = g + flat_grad[o:o + n].view(shape)
+                    if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                        g = g.float().contiguous()
+                    cache[oi] = g
+                    if g is not None:
+                        live.append(g)
+                if g is not None:
+                    host[i] = g.data_ptr() + shift
+                elif flat_ptr:
+                    host[i] = flat_ptr + slices[oi][0] * 4 + shift
+                else:
+                    host[i] = 0
+            self.grad_ptrs.copy_(self.grad_ptrs_host, non_blocking=True)
         stream = L.current_stream()
         lib = L.load()
         nd = self.n_decoder_ops
@@ -362,8 +380,9 @@ class _Backward:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             prof.append(('start', ev))
-            for name, args in self.ops:
-                L.call(name, args, stream)
+            for i, (name, args) in enumerate(self.ops):
+                one = ct.c_void_p(ct.addressof(self.seq) + i * ct.sizeof(L.SeqOp))
+                L.check(lib.ghn3_run_sequence(one, 1, ct.c_void_p(stream)), 'ghn3_run_sequence (%s)' % name)
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 prof.append((name, ev))
@@ -421,17 +440,19 @@ class _PredictFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ghn, prog, pack, out_meta, out_index, *params):
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
         prog.bind_pack(pack)
         total = out_meta['total']
-        pred = torch.empty(total, dtype=torch.float32, device=prog.device)
+        pred = torch.zeros(total, dtype=torch.float32, device=prog.device)      # padding between slices stays 0
         prog.point_descriptors_at(pred, out_meta, ghn.weight_norm)
         if prog.bp.n_tok_elems:
             prog.tok.normal_(mean=0.0, std=0.02)
         prog.run(getattr(ghn, '_profile', None))
         prog.step_id = getattr(prog, 'step_id', 0) + 1
         ctx.ghn, ctx.prog, ctx.out_index, ctx.step_id = ghn, prog, out_index, prog.step_id
+        ctx.slices = out_meta['slices']
         outs = tuple(pred[o:o + n].view(shape) for (o, n, shape) in out_meta['slices'])
-        return outs
+        return outs + (pred,)
 
     @staticmethod
     def backward(ctx, *grads):
@@ -441,7 +462,7 @@ class _PredictFn(torch.autograd.Function):
                                'program; its saved activations have been overwritten')
         if prog.bwd is None:
             prog.bwd = _Backward(prog, ghn)
-        gviews = prog.bwd.run(grads, ctx.out_index)
+        gviews = prog.bwd.run(grads[:-1], ctx.out_index, grads[-1], ctx.slices)
         return (None, None, None, None, None) + tuple(gviews)
 
 
@@ -488,4 +509,7 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
             module.__dict__[attr] = t                      # nn.py:536-539
             module._parameters[attr] = t
     ghn.last_program = prog
+    # every predicted parameter is a slice of this flat tensor (same autograd node): a loss written on it, e.g. the
+    # <p, R> stub of the GHN-only training benchmark, costs one kernel instead of one per parameter
+    prog.pred_flat = outs[-1]
     return prog.emb

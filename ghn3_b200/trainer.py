@@ -65,10 +65,9 @@ class Trainer:
             if name == 'sgd':
                 opt_args.setdefault('momentum', 0.9)
                 self._optimizer = torch.optim.SGD(params, **opt_args)
-            elif name == 'adam':
-                self._optimizer = torch.optim.Adam(params, **opt_args)
-            elif name == 'adamw':
-                self._optimizer = torch.optim.AdamW(params, **opt_args)
+            elif name in ('adam', 'adamw'):
+                opt_args.setdefault('fused', True)          # one multi-tensor kernel per chunk of the 291 tensors
+                self._optimizer = (torch.optim.Adam if name == 'adam' else torch.optim.AdamW)(params, **opt_args)
             else:
                 raise NotImplementedError(opt)
         else:

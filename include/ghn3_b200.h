@@ -496,6 +496,24 @@ typedef struct {
 } ghn3_relu_transpose_bwd_args;
 int ghn3_relu_transpose_bwd(const ghn3_relu_transpose_bwd_args* args, ghn3_stream_t stream);
 
+/* Decoder conv.2 backward, operand preparation: expands the compact per-column-class gradients of the conv decoder
+ * output (class c: [rows_c][o'*i'] at src + src_off) into the full max_shape column space,
+ *   x[row0 + r][col(k)] = xt[col(k)][row0 + r] = src_c[r][k],  col(k) = (k / group) * group_stride + k % group
+ * (group = i' when i' < max_shape[1], else 0 = identity), and adds the column sums into d_bias[col(k)]
+ * (gradient of decoder.conv.2.bias). x / xt must be zeroed by the caller. One 32x32 tile per CTA; tile0 is the
+ * prefix sum of ceil(rows/32) * tiles_c, tiles_c = ceil(ld/32). */
+typedef struct { int64_t src_off; int32_t row0, rows, ld, group, tile0, tiles_c; } ghn3_expand_seg;
+typedef struct {
+  const ghn3_expand_seg* segs; int32_t n_segs; int32_t n_tiles;
+  const float* src;
+  int32_t group_stride;
+  void* x; int64_t ld_x;
+  void* xt; int64_t ld_xt;
+  int32_t dtype;
+  float* d_bias;
+} ghn3_expand_args;
+int ghn3_expand_cols(const ghn3_expand_args* args, ghn3_stream_t stream);
+
 /* Graphormer stack, training flavour. ghn3_graphormer_train_fwd computes the same function as ghn3_graphormer_stack
  * (fwd.x is ignored: the input node features are xs[0]) but keeps every activation of every layer;
  * ghn3_graphormer_bwd consumes them. Buffers are [layers][total_nodes][width] (xs: layers+1), contiguous. */
@@ -552,8 +570,11 @@ enum ghn3_opcode {
   /* training path */
   GHN3_OP_GRAPHORMER_TRAIN_FWD = 7, GHN3_OP_GRAPHORMER_BWD = 8, GHN3_OP_TRANSPOSE = 9, GHN3_OP_ELEMENTWISE = 10,
   GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
-  GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18
+  GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18,
+  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20
 };
+/* GHN3_OP_MEMSET: args points to a ghn3_memset_args; clears `bytes` bytes at `ptr` (cudaMemsetAsync). */
+typedef struct { void* ptr; int64_t bytes; } ghn3_memset_args;
 typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
 int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);
 

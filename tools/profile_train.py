@@ -34,10 +34,7 @@ def step(profile=False):
     opt.zero_grad(set_to_none=True)
     out = ghn(nets, graphs, keep_grads=True, reduce_graph=True)
     t1 = sync(); t['forward (incl. weight conversion)'] = t1 - t0
-    loss = 0
-    for net in out:
-        for p in net.parameters():
-            loss = loss + p.sum() * 1e-3
+    loss = ghn.last_program.pred_flat.sum() * 1e-3
     t2 = sync(); t['stub loss'] = t2 - t1
     if profile:
         ghn._profile_bwd = []
