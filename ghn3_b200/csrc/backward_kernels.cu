@@ -157,26 +157,38 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
 //   S = Q K^T d^-1/2 + lut[h][pair];  P = softmax(S);  O = P V
 //   delta_i = dO_i . O_i;  dP = dO V^T;  dS = P o (dP - delta);  dQ = dS K d^-1/2;  dK = dS^T Q d^-1/2;  dV = P^T dO
 //   dlut[h][pair(i,j)] += dS_ij
-constexpr int kBwdKT = 128;     // keys (kernel A) / queries (kernel B) staged per tile
+constexpr int kBwdKT = 256;     // keys (kernel A) / queries (kernel B) staged per tile; graphs up to this size
+                                // keep their whole K/V (Q/dO) resident in shared memory for the lifetime of the CTA
 constexpr int kBwdWarps = 8;
-constexpr int kBwdPerWarp = 1;  // queries (A) / keys (B) per warp (register budget: 2 CTAs per SM)
-constexpr int kBwdRows = kBwdWarps * kBwdPerWarp;
+constexpr int kBwdBlock = 64;   // queries (A) / keys (B) per CTA, one per warp per round
+
+template <typename T, int D>
+__device__ __forceinline__ void bwd_load_tile(float* s0, float* s1, const T* base0, const T* base1, int64_t ld0,
+                                              int64_t ld1, int rows, float scale0) {
+  constexpr int DP = D + 1;
+  for (int idx = threadIdx.x; idx < rows * D; idx += blockDim.x) {
+    const int j = idx / D, d = idx - j * D;
+    s0[j * DP + d] = to_float(base0[(int64_t)j * ld0 + d]) * scale0;
+    s1[j * DP + d] = to_float(base1[(int64_t)j * ld1 + d]);
+  }
+}
 
 template <typename T, int D>
 __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
+  constexpr int U = kBwdKT / 32;
   float* sK = bw_smem;                         // [KT][DP]
   float* sV = sK + kBwdKT * DP;                // [KT][DP]
-  float* sBias = sV + kBwdKT * DP;             // [rows][KT]
-  uint16_t* sPair = (uint16_t*)(sBias + kBwdRows * kBwdKT);   // [rows][KT]
-  float* sLut = (float*)(sPair + kBwdRows * kBwdKT);          // [lut_size]
-  float* sHist = sLut + a.lut_size;                           // [lut_size]
+  float* sBias = sV + kBwdKT * DP;             // [warps][KT]  (each warp stages the row of its own query)
+  uint16_t* sPair = (uint16_t*)(sBias + kBwdWarps * kBwdKT);   // [warps][KT]
+  float* sLut = (float*)(sPair + kBwdWarps * kBwdKT);          // [lut_size]
+  float* sHist = sLut + a.lut_size;                            // [lut_size]
 
   const int g = blockIdx.z, h = blockIdx.y;
   const int n0 = a.node_off[g];
   const int n = a.node_off[g + 1] - n0;
-  const int q0 = blockIdx.x * kBwdRows;
+  const int q0 = blockIdx.x * kBwdBlock;
   if (q0 >= n) return;
   const int ld = (n + 15) & ~15;
   const int C = a.hid, C3 = 3 * C;
@@ -186,115 +198,108 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kerne
   const T* out = (const T*)a.out + (int64_t)n0 * C;
   const uint16_t* pair = a.pair + a.mat_off[g];
   const float scale = rsqrtf((float)D);
+  const bool single = n <= kBwdKT;             // block-uniform
 
   for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) {
     sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
     sHist[i] = 0.f;
   }
+  if (single) bwd_load_tile<T, D>(sK, sV, qkv + C + h * D, qkv + 2 * C + h * D, C3, C3, n, 1.f);
+  __syncthreads();
 
-  float q[kBwdPerWarp][D], dO[kBwdPerWarp][D], dq[kBwdPerWarp][D];
-  float m[kBwdPerWarp], l[kBwdPerWarp], delta[kBwdPerWarp];
-  int qi[kBwdPerWarp];
+  float* myBias = sBias + warp * kBwdKT;
+  uint16_t* myPair = sPair + warp * kBwdKT;
+  for (int r = 0; r < kBwdBlock / kBwdWarps; ++r) {
+    const int qi = q0 + r * kBwdWarps + warp;
+    const bool ok = qi < n;                    // warp-uniform
+    if (single && !ok) continue;               // no block-level synchronisation below in the single-tile case
+    float q[D], dO[D], dq[D];
+    float delta = 0.f, m = -INFINITY, l = 0.f;
+    {
+      const int64_t row = ok ? qi : 0;
 #pragma unroll
-  for (int t = 0; t < kBwdPerWarp; ++t) {
-    qi[t] = q0 + warp * kBwdPerWarp + t;
-    const bool ok = qi[t] < n;
-    const int64_t r = ok ? qi[t] : 0;
-    float dl = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      q[t][d] = ok ? to_float(qkv[r * C3 + h * D + d]) * scale : 0.f;
-      dO[t][d] = ok ? to_float(dout[r * C + h * D + d]) : 0.f;
-      dq[t][d] = 0.f;
-      dl += dO[t][d] * (ok ? to_float(out[r * C + h * D + d]) : 0.f);
+      for (int d = 0; d < D; ++d) {
+        q[d] = ok ? to_float(qkv[row * C3 + h * D + d]) * scale : 0.f;
+        dO[d] = ok ? to_float(dout[row * C + h * D + d]) : 0.f;
+        dq[d] = 0.f;
+        delta += dO[d] * (ok ? to_float(out[row * C + h * D + d]) : 0.f);
+      }
     }
-    delta[t] = dl;
-    m[t] = -INFINITY;
-    l[t] = 0.f;
-  }
-
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int k0 = 0; k0 < n; k0 += kBwdKT) {
-      const int kt = min(kBwdKT, n - k0);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < kt * D; idx += blockDim.x) {
-        const int j = idx / D, d = idx - j * D;
-        const T* row = qkv + (int64_t)(k0 + j) * C3 + h * D + d;
-        sK[j * DP + d] = to_float(row[C]);
-        sV[j * DP + d] = to_float(row[2 * C]);
-      }
-      for (int idx = threadIdx.x; idx < kBwdRows * kBwdKT; idx += blockDim.x) {
-        const int r = idx / kBwdKT, j = idx - r * kBwdKT;
-        uint16_t p = 0;
-        if (q0 + r < n && j < kt) p = pair[(int64_t)(q0 + r) * ld + k0 + j];
-        sPair[idx] = p;
-        sBias[idx] = sLut[p];
-      }
-      __syncthreads();
-#pragma unroll
-      for (int t = 0; t < kBwdPerWarp; ++t) {
-        if (qi[t] >= n) continue;
-        const int r = warp * kBwdPerWarp + t;
-        if (pass == 0) {
-          // running max / sum of exp
-          float mx = m[t];
-          float sv[kBwdKT / 32];
-#pragma unroll
-          for (int u = 0; u < kBwdKT / 32; ++u) {
-            const int j = lane + 32 * u;
-            float s = -INFINITY;
-            if (j < kt) {
-              s = sBias[r * kBwdKT + j];
-#pragma unroll
-              for (int d = 0; d < D; ++d) s = fmaf(q[t][d], sK[j * DP + d], s);
-            }
-            sv[u] = s;
-            mx = fmaxf(mx, s);
+    for (int pass = 0; pass < 2; ++pass) {
+      const float lse = m + __logf(l);         // only meaningful in pass 1
+      for (int k0 = 0; k0 < n; k0 += kBwdKT) {
+        const int kt = min(kBwdKT, n - k0);
+        if (!single) {
+          __syncthreads();
+          bwd_load_tile<T, D>(sK, sV, qkv + (int64_t)k0 * C3 + C + h * D, qkv + (int64_t)k0 * C3 + 2 * C + h * D, C3,
+                              C3, kt, 1.f);
+        }
+        if (ok) {
+          for (int j = lane; j < kt; j += 32) {
+            const uint16_t p = pair[(int64_t)qi * ld + k0 + j];
+            myPair[j] = p;
+            myBias[j] = sLut[p];
           }
-          mx = warp_max(mx);
-          float sum = 0.f;
+        }
+        if (!single) __syncthreads(); else __syncwarp();
+        if (ok) {
+          if (pass == 0) {
+            float mx = m;
+            float sv[U];
 #pragma unroll
-          for (int u = 0; u < kBwdKT / 32; ++u) sum += (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - mx);
-          sum = warp_sum(sum);
-          l[t] = l[t] * __expf(m[t] - mx) + sum;
-          m[t] = mx;
-        } else {
-          const float lse = m[t] + __logf(l[t]);
+            for (int u = 0; u < U; ++u) {
+              const int j = lane + 32 * u;
+              float s_ = -INFINITY;
+              if (j < kt) {
+                s_ = myBias[j];
 #pragma unroll
-          for (int u = 0; u < kBwdKT / 32; ++u) {
-            const int j = lane + 32 * u;
-            if (j < kt) {
-              float s = sBias[r * kBwdKT + j], dp = 0.f;
-#pragma unroll
-              for (int d = 0; d < D; ++d) {
-                s = fmaf(q[t][d], sK[j * DP + d], s);
-                dp = fmaf(dO[t][d], sV[j * DP + d], dp);
+                for (int d = 0; d < D; ++d) s_ = fmaf(q[d], sK[j * DP + d], s_);
               }
-              const float p = __expf(s - lse);
-              const float ds = p * (dp - delta[t]);
+              sv[u] = s_;
+              mx = fmaxf(mx, s_);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
 #pragma unroll
-              for (int d = 0; d < D; ++d) dq[t][d] = fmaf(ds, sK[j * DP + d], dq[t][d]);
-              if (a.d_lut != nullptr) atomicAdd(sHist + sPair[r * kBwdKT + j], ds);
+            for (int u = 0; u < U; ++u) sum += (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - mx);
+            sum = warp_sum(sum);
+            l = l * __expf(m - mx) + sum;
+            m = mx;
+          } else {
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) {
+              const int j = lane + 32 * u;
+              if (j < kt) {
+                float s_ = myBias[j], dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  s_ = fmaf(q[d], sK[j * DP + d], s_);
+                  dp = fmaf(dO[d], sV[j * DP + d], dp);
+                }
+                const float p = __expf(s_ - lse);
+                const float ds = p * (dp - delta);
+#pragma unroll
+                for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, sK[j * DP + d], dq[d]);
+                if (a.d_lut != nullptr) atomicAdd(sHist + myPair[j], ds);
+              }
             }
           }
         }
+        __syncwarp();
       }
     }
-  }
-
+    if (ok) {
+      const int64_t row = n0 + qi;
+      T* dst = (T*)a.d_qkv + row * C3 + h * D;
 #pragma unroll
-  for (int t = 0; t < kBwdPerWarp; ++t) {
-    if (qi[t] >= n) continue;
-    const int64_t row = n0 + qi[t];
-    T* dst = (T*)a.d_qkv + row * C3 + h * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float v = warp_sum(dq[t][d]) * scale;
-      if (lane == 0) dst[d] = from_float<T>(v);
-    }
-    if (lane == 0) {
-      a.lse[(int64_t)h * a.total_nodes + row] = m[t] + __logf(l[t]);
-      a.delta[(int64_t)h * a.total_nodes + row] = delta[t];
+      for (int d = 0; d < D; ++d) {
+        const float v = warp_sum(dq[d]) * scale;
+        if (lane == 0) dst[d] = from_float<T>(v);
+      }
+      if (lane == 0) {
+        a.lse[(int64_t)h * a.total_nodes + row] = m + __logf(l);
+        a.delta[(int64_t)h * a.total_nodes + row] = delta;
+      }
     }
   }
   __syncthreads();
@@ -307,17 +312,18 @@ template <typename T, int D>
 __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
+  constexpr int U = kBwdKT / 32;
   float* sQ = bw_smem;                         // [QT][DP]   (pre-scaled by d^-1/2)
   float* sdO = sQ + kBwdKT * DP;               // [QT][DP]
-  float* sBias = sdO + kBwdKT * DP;            // [keys][QT]
-  float* sLse = sBias + kBwdRows * kBwdKT;     // [QT]
+  float* sBias = sdO + kBwdKT * DP;            // [warps][QT]
+  float* sLse = sBias + kBwdWarps * kBwdKT;    // [QT]
   float* sDelta = sLse + kBwdKT;               // [QT]
   float* sLut = sDelta + kBwdKT;               // [lut_size]
 
   const int g = blockIdx.z, h = blockIdx.y;
   const int n0 = a.node_off[g];
   const int n = a.node_off[g + 1] - n0;
-  const int j0 = blockIdx.x * kBwdRows;
+  const int j0 = blockIdx.x * kBwdBlock;
   if (j0 >= n) return;
   const int ld = (n + 15) & ~15;
   const int C = a.hid, C3 = 3 * C;
@@ -326,80 +332,85 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kern
   const T* dout = (const T*)a.d_out + (int64_t)n0 * C;
   const uint16_t* pair = a.pair + a.mat_off[g];
   const float scale = rsqrtf((float)D);
+  const bool single = n <= kBwdKT;
+  // pair[i][j] = spd_ij * V + spd_ji, so the column j of the bias is row j of `pair` with its two digits swapped
+  int V = 1;
+  while (V * V < a.lut_size) ++V;
 
-  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
-
-  float k[kBwdPerWarp][D], v[kBwdPerWarp][D], dk[kBwdPerWarp][D], dv[kBwdPerWarp][D];
-  int kj[kBwdPerWarp];
-#pragma unroll
-  for (int t = 0; t < kBwdPerWarp; ++t) {
-    kj[t] = j0 + warp * kBwdPerWarp + t;
-    const bool ok = kj[t] < n;
-    const int64_t r = ok ? kj[t] : 0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      k[t][d] = ok ? to_float(qkv[r * C3 + C + h * D + d]) : 0.f;
-      v[t][d] = ok ? to_float(qkv[r * C3 + 2 * C + h * D + d]) : 0.f;
-      dk[t][d] = 0.f;
-      dv[t][d] = 0.f;
-    }
-  }
-
-  for (int i0 = 0; i0 < n; i0 += kBwdKT) {
-    const int it = min(kBwdKT, n - i0);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < it * D; idx += blockDim.x) {
-      const int i = idx / D, d = idx - i * D;
-      sQ[i * DP + d] = to_float(qkv[(int64_t)(i0 + i) * C3 + h * D + d]) * scale;
-      sdO[i * DP + d] = to_float(dout[(int64_t)(i0 + i) * C + h * D + d]);
-    }
+  auto load_queries = [&](int i0, int it) {
+    bwd_load_tile<T, D>(sQ, sdO, qkv + (int64_t)i0 * C3 + h * D, dout + (int64_t)i0 * C + h * D, C3, C, it, scale);
     for (int i = threadIdx.x; i < it; i += blockDim.x) {
       sLse[i] = a.lse[(int64_t)h * a.total_nodes + n0 + i0 + i];
       sDelta[i] = a.delta[(int64_t)h * a.total_nodes + n0 + i0 + i];
     }
-    for (int idx = threadIdx.x; idx < kBwdKT * kBwdRows; idx += blockDim.x) {
-      const int i = idx / kBwdRows, r = idx - i * kBwdRows;       // kBwdRows consecutive threads read contiguous bytes
-      float b = 0.f;
-      if (i < it && j0 + r < n) b = sLut[pair[(int64_t)(i0 + i) * ld + j0 + r]];
-      sBias[r * kBwdKT + i] = b;
+  };
+
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
+  if (single) load_queries(0, n);
+  __syncthreads();
+
+  float* myBias = sBias + warp * kBwdKT;
+  for (int r = 0; r < kBwdBlock / kBwdWarps; ++r) {
+    const int kj = j0 + r * kBwdWarps + warp;
+    const bool ok = kj < n;
+    if (single && !ok) continue;
+    float k[D], v[D], dk[D], dv[D];
+    {
+      const int64_t row = ok ? kj : 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        k[d] = ok ? to_float(qkv[row * C3 + C + h * D + d]) : 0.f;
+        v[d] = ok ? to_float(qkv[row * C3 + 2 * C + h * D + d]) : 0.f;
+        dk[d] = 0.f;
+        dv[d] = 0.f;
+      }
     }
-    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kBwdKT) {
+      const int it = min(kBwdKT, n - i0);
+      if (!single) {
+        __syncthreads();
+        load_queries(i0, it);
+      }
+      if (ok) {
+        for (int i = lane; i < it; i += 32) {
+          const int pt = pair[(int64_t)kj * ld + i0 + i];          // = spd_ji * V + spd_ij
+          myBias[i] = sLut[(pt % V) * V + pt / V];
+        }
+      }
+      if (!single) __syncthreads(); else __syncwarp();
+      if (ok) {
+#pragma unroll 2
+        for (int u = 0; u < U; ++u) {
+          const int i = lane + 32 * u;
+          if (i < it) {
+            float s_ = myBias[i], dp = 0.f;
 #pragma unroll
-    for (int t = 0; t < kBwdPerWarp; ++t) {
-      if (kj[t] >= n) continue;
-      const int r = warp * kBwdPerWarp + t;
+            for (int d = 0; d < D; ++d) {
+              s_ = fmaf(sQ[i * DP + d], k[d], s_);
+              dp = fmaf(sdO[i * DP + d], v[d], dp);
+            }
+            const float p = __expf(s_ - sLse[i]);
+            const float ds = p * (dp - sDelta[i]);
 #pragma unroll
-      for (int u = 0; u < kBwdKT / 32; ++u) {
-        const int i = lane + 32 * u;
-        if (i < it) {
-          float s = sBias[r * kBwdKT + i], dp = 0.f;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            s = fmaf(sQ[i * DP + d], k[t][d], s);
-            dp = fmaf(sdO[i * DP + d], v[t][d], dp);
-          }
-          const float p = __expf(s - sLse[i]);
-          const float ds = p * (dp - sDelta[i]);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            dv[t][d] = fmaf(p, sdO[i * DP + d], dv[t][d]);
-            dk[t][d] = fmaf(ds, sQ[i * DP + d], dk[t][d]);       // sQ already carries d^-1/2
+            for (int d = 0; d < D; ++d) {
+              dv[d] = fmaf(p, sdO[i * DP + d], dv[d]);
+              dk[d] = fmaf(ds, sQ[i * DP + d], dk[d]);             // sQ already carries d^-1/2
+            }
           }
         }
       }
+      __syncwarp();
     }
-  }
+    if (ok) {
+      T* dst = (T*)a.d_qkv + (int64_t)(n0 + kj) * C3 + h * D;
 #pragma unroll
-  for (int t = 0; t < kBwdPerWarp; ++t) {
-    if (kj[t] >= n) continue;
-    T* dst = (T*)a.d_qkv + (int64_t)(n0 + kj[t]) * C3 + h * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float vk = warp_sum(dk[t][d]);
-      const float vv = warp_sum(dv[t][d]);
-      if (lane == 0) {
-        dst[C + d] = from_float<T>(vk);
-        dst[2 * C + d] = from_float<T>(vv);
+      for (int d = 0; d < D; ++d) {
+        const float vk = warp_sum(dk[d]);
+        const float vv = warp_sum(dv[d]);
+        if (lane == 0) {
+          dst[C + d] = from_float<T>(vk);
+          dst[2 * C + d] = from_float<T>(vv);
+        }
       }
     }
   }
@@ -408,13 +419,13 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kern
 template <typename T, int D>
 static int launch_attention_bwd(const ghn3_attention_bwd_args* a, cudaStream_t stream) {
   constexpr int DP = D + 1;
-  const size_t smem_a = sizeof(float) * (2 * kBwdKT * DP + kBwdRows * kBwdKT + 2 * a->lut_size) +
-                        sizeof(uint16_t) * kBwdRows * kBwdKT;
-  const size_t smem_b = sizeof(float) * (2 * kBwdKT * DP + kBwdRows * kBwdKT + 2 * kBwdKT + a->lut_size);
+  const size_t smem_a = sizeof(float) * (2 * kBwdKT * DP + kBwdWarps * kBwdKT + 2 * a->lut_size) +
+                        sizeof(uint16_t) * kBwdWarps * kBwdKT;
+  const size_t smem_b = sizeof(float) * (2 * kBwdKT * DP + kBwdWarps * kBwdKT + 2 * kBwdKT + a->lut_size);
   GHN3_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "ghn3_attention_bwd: look-up table too large");
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-  const dim3 grid((unsigned)ceil_div(a->max_nodes, kBwdRows), (unsigned)a->heads, (unsigned)a->n_graphs);
+  const dim3 grid((unsigned)ceil_div(a->max_nodes, kBwdBlock), (unsigned)a->heads, (unsigned)a->n_graphs);
   attention_bwd_dq_kernel<T, D><<<grid, 256, smem_a, stream>>>(*a);
   GHN3_LAUNCH_CHECK("attention_bwd_dq_kernel");
   attention_bwd_dkv_kernel<T, D><<<grid, 256, smem_b, stream>>>(*a);

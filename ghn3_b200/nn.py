@@ -203,6 +203,16 @@ class GHN3(GHN):
             self.__dict__['_param_list'] = plist
         return tuple([p._version for p in plist]), self.compute_dtype
 
+    def train(self, mode=True):
+        # Tensor version counters do not see every in-place update (fused optimizers -- torch.optim.AdamW(fused=True)
+        # -- leave them untouched), so switching mode, like every keep_grads forward, marks the device copies stale.
+        self.__dict__['_dev_dirty'] = True
+        return super().train(mode)
+
+    def weights_updated(self):
+        """Call after changing parameter values through a path that does not bump tensor versions."""
+        self.__dict__['_dev_dirty'] = True
+
     def _apply(self, fn, *args, **kwargs):                 # .to() / .cuda() / .float(): parameters may be replaced
         self.__dict__['_param_list'] = None
         self._dev = None
@@ -217,8 +227,10 @@ class GHN3(GHN):
         """Device copies of the weights in the compute dtype. Built once; when the parameters change IN PLACE
         (optimizer step, load_state_dict) the same buffers are refreshed, so prebuilt programs stay valid."""
         sig = self._weights_signature()
-        if self._dev is not None and self._dev['sig'] == sig:
+        dirty = self.__dict__.get('_dev_dirty', False)
+        if self._dev is not None and self._dev['sig'] == sig and not dirty:
             return self._dev
+        self.__dict__['_dev_dirty'] = False
         dev = self.embed.weight.device
         if dev.type != 'cuda':
             raise RuntimeError('ghn3_b200: the GHN must be on a CUDA device (got %s); there is no CPU path' % dev)
@@ -329,9 +341,12 @@ class GHN3(GHN):
             graphs.to_device(device)
         assert len(graphs) == len(nets), 'number of graphs and networks must match'
 
+        if keep_grads:                     # a training step: the optimizer has (probably) just moved the weights
+            self.__dict__['_dev_dirty'] = True
         w = self._device_weights()
         bp = self._batch_plan(graphs, nets, predict_class_layers, reduce_graph)
         if keep_grads:
+            self.__dict__['_dev_dirty'] = True
             from .train import forward_keep_grads
             emb = forward_keep_grads(self, nets, graphs, w, bp, return_embeddings)
         else:

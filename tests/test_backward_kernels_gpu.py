@@ -126,13 +126,16 @@ def test_layernorm_bwd_row_gather():
     assert _rel(dx, x.grad) < 2e-4 and _rel(dg, gamma.grad) < 1e-4 and _rel(db, beta.grad) < 1e-4
 
 
-@pytest.mark.parametrize('cfg_name', ['ghn3tiny', 'ghn3tm8', 'ghn3lm8', 'ghn3xlm16'])
+@pytest.mark.parametrize('cfg_name,archs', [('ghn3tiny', 'small'), ('ghn3tm8', 'small'), ('ghn3lm8', 'small'),
+                                            ('ghn3xlm16', 'small'), ('ghn3xlm16', 'large'), ('ghn3tiny', 'large')])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_attention_bwd(cfg_name, dtype):
+def test_attention_bwd(cfg_name, archs, dtype):
     cfg = CONFIGS[cfg_name]
     C_, H_ = cfg['hid'], cfg['heads']
     D = C_ // H_
-    archs = ['resnet18', 'squeezenet1_0', 'mobilenet_v3_small']
+    # 'large': graphs with more nodes than one shared-memory tile (256) next to a small one
+    archs = ['resnet18', 'squeezenet1_0', 'mobilenet_v3_small'] if archs == 'small' else \
+        ['swin_v2_t', 'resnet18', 'efficientnet_b3']
     recs, pack = _pack(archs)
     torch.manual_seed(6)
     N = pack.total_nodes

@@ -131,13 +131,16 @@ def test_xl_gradients(arch, dtype):
     _run('ghn3xlm16', [arch], dtype)
 
 
-def test_second_step_after_weight_update():
-    """the device weight copies, their transposes and the LUT follow an in-place optimizer update"""
+@pytest.mark.parametrize('optimizer', ['sgd', 'adamw_fused'])
+def test_second_step_after_weight_update(optimizer):
+    """the device weight copies, their transposes and the LUT follow an in-place optimizer update -- also a fused
+    optimizer's, which does not bump tensor version counters"""
     cfg = CONFIGS['ghn3tiny']
     ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
     ghn.load_state_dict(procedural_state_dict(cfg, 0))
     ghn = ghn.to(DEV).train()
-    opt = torch.optim.SGD(ghn.parameters(), lr=1e-2)
+    opt = torch.optim.SGD(ghn.parameters(), lr=1e-2) if optimizer == 'sgd' else \
+        torch.optim.AdamW(ghn.parameters(), lr=2e-3, fused=True)
     rec = H.graph_records()['resnet18']
     graph = Graph.from_record(rec)
     losses = []
@@ -154,6 +157,16 @@ def test_second_step_after_weight_update():
         opt.step()
         losses.append(float(loss))
     assert losses[2] < losses[0], losses
+    # the prediction path sees the trained weights too: same parameters as a freshly built GHN with this state_dict
+    ghn.eval()
+    fresh = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    fresh.load_state_dict(ghn.state_dict())
+    fresh = fresh.to(DEV).eval()
+    with torch.no_grad():
+        m1 = ghn(H.build_model('resnet18').to(DEV), graph)
+        m2 = fresh(H.build_model('resnet18').to(DEV), graph)
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert H.max_rel_err(p1, p2) < 1e-4, n1          # split-K atomics: summation order is not fixed
 
 
 def test_trainer_update_reduces_loss():
