@@ -136,7 +136,8 @@ EW_COPY, EW_GELU, EW_GELU_BWD, EW_RELU_BWD, EW_ADD = 0, 1, 2, 3, 4
 
 class TransposeArgs(C.Structure):
     _fields_ = [('src', vp), ('src_dtype', i32), ('ld_src', i64), ('rows', i32), ('cols', i32), ('group', i32),
-                ('group_stride', i32), ('dst', vp), ('dst_dtype', i32), ('ld_dst', i64)]
+                ('group_stride', i32), ('dst', vp), ('dst_dtype', i32), ('ld_dst', i64), ('mul_gelu_grad', vp),
+                ('mul_dtype', i32), ('copy_out', vp), ('copy_dtype', i32), ('colsum_out', vp)]
 
 
 class ElementwiseArgs(C.Structure):

@@ -16,9 +16,16 @@ __device__ __forceinline__ void st_f(void* p, int64_t i, int dt, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dst[c][r] = src[row(r)][c]: 32 x 32 tiles through shared memory, dtype conversion on the way
+// dst[c][r] = v(r, c), v = src[row(r)][c] (* gelu'(mul[r][c])): 32 x 32 tiles through shared memory, dtype conversion
+// on the way; optionally also the un-transposed copy of v and its column sums (bias gradients)
+__device__ __forceinline__ float gelu_grad_f(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752440f)) + u * 0.39894228040143267794f * __expf(-0.5f * u * u);
+}
+
 __global__ void __launch_bounds__(256) transpose_kernel(const ghn3_transpose_args a) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -28,6 +35,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const ghn3_transpose_arg
     if (r < a.rows && c < a.cols) {
       const int64_t sr = a.group > 0 ? (int64_t)(r / a.group) * a.group_stride + r % a.group : r;
       v = ld_f(a.src, sr * a.ld_src + c, a.src_dtype);
+      if (a.mul_gelu_grad != nullptr) v *= gelu_grad_f(ld_f(a.mul_gelu_grad, (int64_t)r * a.cols + c, a.mul_dtype));
+      if (a.copy_out != nullptr) st_f(a.copy_out, (int64_t)r * a.cols + c, a.copy_dtype, v);
     }
     tile[ty + 8 * i][tx] = v;
   }
@@ -37,15 +46,21 @@ __global__ void __launch_bounds__(256) transpose_kernel(const ghn3_transpose_arg
     const int c = c0 + ty + 8 * i, r = r0 + tx;
     if (c < a.cols && r < a.rows) st_f(a.dst, (int64_t)c * a.ld_dst + r, a.dst_dtype, tile[tx][ty + 8 * i]);
   }
+  if (a.colsum_out != nullptr && ty == 0 && c0 + tx < a.cols) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) t += tile[r][tx];
+    if (t != 0.f) atomicAdd(a.colsum_out + c0 + tx, t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752440f)); }
-__device__ __forceinline__ float gelu_grad(float u) {
-  return 0.5f * (1.f + erff(u * 0.70710678118654752440f)) + u * 0.39894228040143267794f * __expf(-0.5f * u * u);
-}
+__device__ __forceinline__ float gelu_grad(float u) { return gelu_grad_f(u); }
 
 __global__ void __launch_bounds__(256) elementwise_kernel(const ghn3_elementwise_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     float v;
     switch (a.op) {
@@ -63,6 +78,8 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const ghn3_elementwise
 // dst[col(c)] += sum_r src[r][c]
 __global__ void __launch_bounds__(256) colsum_kernel(const ghn3_colsum_args a) {
   __shared__ float part[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   const int r0 = blockIdx.y * 256;
@@ -90,7 +107,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
   const int C = a.hid;
   float* sG = ln_smem;
   float* sB = ln_smem + C;
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ln_smem[i] = 0.f;
+  pdl_wait();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invC = 1.f / (float)C;
@@ -200,10 +219,12 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kerne
   const float scale = rsqrtf((float)D);
   const bool single = n <= kBwdKT;             // block-uniform
 
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) {
     sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
     sHist[i] = 0.f;
   }
+  pdl_wait();
   if (single) bwd_load_tile<T, D>(sK, sV, qkv + C + h * D, qkv + 2 * C + h * D, C3, C3, n, 1.f);
   __syncthreads();
 
@@ -345,7 +366,9 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kern
     }
   };
 
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
+  pdl_wait();
   if (single) load_queries(0, n);
   __syncthreads();
 
@@ -426,9 +449,9 @@ static int launch_attention_bwd(const ghn3_attention_bwd_args* a, cudaStream_t s
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   const dim3 grid((unsigned)ceil_div(a->max_nodes, kBwdBlock), (unsigned)a->heads, (unsigned)a->n_graphs);
-  attention_bwd_dq_kernel<T, D><<<grid, 256, smem_a, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(attention_bwd_dq_kernel<T, D>, grid, dim3(256), smem_a, stream, *a));
   GHN3_LAUNCH_CHECK("attention_bwd_dq_kernel");
-  attention_bwd_dkv_kernel<T, D><<<grid, 256, smem_b, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(attention_bwd_dkv_kernel<T, D>, grid, dim3(256), smem_b, stream, *a));
   GHN3_LAUNCH_CHECK("attention_bwd_dkv_kernel");
   return GHN3_OK;
 }
@@ -782,7 +805,7 @@ extern "C" int ghn3_transpose(const ghn3_transpose_args* a, ghn3_stream_t stream
   GHN3_REQUIRE(a->ld_dst >= a->rows && a->ld_src >= a->cols, "ghn3_transpose: leading dimensions too small");
   const dim3 grid((unsigned)ceil_div(a->cols, 32), (unsigned)ceil_div(a->rows, 32));
   GHN3_REQUIRE(grid.y < 65536, "ghn3_transpose: too many rows");
-  transpose_kernel<<<grid, 256, 0, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(transpose_kernel, grid, dim3(256), 0, stream, *a));
   GHN3_LAUNCH_CHECK("transpose_kernel");
   return GHN3_OK;
 }
@@ -794,7 +817,7 @@ extern "C" int ghn3_elementwise(const ghn3_elementwise_args* a, ghn3_stream_t st
   GHN3_REQUIRE(a->op == GHN3_EW_COPY || a->op == GHN3_EW_GELU || a->b != nullptr, "ghn3_elementwise: second operand missing");
   if (a->n <= 0) return GHN3_OK;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->n, 256), (int64_t)num_sms() * 16);
-  elementwise_kernel<<<blocks, 256, 0, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(elementwise_kernel, dim3(blocks), dim3(256), 0, stream, *a));
   GHN3_LAUNCH_CHECK("elementwise_kernel");
   return GHN3_OK;
 }
@@ -805,7 +828,7 @@ extern "C" int ghn3_colsum(const ghn3_colsum_args* a, ghn3_stream_t stream_) {
   if (a->rows <= 0 || a->cols <= 0) return GHN3_OK;
   const dim3 grid((unsigned)ceil_div(a->cols, 32), (unsigned)ceil_div(a->rows, 256));
   GHN3_REQUIRE(grid.y < 65536, "ghn3_colsum: too many rows");
-  colsum_kernel<<<grid, 256, 0, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, *a));
   GHN3_LAUNCH_CHECK("colsum_kernel");
   return GHN3_OK;
 }
@@ -817,7 +840,7 @@ extern "C" int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* a, ghn3_stream_
   GHN3_REQUIRE(a->x && a->gamma && a->dy && a->dx && a->dgamma && a->dbeta, "ghn3_layernorm_bwd: null pointer");
   if (a->rows <= 0) return GHN3_OK;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 8), (int64_t)num_sms() * 2);
-  layernorm_bwd_kernel<<<blocks, 256, sizeof(float) * 2 * a->hid, stream>>>(*a);
+  GHN3_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), sizeof(float) * 2 * a->hid, stream, *a));
   GHN3_LAUNCH_CHECK("layernorm_bwd_kernel");
   return GHN3_OK;
 }

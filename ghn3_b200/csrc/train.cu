@@ -45,11 +45,16 @@ ghn3_gemm_args mm(const Ctx& c, const void* a, int64_t m, int64_t lda, const voi
   return g;
 }
 
-int transpose_to(const Ctx& c, const void* src, int src_dtype, int rows, int cols, void* dst, int64_t ld_dst) {
+// dst = v^T, optionally with the activation-dtype copy of v, its column sums, and v = src * gelu'(u)
+int transpose_to(const Ctx& c, const void* src, int src_dtype, int rows, int cols, void* dst, int64_t ld_dst,
+                 void* copy_out = nullptr, float* colsum_out = nullptr, const void* gelu_u = nullptr) {
   ghn3_transpose_args t = {};
   t.src = src; t.src_dtype = src_dtype; t.ld_src = cols;
   t.rows = rows; t.cols = cols;
   t.dst = dst; t.dst_dtype = c.act_dt; t.ld_dst = ld_dst;
+  t.mul_gelu_grad = gelu_u; t.mul_dtype = c.act_dt;
+  t.copy_out = copy_out; t.copy_dtype = c.act_dt;
+  t.colsum_out = colsum_out;
   return ghn3_transpose(&t, (ghn3_stream_t)c.stream);
 }
 
@@ -179,9 +184,7 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
     const void* g = at((const void*)t->g, l, 4 * C, c);
 
     // ---- FFN2: xn = xm + g W2^T + b2 ----
-    GHN3_TRY(ew(c, GHN3_EW_COPY, (int64_t)M * C, b->dx, GHN3_F32, nullptr, 0, b->dxa, adt));
-    GHN3_TRY(colsum_to(c, b->dx, GHN3_F32, M, C, gr.b_ff2));
-    GHN3_TRY(transpose_to(c, b->dx, GHN3_F32, M, C, b->ta, mp));
+    GHN3_TRY(transpose_to(c, b->dx, GHN3_F32, M, C, b->ta, mp, b->dxa, gr.b_ff2));     // dx^T, act copy, bias grad
     GHN3_TRY(transpose_to(c, g, adt, M, 4 * C, b->tb, mp));
     {
       ghn3_gemm_args wg = mm(c, b->ta, C, mp, b->tb, 4 * C, mp, M, nullptr, gr.w_ff2, GHN3_F32, 1, 1);
@@ -190,9 +193,8 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
       GHN3_TRY(gemm_impl(&dg, stream));
     }
     // ---- GELU, FFN1: u = h2 W1^T + b1 ----
-    GHN3_TRY(ew(c, GHN3_EW_GELU_BWD, (int64_t)M * 4 * C, b->dff, adt, u, adt, b->dff, adt));
-    GHN3_TRY(colsum_to(c, b->dff, adt, M, 4 * C, gr.b_ff1));
-    GHN3_TRY(transpose_to(c, b->dff, adt, M, 4 * C, b->ta, mp));
+    // du = dg * gelu'(u) written back in place, du^T and the bias gradient in the same pass
+    GHN3_TRY(transpose_to(c, b->dff, adt, M, 4 * C, b->ta, mp, b->dff, gr.b_ff1, u));
     GHN3_TRY(transpose_to(c, h2, adt, M, C, b->tb, mp));
     {
       ghn3_gemm_args wg = mm(c, b->ta, 4 * C, mp, b->tb, C, mp, M, nullptr, gr.w_ff1, GHN3_F32, 1, 1);
@@ -207,9 +209,7 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
       GHN3_TRY(ghn3_layernorm_bwd(&lb, s_));
     }
     // ---- attention output projection: xm = x + ao Wo^T + bo ----
-    GHN3_TRY(ew(c, GHN3_EW_COPY, (int64_t)M * C, b->dx, GHN3_F32, nullptr, 0, b->dxa, adt));
-    GHN3_TRY(colsum_to(c, b->dx, GHN3_F32, M, C, gr.b_out));
-    GHN3_TRY(transpose_to(c, b->dx, GHN3_F32, M, C, b->ta, mp));
+    GHN3_TRY(transpose_to(c, b->dx, GHN3_F32, M, C, b->ta, mp, b->dxa, gr.b_out));
     GHN3_TRY(transpose_to(c, ao, adt, M, C, b->tb, mp));
     {
       ghn3_gemm_args wg = mm(c, b->ta, C, mp, b->tb, C, mp, M, nullptr, gr.w_out, GHN3_F32, 1, 1);

@@ -377,6 +377,10 @@ typedef struct {
   int32_t rows, cols;
   int32_t group, group_stride;
   void* dst; int32_t dst_dtype; int64_t ld_dst;
+  /* optional fused extras; v(r, c) below is the value that gets transposed */
+  const void* mul_gelu_grad; int32_t mul_dtype;  /* v = src * gelu'(mul_gelu_grad[r][c]) (dense [rows][cols]); NULL: v = src */
+  void* copy_out; int32_t copy_dtype;            /* un-transposed dense [rows][cols] copy of v (may alias src) */
+  float* colsum_out;                             /* colsum_out[c] += sum_r v(r, c) */
 } ghn3_transpose_args;
 int ghn3_transpose(const ghn3_transpose_args* args, ghn3_stream_t stream);
 
