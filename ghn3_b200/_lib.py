@@ -198,6 +198,13 @@ class ExpandArgs(C.Structure):
                 ('ld_x', i64), ('xt', vp), ('ld_xt', i64), ('dtype', i32), ('d_bias', vp)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [('params', vp), ('grads', vp), ('exp_avg', vp), ('exp_avg_sq', vp), ('offsets', vp), ('numels', vp),
+                ('chunk0', vp), ('chunk_tensor', vp), ('n_chunks', i64), ('total', i64), ('lr', f32), ('beta1', f32),
+                ('beta2', f32), ('eps', f32), ('weight_decay', f32), ('bias_correction1', f32),
+                ('bias_correction2', f32), ('max_norm', f32), ('sumsq', vp)]
+
+
 class MemsetArgs(C.Structure):
     _fields_ = [('ptr', vp), ('bytes', i64)]
 
@@ -230,7 +237,7 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
-                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols']
+                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw']
 SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None

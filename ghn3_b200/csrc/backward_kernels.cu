@@ -794,6 +794,84 @@ __global__ void __launch_bounds__(256) expand_kernel(const ghn3_expand_args a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer step of the training path: global-norm gradient clipping + decoupled-weight-decay Adam (AdamW) in ONE
+// pass over the flat gradient buffer (reference: nn.utils.clip_grad_norm_ + torch.optim.AdamW.step, trainer.py:
+// 343-379). Gradients and both moment buffers are flat (same layout); parameters stay separate tensors and are
+// reached through a pointer table. The clipping coefficient is computed on the device from the squared norm.
+__global__ void __launch_bounds__(256) sumsq_flat_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ((const float4*)g)[i];
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    acc += v * v;
+  }
+  double d = (double)warp_sum(acc);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(const ghn3_adamw_args a) {
+  const int t = a.chunk_tensor[blockIdx.x];
+  const int64_t off = a.offsets[t];
+  const int64_t n = a.numels[t];
+  const int64_t c0 = ((int64_t)blockIdx.x - a.chunk0[t]) * GHN3_ADAMW_CHUNK;
+  const int64_t c1 = min(c0 + (int64_t)GHN3_ADAMW_CHUNK, n);
+  float* __restrict__ p = a.params[t];
+  const float* __restrict__ g = a.grads + off;
+  float* __restrict__ m = a.exp_avg + off;
+  float* __restrict__ v = a.exp_avg_sq + off;
+  float coef = 1.f;
+  if (a.max_norm > 0.f) {
+    const float norm = sqrtf((float)*a.sumsq);
+    coef = fminf(1.f, a.max_norm / (norm + 1e-6f));        // nn.utils.clip_grad_norm_
+  }
+  const float b1 = a.beta1, b2 = a.beta2;
+  const float decay = 1.f - a.lr * a.weight_decay;
+  const float step_size = a.lr / a.bias_correction1;
+  const float inv_bc2_sqrt = rsqrtf(a.bias_correction2);
+  const bool vec = (((uintptr_t)p) & 15) == 0;             // flat buffers are 16-byte aligned per tensor
+  if (vec) {
+    for (int64_t i = c0 + threadIdx.x * 4; i + 4 <= c1; i += 1024) {
+      float4 pv = *(float4*)(p + i);
+      const float4 gv = *(const float4*)(g + i);
+      float4 mv = *(float4*)(m + i), vv = *(float4*)(v + i);
+      float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = gp[k] * coef;
+        mp[k] = b1 * mp[k] + (1.f - b1) * gr;
+        vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+        const float denom = sqrtf(vp[k]) * inv_bc2_sqrt + a.eps;
+        pp[k] = pp[k] * decay - step_size * (mp[k] / denom);
+      }
+      *(float4*)(p + i) = pv;
+      *(float4*)(m + i) = mv;
+      *(float4*)(v + i) = vv;
+    }
+  }
+  // tail (or everything, for an unaligned parameter)
+  const int64_t t0 = vec ? c0 + ((c1 - c0) & ~(int64_t)3) : c0;
+  for (int64_t i = t0 + threadIdx.x; i < c1; i += 256) {
+    const float gr = g[i] * coef;
+    const float mm = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mm;
+    v[i] = vv;
+    p[i] = p[i] * decay - step_size * (mm / (sqrtf(vv) * inv_bc2_sqrt + a.eps));
+  }
+}
+
 }  // namespace ghn3
 
 using namespace ghn3;
@@ -932,5 +1010,23 @@ extern "C" int ghn3_expand_cols(const ghn3_expand_args* a, ghn3_stream_t stream_
   GHN3_REQUIRE(a->segs && a->src && a->x && a->xt, "ghn3_expand_cols: null pointer");
   expand_kernel<<<(unsigned)a->n_tiles, 256, 0, stream>>>(*a);
   GHN3_LAUNCH_CHECK("expand_kernel");
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_adamw(const ghn3_adamw_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_adamw: null args");
+  if (a->n_chunks <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->offsets && a->numels && a->chunk0 &&
+                   a->chunk_tensor, "ghn3_adamw: null pointer");
+  GHN3_REQUIRE(a->bias_correction1 > 0.f && a->bias_correction2 > 0.f, "ghn3_adamw: bias corrections must be positive");
+  if (a->max_norm > 0.f) {
+    GHN3_REQUIRE(a->sumsq != nullptr, "ghn3_adamw: max_norm > 0 needs the sumsq scratch double");
+    GHN3_CUDA(cudaMemsetAsync(a->sumsq, 0, sizeof(double), stream));
+    sumsq_flat_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(a->grads, a->total, a->sumsq);
+    GHN3_LAUNCH_CHECK("sumsq_flat_kernel");
+  }
+  adamw_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(*a);
+  GHN3_LAUNCH_CHECK("adamw_kernel");
   return GHN3_OK;
 }

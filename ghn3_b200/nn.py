@@ -239,8 +239,7 @@ class GHN3(GHN):
         self.fix_embed_layers()
         if self._dev is not None and self._dev['compute_dtype'] == self.compute_dtype and self._dev['ptrs'] == \
                 [p.data_ptr() for p in self._param_list]:
-            for fn in self._dev['refresh']:
-                fn()
+            self._run_refresh(self._dev)
             self._dev['sig'] = sig
             return self._dev
         dt, x3 = DTYPES[self.compute_dtype]
@@ -256,16 +255,25 @@ class GHN3(GHN):
             refresh.append(lambda: buf.copy_(p.detach()))
             return buf
 
+        refresh_ops = []                                   # (entry point, args): replayed by ONE ghn3_run_sequence call
+
         def cv(p):
             if x3:                                         # x3 keeps the fp32 master weights
                 return f(p)
-            buf = ops.convert(f(p), dt)
-            refresh.append(lambda: ops.convert(p.detach().float().contiguous(), dt, out=buf))
+            src = f(p)
+            buf = ops.convert(src, dt)
+            if src.data_ptr() == p.data_ptr():             # aliasing fp32 parameter: a prebuilt conversion op
+                refresh_ops.append(('elementwise', L.ElementwiseArgs(op=L.EW_COPY, n=src.numel(), a=src.data_ptr(),
+                                                                     a_dtype=ops.F32, b=None, b_dtype=0,
+                                                                     out=buf.data_ptr(), out_dtype=dt)))
+            else:
+                refresh.append(lambda: ops.convert(p.detach().float().contiguous(), dt, out=buf))
             return buf
 
         g0 = self.gnn[0]
         w = {'sig': sig, 'dtype': dt, 'x3': x3, 'act': ops.F32 if x3 else dt, 'compute_dtype': self.compute_dtype,
-             'ptrs': [p.data_ptr() for p in self._param_list], 'refresh': refresh}
+             'ptrs': [p.data_ptr() for p in self._param_list], 'refresh': refresh, 'refresh_ops': refresh_ops,
+             'refresh_seq': None}
         w['tables'] = {'embed_op': f(self.embed.weight), 'embed_ch': f(self.shape_enc.embed_channel.weight),
                        'embed_sp': f(self.shape_enc.embed_spatial.weight),
                        'cent_in': f(g0.centrality_embed_in.weight), 'cent_out': f(g0.centrality_embed_out.weight),
@@ -311,6 +319,24 @@ class GHN3(GHN):
         w['bc_w'], w['bc_b'] = f(self.bias_class[1].weight), f(self.bias_class[1].bias)
         self._dev = w
         return w
+
+    _REFRESH_OPC = {'elementwise': 10, 'transpose': 9}
+
+    def _run_refresh(self, w):
+        """Re-derives every device copy from the current parameter values (same buffers, same addresses)."""
+        ops_ = w['refresh_ops']
+        if ops_:
+            seq = w['refresh_seq']
+            if seq is None or len(seq) != len(ops_):
+                seq = (L.SeqOp * len(ops_))()
+                for i, (name, args) in enumerate(ops_):
+                    seq[i].op = self._REFRESH_OPC[name]
+                    seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
+                w['refresh_seq'] = seq
+            L.check(L.load().ghn3_run_sequence(seq, len(ops_), ct.c_void_p(L.current_stream())),
+                    'ghn3_run_sequence (weight refresh)')
+        for fn in w['refresh']:
+            fn()
 
     def _lut(self, w, vmax):
         if vmax not in self._lut_cache:

@@ -1,0 +1,92 @@
+"""
+Optimizer of the training path: global-norm gradient clipping + AdamW in one kernel pass (ghn3_adamw) over the flat
+gradient buffer the hand-written backward pass produces. Replaces `nn.utils.clip_grad_norm_` +
+`torch.optim.AdamW.step` of the reference's `Trainer.update` (ghn3/trainer.py:343-379): no per-tensor norm kernels, no
+host synchronisation, 7 HBM passes over the parameters' bytes instead of ~12.
+"""
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .train import flat_layout
+
+CHUNK = 8192
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, ghn, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
+        params, order, offs, _ = flat_layout(ghn)
+        super().__init__(order, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                     max_grad_norm=max_grad_norm))
+        dev = order[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('ghn3_b200.FusedAdamW: the GHN must be on a CUDA device')
+        for p in order:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError('ghn3_b200.FusedAdamW: parameters must be contiguous fp32 tensors')
+        self._order, self._offs, self._dev = order, offs, dev
+        total = int(offs[-1])
+        self._total = total
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._own_grads = None
+        numels = np.array([p.numel() for p in order], dtype=np.int64)
+        chunks = (numels + CHUNK - 1) // CHUNK
+        chunk0 = np.concatenate([[0], np.cumsum(chunks)[:-1]]).astype(np.int64)
+        self._n_chunks = int(chunks.sum())
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self._tables = dict(offsets=to_dev(offs[:-1]), numels=to_dev(numels), chunk0=to_dev(chunk0),
+                            chunk_tensor=to_dev(np.repeat(np.arange(len(order), dtype=np.int32), chunks)))
+        self._ptrs_host, self._ptrs = None, None
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._step = 0
+
+    def _param_table(self):
+        ptrs = [p.data_ptr() for p in self._order]
+        if ptrs != self._ptrs_host:
+            self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self._dev)
+            self._ptrs_host = ptrs
+        return self._ptrs
+
+    def _flat_grads(self):
+        """The flat gradient buffer: the backward pass's own buffer when every p.grad is still the view it handed
+        out (the normal case, zero copies); otherwise the gradients are gathered into a private flat buffer."""
+        g0 = self._order[0].grad
+        if g0 is not None:
+            base = g0.data_ptr()
+            if all(p.grad is not None and p.grad.data_ptr() == base + int(o) * 4 and p.grad.is_contiguous()
+                   for p, o in zip(self._order, self._offs[:-1])):
+                return base, None
+        if self._own_grads is None:
+            self._own_grads = torch.zeros(self._total, dtype=torch.float32, device=self._dev)
+        flat = self._own_grads
+        flat.zero_()
+        views = [flat[int(o):int(o) + p.numel()].view(p.shape) for p, o in zip(self._order, self._offs[:-1])]
+        have = [(v, p.grad) for v, p in zip(views, self._order) if p.grad is not None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        return flat.data_ptr(), flat
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        self._step += 1
+        b1, b2 = g['betas']
+        base, keep = self._flat_grads()
+        t = self._tables
+        a = L.AdamWArgs(params=self._param_table().data_ptr(), grads=base, exp_avg=self.exp_avg.data_ptr(),
+                        exp_avg_sq=self.exp_avg_sq.data_ptr(), offsets=t['offsets'].data_ptr(),
+                        numels=t['numels'].data_ptr(), chunk0=t['chunk0'].data_ptr(),
+                        chunk_tensor=t['chunk_tensor'].data_ptr(), n_chunks=self._n_chunks, total=self._total,
+                        lr=g['lr'], beta1=b1, beta2=b2, eps=g['eps'], weight_decay=g['weight_decay'],
+                        bias_correction1=1.0 - b1 ** self._step, bias_correction2=1.0 - b2 ** self._step,
+                        max_norm=float(g['max_grad_norm'] or 0.0), sumsq=self._sumsq.data_ptr())
+        L.call('adamw', a, L.current_stream())
+        return loss
+
+    def grad_norm(self):
+        """Global gradient norm seen by the last step (device tensor, float64) when clipping is enabled."""
+        return self._sumsq.sqrt()

@@ -36,10 +36,14 @@ def transposed_weights(ghn, w):
     act = w['act']
 
     def T(t):
-        """[cols, rows] view of a buffer whose row stride is padded to 8 elements; refreshed with the weights."""
+        """[cols, rows] view of a buffer whose row stride is padded to 8 elements; refreshed with the weights (the
+        transposes are appended AFTER the conversions in the prebuilt refresh sequence)."""
         view = ops.transpose(t, dst_dtype=act)
         base = view._base if view._base is not None else view
-        w['refresh'].append(lambda: ops.transpose(t, dst_dtype=act, out=base))
+        w['refresh_ops'].append(('transpose', L.TransposeArgs(
+            src=t.data_ptr(), src_dtype=ops.BF16 if t.dtype == torch.bfloat16 else ops.F32, ld_src=t.stride(0),
+            rows=t.shape[0], cols=t.shape[1], group=0, group_stride=0, dst=base.data_ptr(), dst_dtype=act,
+            ld_dst=base.stride(0))))
         return view
     layers = (L.LayerWeightsT * ghn.layers)()
     keep = []
@@ -52,6 +56,18 @@ def transposed_weights(ghn, w):
           'd1_w1T': T(w['d1_w1']), 'cls_wT': T(w['cls_w'])}
     w['T'] = wt
     return wt
+
+
+def flat_layout(ghn):
+    """Order and offsets of the GHN parameters in the flat fp32 gradient buffer: [decoder, decoder_1d, bias_class |
+    everything else], every tensor starting at a multiple of 4 elements. The first region is final as soon as the
+    decoder adjoint has run, so its all-reduce (93% of the bytes at XL) overlaps the Graphormer adjoint.
+    Returns (params in module order, params in buffer order, offsets [n+1], elements of the first region)."""
+    params = list(ghn.parameters())
+    early = {id(p) for m in (ghn.decoder, ghn.decoder_1d, ghn.bias_class) for p in m.parameters()}
+    order = [p for p in params if id(p) in early] + [p for p in params if id(p) not in early]
+    offs = np.concatenate([[0], np.cumsum([(p.numel() + 3) // 4 * 4 for p in order])]).astype(np.int64)
+    return params, order, offs, int(offs[sum(1 for p in order if id(p) in early)])
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -76,17 +92,11 @@ class _Backward:
         E = lambda *shape, dtype=adt: torch.empty(*shape, dtype=dtype, device=dev)
 
         # ---- fp32 gradient of every GHN parameter: one flat buffer, views per parameter ----
-        # Layout: [decoder, decoder_1d, bias_class | everything else]. The first region is final as soon as the
-        # decoder adjoint has run, so its all-reduce (93% of the bytes at XL) overlaps the Graphormer adjoint.
-        params = list(ghn.parameters())
-        early = {id(p) for m in (ghn.decoder, ghn.decoder_1d, ghn.bias_class) for p in m.parameters()}
-        order = [p for p in params if id(p) in early] + [p for p in params if id(p) not in early]
-        offs = np.concatenate([[0], np.cumsum([(p.numel() + 3) // 4 * 4 for p in order])]).astype(np.int64)
+        params, order, offs, self.early_elems = flat_layout(ghn)
         self.params = params
         self.gflat = Z(int(offs[-1]))
         gof = {id(p): self.gflat[int(o):int(o) + p.numel()].view(p.shape) for o, p in zip(offs[:-1], order)}
         self.gviews = [gof[id(p)] for p in params]
-        self.early_elems = int(offs[sum(1 for p in order if id(p) in early)])
         G = lambda p: gof[id(p)]
         self.zero.append(self.gflat)
 
@@ -451,7 +461,7 @@ class _PredictFn(torch.autograd.Function):
         prog.step_id = getattr(prog, 'step_id', 0) + 1
         ctx.ghn, ctx.prog, ctx.out_index, ctx.step_id = ghn, prog, out_index, prog.step_id
         ctx.slices = out_meta['slices']
-        outs = tuple(pred[o:o + n].view(shape) for (o, n, shape) in out_meta['slices'])
+        outs = tuple(pred.as_strided(shape, st, o) for (o, n, shape), st in zip(out_meta['slices'], out_meta['strides']))
         return outs + (pred,)
 
     @staticmethod
@@ -489,7 +499,14 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
                 slices.append((off, n, full))
                 off += (n + 3) // 4 * 4
             index.append(keys[key])
-        meta = {'slices': slices, 'total': max(off, 4), 'desc_out': index,
+        def contiguous_strides(shape):
+            st, acc = [], 1
+            for d in reversed(shape):
+                st.append(acc)
+                acc *= d
+            return tuple(reversed(st))
+        meta = {'slices': slices, 'strides': [contiguous_strides(sh) for (_, _, sh) in slices], 'total': max(off, 4),
+                'desc_out': index,
                 'targets': [(m, a) for (m, a, _, v) in bp.desc_targets]}
         shifts = [int(s) for s in bp.desc_dst_shift]
         meta['out_index'] = [(index[i], shifts[i], bp.desc_targets[i][3] != 'tok') for i in range(len(index))]

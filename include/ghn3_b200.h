@@ -518,6 +518,25 @@ typedef struct {
 } ghn3_expand_args;
 int ghn3_expand_cols(const ghn3_expand_args* args, ghn3_stream_t stream);
 
+/* Optimizer step of the training path: global-norm clipping (nn.utils.clip_grad_norm_, trainer.py:343-349) and AdamW
+ * (decoupled weight decay, bias-corrected) in one pass. grads / exp_avg / exp_avg_sq are FLAT fp32 buffers with the
+ * same layout (tensor t at offsets[t], numels[t] elements, offsets multiples of 4); params[t] are the parameter
+ * tensors. chunk tables as in ghn3_scatter: chunk0[t] = first chunk of tensor t, chunk_tensor[c] = tensor of chunk c,
+ * chunks of GHN3_ADAMW_CHUNK elements. max_norm <= 0 disables clipping; otherwise sumsq (one device double) receives
+ * |g|^2 and the coefficient min(1, max_norm / (|g| + 1e-6)) is applied on the fly -- no host synchronisation.
+ * bias_correction{1,2} = 1 - beta{1,2}^step are computed by the host. */
+#define GHN3_ADAMW_CHUNK 8192
+typedef struct {
+  float* const* params;        /* device [n_tensors] */
+  const float* grads; float* exp_avg; float* exp_avg_sq;
+  const int64_t* offsets; const int64_t* numels; const int64_t* chunk0;   /* device [n_tensors] */
+  const int32_t* chunk_tensor; /* device [n_chunks] */
+  int64_t n_chunks; int64_t total;   /* total = elements of the flat buffers */
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
+  double* sumsq;
+} ghn3_adamw_args;
+int ghn3_adamw(const ghn3_adamw_args* args, ghn3_stream_t stream);
+
 /* Graphormer stack, training flavour. ghn3_graphormer_train_fwd computes the same function as ghn3_graphormer_stack
  * (fwd.x is ignored: the input node features are xs[0]) but keeps every activation of every layer;
  * ghn3_graphormer_bwd consumes them. Buffers are [layers][total_nodes][width] (xs: layers+1), contiguous. */

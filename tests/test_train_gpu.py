@@ -209,3 +209,43 @@ def test_two_rank_gradients_equal_single_rank_mean():
         if denom == 0 or k.endswith('proj_e.2.bias'):
             continue
         assert float((g1[k] - g2[k]).abs().max()) / denom < 2e-3, k
+
+
+def test_fused_adamw_matches_torch_clip_and_adamw():
+    """ghn3_adamw (clip + AdamW, one pass) against nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same grads."""
+    from ghn3_b200.optim import FusedAdamW
+    cfg = CONFIGS['ghn3tiny']
+
+    def make():
+        g = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+        g.load_state_dict(procedural_state_dict(cfg, 0))
+        return g.to(DEV).train()
+    a, b = make(), make()
+    opt_a = FusedAdamW(a, lr=3e-3, weight_decay=0.05, max_grad_norm=0.5)
+    opt_b = torch.optim.AdamW(b.parameters(), lr=3e-3, weight_decay=0.05)
+    graph = Graph.from_record(H.graph_records()['resnet18'])
+    for step in range(3):
+        grads = None
+        for ghn, opt in ((a, opt_a), (b, opt_b)):
+            opt.zero_grad(set_to_none=True)
+            model = ghn(H.build_model('resnet18').to(DEV), graph, keep_grads=True)
+            torch.manual_seed(step)
+            loss = sum((p * torch.randn_like(p)).sum() for p in model.parameters())
+            loss.backward()
+            if ghn is b:
+                # same gradients on both sides (the backward has atomics): copy a's into b before the torch step
+                for pb, ga in zip(b.parameters(), grads):
+                    pb.grad.copy_(ga)
+                torch.nn.utils.clip_grad_norm_(b.parameters(), 0.5)
+            else:
+                grads = [p.grad.clone() for p in a.parameters()]
+            opt.step()
+    torch.cuda.synchronize()
+    for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert H.max_rel_err(pa, pb) < 2e-5, n
+    # gradients that do not alias the backward's flat buffer are gathered first
+    for p in a.parameters():
+        p.grad = torch.ones_like(p)
+    before = [p.detach().clone() for p in a.parameters()]
+    opt_a.step()
+    assert all(not torch.equal(x, p) for x, p in zip(before, a.parameters()))
