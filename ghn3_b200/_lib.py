@@ -54,7 +54,8 @@ class GemmArgs(C.Structure):
                 ('in_dtype', i32), ('d', vp), ('out_dtype', i32), ('bias', vp), ('act', i32), ('accumulate', i32),
                 ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32),
                 ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp), ('swap_ab', i32), ('ln_out', vp),
-                ('ln_gamma', vp), ('ln_beta', vp), ('ln_counters', vp), ('ln_out_dtype', i32)]
+                ('ln_gamma', vp), ('ln_beta', vp), ('ln_counters', vp), ('ln_out_dtype', i32), ('kb_list', vp),
+                ('kb_off', vp)]
 
 
 class GemmSimtArgs(C.Structure):

@@ -139,6 +139,8 @@ struct GemmKernelArgs {
   int32_t act;
   int32_t accumulate;
   int32_t k_splits;      // single-problem mode: blockIdx.z = K split; partial sums are added atomically (fp32)
+  const int32_t* kb_list;   // optional (single-problem): K blocks visited by M tile mt = kb_list[kb_off[mt] .. kb_off[mt+1])
+  const int32_t* kb_off;
   long long* trace;      // optional [n_ctas][8] globaltimer stamps (bring-up / profiling aid, normally NULL)
   // "grouped rows" view of B (decoder conv.2 column sub-blocks): B is seen as [outer][b_stride][K] and an N tile is
   // the 3-D TMA box {K chunk, b_group inner rows, b_outer outer rows}: tile column c <-> B row (c / b_group) *
@@ -475,7 +477,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if (kb0 >= kb1) return;               // uniform for the CTA, before any barrier / TMEM allocation
     }
   }
+  // sparse-K mode: this M tile only visits the listed K blocks (everything else is known to be zero)
+  const int32_t* kbl = nullptr;
+  if (args.kb_list != nullptr && args.tiles == nullptr) {
+    const int o0 = __ldg(args.kb_off + mt), o1 = __ldg(args.kb_off + mt + 1);
+    if (o1 <= o0) return;                   // nothing to add: the (pre-zeroed / accumulated) output stays as it is
+    kbl = args.kb_list + o0;
+    kb0 = 0;
+    kb1 = o1 - o0;
+  }
   const int num_kb = kb1 - kb0;
+  auto kcoord = [&](int i) -> int { return (kbl != nullptr ? __ldg(kbl + i) : kb0 + i) * BK; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -512,17 +524,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if (args.b_dynamic) pdl_wait();
       for (int i = 0; i < pre; ++i) {
         mbar_arrive_expect_tx(full_bar + 8 * i, A_BYTES + b_bytes);
-        load_b(sB + i * B_BYTES, full_bar + 8 * i, (kb0 + i) * BK);
+        load_b(sB + i * B_BYTES, full_bar + 8 * i, kcoord(i));
       }
       pdl_wait();
-      for (int i = 0; i < pre; ++i) tma_load_2d(sA + i * A_BYTES, &tma_a, full_bar + 8 * i, (kb0 + i) * BK, a_row);
+      for (int i = 0; i < pre; ++i) tma_load_2d(sA + i * A_BYTES, &tma_a, full_bar + 8 * i, kcoord(i), a_row);
       for (int i = pre; i < num_kb; ++i) {
         const int s = i % kStages;
         const uint32_t ph = (i / kStages) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         mbar_arrive_expect_tx(full_bar + 8 * s, A_BYTES + b_bytes);
-        tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, (kb0 + i) * BK, a_row);
-        load_b(sB + s * B_BYTES, full_bar + 8 * s, (kb0 + i) * BK);
+        const int kc = kcoord(i);
+        tma_load_2d(sA + s * A_BYTES, &tma_a, full_bar + 8 * s, kc, a_row);
+        load_b(sB + s * B_BYTES, full_bar + 8 * s, kc);
       }
     }
   } else if (warp == 1) {
@@ -1063,7 +1076,10 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
     const int64_t mt = ceil_div(a->single.m, kBlockM);
     if (bn == 0) bn = (mt * ceil_div(a->single.n, 128) >= sms) ? 128 : 64;   // small problems: more, smaller tiles
     const int64_t ctas = mt * ceil_div(a->single.n, bn);
-    if (a->k_splits > 0) {
+    if (a->kb_list != nullptr) {
+      GHN3_REQUIRE(a->kb_off != nullptr, "ghn3_gemm: kb_list needs kb_off");
+      splits = 1;
+    } else if (a->k_splits > 0) {
       splits = a->k_splits;
     } else if (a->accumulate && a->out_dtype == GHN3_F32 && ctas < sms && num_kb >= 4) {
       // residual updates are sums anyway: split K so that ~one wave of CTAs shares the reduction
@@ -1103,6 +1119,8 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.act = a->act;
   ka.accumulate = a->accumulate;
   ka.k_splits = splits;
+  ka.kb_list = a->kb_list;
+  ka.kb_off = a->kb_off;
   ka.trace = g_gemm_trace;
   ka.b_group = a->b_group;
   ka.b_stride = a->b_group_stride;

@@ -58,6 +58,38 @@ def transposed_weights(ghn, w):
     return wt
 
 
+def _conv2_k_blocks(segments, R, KF, ms1, bk, dev):
+    """Sparse-K block lists (ghn3_gemm_args.kb_list / kb_off) of the two conv.2 backward GEMMs over the
+    column-expanded operands: class (o', i') at rows [row0, row0 + rows) is non-zero only in the columns
+    a * ms1 + b, a < o', b < i'.
+      dgrad  dh1 = X . W2^T   : M tiles = 128 rows of X,  K blocks = `bk` expanded columns
+      wgrad  dW2 = X^T . h1   : M tiles = 128 expanded columns, K blocks = `bk` rows"""
+    n_cb, n_rt = -(-KF // bk), -(-R // 128)
+    n_ct, n_rb = -(-KF // 128), -(-R // bk)
+    d_mask = np.zeros((n_rt, n_cb), dtype=bool)            # dgrad: row tile x column block
+    w_mask = np.zeros((n_ct, n_rb), dtype=bool)            # wgrad: column tile x row block
+    for (o, ii, row0, rows, _) in segments:
+        a = np.arange(o, dtype=np.int64) * ms1
+        cols = np.zeros(KF + 1, dtype=np.int32)            # coverage of expanded columns via a difference array
+        np.add.at(cols, a, 1)
+        np.add.at(cols, a + ii, -1)
+        used = np.cumsum(cols[:-1]) > 0
+        cb = np.add.reduceat(used, np.arange(0, KF, bk)) > 0
+        ct = np.add.reduceat(used, np.arange(0, KF, 128)) > 0
+        rt0, rt1 = row0 // 128, (row0 + rows - 1) // 128
+        rb0, rb1 = row0 // bk, (row0 + rows - 1) // bk
+        d_mask[rt0:rt1 + 1] |= cb[None, :]
+        w_mask[np.nonzero(ct)[0], rb0:rb1 + 1] = True
+
+    def pack(mask):
+        off = np.concatenate([[0], np.cumsum(mask.sum(1))]).astype(np.int32)
+        lst = np.nonzero(mask)[1].astype(np.int32)
+        if len(lst) == 0:
+            lst = np.zeros(1, np.int32)
+        return torch.from_numpy(lst).to(dev), torch.from_numpy(off).to(dev)
+    return pack(d_mask), pack(w_mask)
+
+
 def flat_layout(ghn):
     """Order and offsets of the GHN parameters in the flat fp32 gradient buffer: [decoder, decoder_1d, bias_class |
     everything else], every tensor starting at a multiple of 4 elements. The first region is final as soon as the
@@ -122,11 +154,13 @@ class _Backward:
             add('colsum', L.ColsumArgs(src=P(src), src_dtype=src_dt, ld=ld, rows=rows, cols=cols, group=group,
                                        group_stride=group_stride, dst=P(dst)))
 
-        def gemm(a, m, lda, b, n, ldb, k, d, out_dtype, accumulate=0, b_dynamic=1, rowmap=None, ldd=None):
+        def gemm(a, m, lda, b, n, ldb, k, d, out_dtype, accumulate=0, b_dynamic=1, rowmap=None, ldd=None, kb=None):
             P = lambda t: t if isinstance(t, int) else t.data_ptr()
             g = L.GemmArgs(a=P(a), a_rows=m, lda=lda, b=P(b), b_rows=n, ldb=ldb, k=k, in_dtype=in_dt, d=P(d),
                            out_dtype=out_dtype, bias=None, act=ops.ACT_NONE, accumulate=accumulate, tf32_x3=x3,
                            b_dynamic=b_dynamic, rowmap=L.ptr(rowmap))
+            if kb is not None:
+                g.kb_list, g.kb_off = kb[0].data_ptr(), kb[1].data_ptr()
             g.single = L.GemmProblem(a_row0=0, b_row0=0, m=m, n=n, d_off=0, ldd=n if ldd is None else ldd, bias_off=-1)
             add('gemm', g)
 
@@ -253,10 +287,12 @@ class _Backward:
             h1T = E(8 * C * rp)
             self.dh1, self.dh0 = E(R, 8 * C), E(R, 4 * C)
             self.keep.append(h1T)
+            kb_d, kb_w = _conv2_k_blocks(bp.segments, R, KF, ms1, 64 if act == ops.BF16 else 32, dev)
+            self.keep += [kb_d, kb_w]
             c2T = wt['c2_wT']
-            gemm(self.X, R, KF, c2T, 8 * C, c2T.stride(0), KF, self.dh1, act, b_dynamic=0)
+            gemm(self.X, R, KF, c2T, 8 * C, c2T.stride(0), KF, self.dh1, act, b_dynamic=0, kb=kb_d)
             transpose(prog.h1, R, 8 * C, 8 * C, h1T, src_dtype=act)
-            gemm(self.XT, KF, rp, h1T, 8 * C, rp, R, G(c2w), F32)
+            gemm(self.XT, KF, rp, h1T, 8 * C, rp, R, G(c2w), F32, kb=kb_w)      # D pre-zeroed with the flat buffer
             rp = _pad8(R)
             h0T = E(4 * C * rp)
             self.keep.append(h0T)

@@ -213,6 +213,12 @@ typedef struct {
   const float* ln_beta;
   int32_t* ln_counters;
   int32_t ln_out_dtype;
+  /* Sparse-K mode for single-problem launches whose operands are known to be zero outside a few K blocks (the
+   * column-expanded operands of the decoder conv.2 backward): the M tile mt (128 rows) only visits the K blocks
+   * kb_list[kb_off[mt] .. kb_off[mt+1]) (block = 64 bf16 / 32 fp32 elements of K). An M tile with an empty list is
+   * skipped and leaves D untouched (the caller pre-zeroes D). Device arrays; NULL = dense. */
+  const int32_t* kb_list;
+  const int32_t* kb_off;
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);

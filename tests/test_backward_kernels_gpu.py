@@ -290,3 +290,32 @@ def test_scatter_bwd_matches_autograd_of_forward():
     src.copy_(base)
     # elements the forward never reads get no gradient
     assert float(d_src[:, so * si + 5:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('dtype', [ops.BF16, ops.TF32])
+def test_gemm_sparse_k_blocks(dtype):
+    """ghn3_gemm_args.kb_list / kb_off: every M tile visits only its listed K blocks; an empty list leaves D alone."""
+    torch.manual_seed(10)
+    bk = 64 if dtype == ops.BF16 else 32
+    M, N, K = 3 * 128 + 40, 200, 16 * bk
+    a = torch.zeros(M, K, device=DEV)
+    lists = [[0, 3, 4], [], [15], [2, 7, 8, 9]]
+    for mt, blocks in enumerate(lists):
+        for kb in blocks:
+            a[mt * 128:(mt + 1) * 128, kb * bk:(kb + 1) * bk] = torch.randn(min(128, M - mt * 128), bk, device=DEV)
+    b = torch.randn(N, K, device=DEV) / K ** 0.5
+    a_in, b_in = (a.bfloat16(), b.bfloat16()) if dtype == ops.BF16 else (ops.convert(a, ops.TF32), ops.convert(b, ops.TF32))
+    kb_list = torch.tensor(sum(lists, []), dtype=torch.int32, device=DEV)
+    kb_off = torch.tensor(np.concatenate([[0], np.cumsum([len(x) for x in lists])]), dtype=torch.int32, device=DEV)
+    out = torch.full((M, N), 7.0, device=DEV)
+    g = L.GemmArgs(a=a_in.data_ptr(), a_rows=M, lda=K, b=b_in.data_ptr(), b_rows=N, ldb=K, k=K, in_dtype=dtype,
+                   d=out.data_ptr(), out_dtype=ops.F32, bias=None, act=ops.ACT_NONE, b_dynamic=1,
+                   kb_list=kb_list.data_ptr(), kb_off=kb_off.data_ptr())
+    g.single = L.GemmProblem(a_row0=0, b_row0=0, m=M, n=N, d_off=0, ldd=N, bias_off=-1)
+    L.call('gemm', g, L.current_stream())
+    torch.cuda.synchronize()
+    ref = (a_in.double() @ b_in.double().t()).float()
+    assert bool((out[128:256] == 7.0).all())                       # empty list: untouched
+    for mt in (0, 2, 3):
+        sl = slice(mt * 128, min((mt + 1) * 128, M))
+        assert _rel(out[sl], ref[sl]) < 2e-5
