@@ -1,0 +1,237 @@
+"""
+DeepNets-1M-style architecture sampler for the training path (BASELINE config 5).
+
+The reference trains on architectures stored in the DeepNets-1M HDF5 file (ghn3/deepnets1m.py:84-147), which were
+produced by ppuda's NetGenerator and are instantiated as `Network` / `NetworkLight` (ghn3/ops.py:306-569). Neither the
+file nor ppuda is available offline, so this module samples architectures from the same design space directly:
+DARTS-format genotypes over the primitives of ghn3/ops.py:291-304, 4-18 cells, C in 32..128 step 16, two stem types,
+1-2 fully connected layers, optional global pooling, BatchNorm. The networks are ordinary `nn.Module`s; their graphs
+come from the host tracer (ghn3_b200/tracer.py) like those of any other model.
+
+This is a from-scratch generator, not a port of the reference's classes: module names and the exact wiring of the
+stems differ, so graphs are DeepNets-1M-*style*, not bit-identical to the released dataset.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+OPS = ('none', 'skip_connect', 'max_pool', 'avg_pool', 'conv', 'sep_conv', 'dil_conv', 'cse')
+KERNELS = {'max_pool': (3,), 'avg_pool': (3,), 'conv': (1, 3, 5), 'sep_conv': (3, 5), 'dil_conv': (3, 5)}
+CHANNELS = tuple(range(32, 129, 16))            # deepnets1m.py:122-128
+FC_DIMS = tuple(range(64, 257, 64))
+
+
+class ReLUConvBN(nn.Sequential):
+    def __init__(self, c_in, c_out, k=1, stride=1):
+        super().__init__(nn.ReLU(), nn.Conv2d(c_in, c_out, k, stride, k // 2, bias=False), nn.BatchNorm2d(c_out))
+
+
+class SepConv(nn.Sequential):
+    """depthwise-separable convolution applied twice (DARTS)"""
+
+    def __init__(self, c_in, c_out, k, stride):
+        super().__init__(
+            nn.ReLU(), nn.Conv2d(c_in, c_in, k, stride, k // 2, groups=c_in, bias=False),
+            nn.Conv2d(c_in, c_in, 1, bias=False), nn.BatchNorm2d(c_in),
+            nn.ReLU(), nn.Conv2d(c_in, c_in, k, 1, k // 2, groups=c_in, bias=False),
+            nn.Conv2d(c_in, c_out, 1, bias=False), nn.BatchNorm2d(c_out))
+
+
+class DilConv(nn.Sequential):
+    def __init__(self, c_in, c_out, k, stride):
+        super().__init__(
+            nn.ReLU(), nn.Conv2d(c_in, c_in, k, stride, k - k % 2, dilation=2, groups=c_in, bias=False),
+            nn.Conv2d(c_in, c_out, 1, bias=False), nn.BatchNorm2d(c_out))
+
+
+class FactorizedReduce(nn.Module):
+    """stride-2 skip connection: two offset 1x1 stride-2 convolutions, concatenated"""
+
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.conv_1 = nn.Conv2d(c_in, c_out // 2, 1, 2, bias=False)
+        self.conv_2 = nn.Conv2d(c_in, c_out - c_out // 2, 1, 2, bias=False)
+        self.bn = nn.BatchNorm2d(c_out)
+
+    def forward(self, x):
+        x = F.relu(x)
+        y = F.pad(x, (0, 1, 0, 1))[:, :, 1:, 1:]
+        return self.bn(torch.cat([self.conv_1(x), self.conv_2(y)], 1))
+
+
+class Zero(nn.Module):
+    def __init__(self, stride):
+        super().__init__()
+        self.stride = stride
+
+    def forward(self, x):
+        return (x if self.stride == 1 else x[:, :, ::self.stride, ::self.stride]) * 0.0
+
+
+class ChannelSE(nn.Module):
+    """squeeze-and-excitation over channels ('cse')"""
+
+    def __init__(self, c, stride):
+        super().__init__()
+        self.fc1 = nn.Linear(c, max(c // 2, 4))
+        self.fc2 = nn.Linear(max(c // 2, 4), c)
+        self.stride = stride
+
+    def forward(self, x):
+        if self.stride > 1:
+            x = F.avg_pool2d(x, self.stride)
+        s = torch.sigmoid(self.fc2(F.relu(self.fc1(x.mean((2, 3))))))
+        return x * s[:, :, None, None]
+
+
+def make_op(name, k, c, stride):
+    if name == 'none':
+        return Zero(stride)
+    if name == 'skip_connect':
+        return nn.Identity() if stride == 1 else FactorizedReduce(c, c)
+    if name == 'max_pool':
+        return nn.MaxPool2d(k, stride, k // 2)
+    if name == 'avg_pool':
+        return nn.AvgPool2d(k, stride, k // 2, count_include_pad=False)
+    if name == 'conv':
+        return ReLUConvBN(c, c, k, stride)
+    if name == 'sep_conv':
+        return SepConv(c, c, k, stride)
+    if name == 'dil_conv':
+        return DilConv(c, c, k, stride)
+    if name == 'cse':
+        return ChannelSE(c, stride)
+    raise ValueError(name)
+
+
+class Cell(nn.Module):
+    """DARTS cell: two input states, `steps` intermediate nodes with two incoming edges each, concat of the nodes
+    listed in `concat`."""
+
+    def __init__(self, edges, concat, c_pp, c_p, c, reduction, reduction_prev):
+        super().__init__()
+        self.preprocess0 = FactorizedReduce(c_pp, c) if reduction_prev else ReLUConvBN(c_pp, c)
+        self.preprocess1 = ReLUConvBN(c_p, c)
+        self.edges, self.concat = edges, list(concat)
+        self.ops = nn.ModuleList()
+        for (name, k, src) in edges:
+            stride = 2 if reduction and src < 2 else 1
+            self.ops.append(make_op(name, k, c, stride))
+        self.multiplier = len(self.concat)
+
+    def forward(self, s0, s1):
+        states = [self.preprocess0(s0), self.preprocess1(s1)]
+        for i in range(0, len(self.ops), 2):
+            a = self.ops[i](states[self.edges[i][2]])
+            b = self.ops[i + 1](states[self.edges[i + 1][2]])
+            states.append(a + b)
+        return torch.cat([states[i] for i in self.concat], 1)
+
+
+class CellNet(nn.Module):
+    """Stem -> n_cells cells (reduction at 1/3 and 2/3 of the depth) -> (global pool) -> fc_layers classifier."""
+
+    def __init__(self, genotype, C=32, n_cells=8, stem_type=0, fc_layers=1, fc_dim=128, glob_avg=True,
+                 num_classes=1000, **unused):
+        super().__init__()
+        self.net_args = dict(genotype=genotype, C=C, n_cells=n_cells, stem_type=stem_type, fc_layers=fc_layers,
+                             fc_dim=fc_dim, glob_avg=glob_avg, num_classes=num_classes)
+        self._n_cells = n_cells                # read by the tracer / layered-module walk (reference graph.py:327)
+        if stem_type == 0:                     # one strided stem (stride 4 overall)
+            self.stem = nn.Sequential(nn.Conv2d(3, C, 3, 2, 1, bias=False), nn.BatchNorm2d(C), nn.ReLU(),
+                                      nn.MaxPool2d(3, 2, 1))
+            c_pp = c_p = C
+        else:                                  # ImageNet-style double stem
+            self.stem = nn.Sequential(nn.Conv2d(3, C // 2, 3, 2, 1, bias=False), nn.BatchNorm2d(C // 2), nn.ReLU(),
+                                      nn.Conv2d(C // 2, C, 3, 2, 1, bias=False), nn.BatchNorm2d(C))
+            c_pp = c_p = C
+        self.cells = nn.ModuleList()
+        c, red_prev = C, False
+        for i in range(n_cells):
+            reduction = n_cells >= 3 and i in (n_cells // 3, 2 * n_cells // 3)
+            if reduction:
+                c *= 2
+            g = genotype['reduce' if reduction else 'normal']
+            cell = Cell(g, genotype['reduce_concat' if reduction else 'normal_concat'], c_pp, c_p, c, reduction,
+                        red_prev)
+            self.cells.append(cell)
+            c_pp, c_p, red_prev = c_p, cell.multiplier * c, reduction
+        self.glob_avg = glob_avg
+        feat = c_p if glob_avg else c_p * 4
+        layers = []
+        for _ in range(fc_layers - 1):
+            layers += [nn.Linear(feat, fc_dim), nn.ReLU()]
+            feat = fc_dim
+        layers.append(nn.Linear(feat, num_classes))
+        self.classifier = nn.Sequential(*layers)
+
+    def forward(self, x):
+        s0 = s1 = self.stem(x)
+        for cell in self.cells:
+            s0, s1 = s1, cell(s0, s1)
+        x = F.adaptive_avg_pool2d(s1, 1 if self.glob_avg else 2)
+        return self.classifier(torch.flatten(x, 1))
+
+
+def sample_genotype(rng, steps=None):
+    """DARTS-format genotype: per intermediate node two (op, kernel, source state) edges; `none` at most once."""
+    def cell():
+        n = int(rng.integers(2, 5)) if steps is None else steps
+        edges = []
+        for node in range(n):
+            srcs = rng.choice(node + 2, size=2, replace=False)
+            for src in sorted(int(s) for s in srcs):
+                name = OPS[int(rng.integers(1, len(OPS)))]
+                k = int(rng.choice(KERNELS[name])) if name in KERNELS else 1
+                edges.append((name, k, src))
+        used = {e[2] for e in edges}
+        concat = [i for i in range(2, n + 2) if i not in used] or [n + 1]
+        return edges, concat
+    normal, normal_concat = cell()
+    reduce, reduce_concat = cell()
+    return {'normal': normal, 'normal_concat': normal_concat, 'reduce': reduce, 'reduce_concat': reduce_concat}
+
+
+def sample_net_args(rng):
+    """Hyper-parameters in the ranges the reference's training loader draws from (deepnets1m.py:113-133)."""
+    n_cells = int(rng.integers(4, 19))
+    if n_cells > 12:
+        C = CHANNELS[0]
+    elif n_cells > 10:
+        C = int(rng.choice(CHANNELS[:2]))
+    elif n_cells > 8:
+        C = int(rng.choice(CHANNELS[:3]))
+    else:
+        C = int(rng.choice(CHANNELS))
+    return dict(genotype=sample_genotype(rng), C=C, n_cells=n_cells, stem_type=int(rng.integers(0, 2)),
+                fc_layers=int(rng.integers(1, 3)), fc_dim=int(rng.choice(FC_DIMS)), glob_avg=bool(rng.random() < 0.8))
+
+
+class NetGenerator:
+    """Deterministic stream of (CellNet, Graph) pairs: `NetGenerator(seed).sample(n)`; the same seed gives the same
+    global meta-batch on every rank."""
+
+    def __init__(self, seed=0, num_classes=1000, max_params=20e6):
+        self.rng = np.random.default_rng(seed)
+        self.num_classes, self.max_params = num_classes, max_params
+
+    def sample_net(self):
+        while True:
+            args = sample_net_args(self.rng)
+            net = CellNet(num_classes=self.num_classes, **args)
+            if sum(p.numel() for p in net.parameters()) <= self.max_params:
+                return net
+
+    def sample(self, n, device=None, input_size=64):
+        """n (net, graph) pairs; graphs are traced on the host with a small input (the graph does not depend on it)."""
+        from .graph import Graph
+        out = []
+        for _ in range(n):
+            net = self.sample_net()
+            net.expected_input_sz = input_size
+            graph = Graph(net)
+            if device is not None:
+                net = net.to(device)
+            out.append((net, graph))
+        return out

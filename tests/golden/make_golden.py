@@ -12,7 +12,9 @@ only the committed outputs:
                            ghn3_b200.weights.procedural_state_dict(cfg, seed=0) loaded into the reference GHN3
   emb_<cfg>_<arch>.npy     node embeddings after the Graphormer stack + final LayerNorm (return_embeddings=True)
 
-Usage:  python tests/golden/make_golden.py graphs | preds | all
+  graphs_cellnets.json.gz  the same for the first 8 networks of ghn3_b200.deepnets.NetGenerator(seed=0)
+
+Usage:  python tests/golden/make_golden.py graphs | cellnets | preds | all
 """
 import gzip
 import inspect
@@ -50,6 +52,9 @@ def tv_model_names():
 
 
 def build_model(name):
+    if name.startswith('cellnet'):                    # i-th network of ghn3_b200.deepnets.NetGenerator(seed=0)
+        from tests import helpers
+        return helpers.build_model(name)
     kw = {'init_weights': False} if name in ['googlenet', 'inception_v3'] else {}
     torch.manual_seed(0)
     m = getattr(models, name)(**kw)
@@ -62,8 +67,8 @@ def ser_sz(sz):
     return None if sz is None else [int(v) for v in sz]
 
 
-def graph_record(name):
-    model = build_model(name)
+def graph_record(name, model=None):
+    model = build_model(name) if model is None else model
     t0 = time.time()
     g = ref.Graph(model, ve_cutoff=50, verbose=False)
     dt = time.time() - t0
@@ -96,6 +101,24 @@ def make_graphs():
     with gzip.open(os.path.join(HERE, 'graphs_tv.json.gz'), 'wt') as f:
         json.dump(out, f, separators=(',', ':'))
     print('wrote %d graphs' % len(out))
+
+
+def make_cellnet_graphs(n=8, seed=0):
+    """graphs_cellnets.json.gz: the reference's tracer on the first `n` networks of
+    ghn3_b200.deepnets.NetGenerator(seed) (DeepNets-1M-style cell networks with `_n_cells`, per-cell node_info)."""
+    from ghn3_b200.deepnets import NetGenerator
+    gen = NetGenerator(seed=seed)
+    out = {}
+    for i in range(n):
+        net = gen.sample_net()
+        net.expected_input_sz = 64
+        rec = graph_record('cellnet%d' % i, model=net)
+        out['cellnet%d' % i] = rec
+        print('%3d cellnet N=%4d edges=%4d nnz=%6d max=%2d trace=%.2fs' % (
+            i, rec['n'], len(rec['edges']), rec['spd_nnz'], rec['spd_max'], rec['trace_sec']), flush=True)
+    with gzip.open(os.path.join(HERE, 'graphs_cellnets.json.gz'), 'wt') as f:
+        json.dump({'seed': seed, 'graphs': out}, f, separators=(',', ':'))
+    print('wrote %d cell-network graphs' % len(out))
 
 
 def fingerprint(t):
@@ -133,7 +156,7 @@ def make_pred(cfg_name, arch, save_emb=True):
 
 PRED_CASES = [('ghn3tiny', 'resnet18'), ('ghn3tiny', 'squeezenet1_1'), ('ghn3tiny', 'mobilenet_v3_small'),
               ('ghn3tiny', 'vit_b_32'), ('ghn3tiny', 'swin_v2_t'), ('ghn3tiny', 'convnext_tiny'),
-              ('ghn3tm8', 'resnet50'),
+              ('ghn3tiny', 'cellnet7'), ('ghn3tm8', 'resnet50'),
               ('ghn3xlm16', 'vit_b_16'), ('ghn3xlm16', 'convnext_base')]
 
 
@@ -146,5 +169,10 @@ if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if what in ('graphs', 'all'):
         make_graphs()
+    if what in ('cellnets', 'all'):
+        make_cellnet_graphs()
     if what in ('preds', 'all'):
         make_preds()
+    if what.startswith('pred:'):                      # one case, e.g. pred:ghn3tiny:cellnet7
+        _, cfg_name, arch = what.split(':')
+        make_pred(cfg_name, arch)

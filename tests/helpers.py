@@ -19,11 +19,27 @@ def graph_records():
     if _graphs is None:
         with gzip.open(os.path.join(GOLDEN, 'graphs_tv.json.gz'), 'rt') as f:
             _graphs = json.load(f)
+        _graphs.update(cellnet_records()['graphs'])          # 'cellnet0' .. 'cellnet7'
     return _graphs
+
+
+def cellnet_records():
+    """tests/golden/graphs_cellnets.json.gz: the reference's tracer on NetGenerator(seed) networks."""
+    with gzip.open(os.path.join(GOLDEN, 'graphs_cellnets.json.gz'), 'rt') as f:
+        return json.load(f)
 
 
 def build_model(name):
     """Same construction as tests/golden/make_golden.py:build_model (seeded default init)."""
+    if name.startswith('cellnet'):
+        # the i-th network of ghn3_b200.deepnets.NetGenerator(seed of the fixture); default (unseeded) weight init is
+        # irrelevant: every parameter is predicted
+        from ghn3_b200.deepnets import NetGenerator
+        gen = NetGenerator(seed=cellnet_records()['seed'])
+        for _ in range(int(name[7:]) + 1):
+            net = gen.sample_net()
+        net.expected_input_sz = 64
+        return net
     kw = {'init_weights': False} if name in ['googlenet', 'inception_v3'] else {}
     torch.manual_seed(0)
     m = getattr(tvm, name)(**kw)

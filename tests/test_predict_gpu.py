@@ -80,6 +80,12 @@ def test_tiny_single(arch, dtype):
     run_case('ghn3tiny', [arch], dtype)
 
 
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+def test_tiny_deepnets_style_cell_networks(dtype):
+    """NetGenerator-sampled cell networks (DeepNets-1M style): per-cell node_info, dilated / separable convolutions."""
+    run_case('ghn3tiny', ['cellnet7', 'cellnet4'], dtype, check_logits=False)
+
+
 @pytest.mark.parametrize('dtype', ['tf32', 'tf32x1', 'bf16'])
 def test_tm8_resnet50(dtype):
     run_case('ghn3tm8', ['resnet50'], dtype)

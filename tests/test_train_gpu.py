@@ -121,6 +121,12 @@ def test_tiny_gradients_batch_of_graphs(dtype):
     _run('ghn3tiny', ['resnet18', 'alexnet', 'squeezenet1_1'], dtype)
 
 
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+def test_tiny_gradients_deepnets_style_cell_network(dtype):
+    """BASELINE config 5 targets: a NetGenerator-sampled cell network (per-cell node_info, `_n_cells` > 1)."""
+    _run('ghn3tiny', ['cellnet7', 'cellnet1'], dtype)
+
+
 def test_tm8_gradients_resnet50():
     _run('ghn3tm8', ['resnet50'], 'bf16')
 
