@@ -176,30 +176,53 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
 //   S = Q K^T d^-1/2 + lut[h][pair];  P = softmax(S);  O = P V
 //   delta_i = dO_i . O_i;  dP = dO V^T;  dS = P o (dP - delta);  dQ = dS K d^-1/2;  dK = dS^T Q d^-1/2;  dV = P^T dO
 //   dlut[h][pair(i,j)] += dS_ij
-constexpr int kBwdKT = 256;     // keys (kernel A) / queries (kernel B) staged per tile; graphs up to this size
-                                // keep their whole K/V (Q/dO) resident in shared memory for the lifetime of the CTA
+constexpr int kBwdKT = 256;     // keys (kernel A) / queries (kernel B) staged per shared-memory tile
 constexpr int kBwdWarps = 8;
-constexpr int kBwdBlock = 64;   // queries (A) / keys (B) per CTA, one per warp per round
+constexpr int kBwdBlock = 64;   // queries (A) / keys (B) owned by a CTA: 8 per warp, state kept in shared memory
 
+// rows x D slice of a [*, ld] matrix of T -> fp32 shared-memory tile with row stride D+1 (bank-conflict free),
+// 16-byte global loads when the slice allows it
 template <typename T, int D>
-__device__ __forceinline__ void bwd_load_tile(float* s0, float* s1, const T* base0, const T* base1, int64_t ld0,
-                                              int64_t ld1, int rows, float scale0) {
+__device__ __forceinline__ void bwd_load_tile(float* dst, const T* base, int64_t ld, int rows, float scale) {
   constexpr int DP = D + 1;
+  constexpr int EPV = 16 / (int)sizeof(T);                 // elements per 16-byte vector
+  if constexpr (D % EPV == 0) {
+    const bool aligned = ((((uintptr_t)base) & 15) == 0) && ((ld * sizeof(T)) % 16 == 0);
+    if (aligned) {
+      constexpr int VPR = D / EPV;
+      for (int idx = threadIdx.x; idx < rows * VPR; idx += blockDim.x) {
+        const int j = idx / VPR, v = idx - j * VPR;
+        const uint4 raw = *(const uint4*)(base + (int64_t)j * ld + v * EPV);
+        const T* e = (const T*)&raw;
+#pragma unroll
+        for (int t = 0; t < EPV; ++t) dst[j * DP + v * EPV + t] = to_float(e[t]) * scale;
+      }
+      return;
+    }
+  }
   for (int idx = threadIdx.x; idx < rows * D; idx += blockDim.x) {
     const int j = idx / D, d = idx - j * D;
-    s0[j * DP + d] = to_float(base0[(int64_t)j * ld0 + d]) * scale0;
-    s1[j * DP + d] = to_float(base1[(int64_t)j * ld1 + d]);
+    dst[j * DP + d] = to_float(base[(int64_t)j * ld + d]) * scale;
   }
 }
 
+// Kernel A: one CTA = 64 queries of one (graph, head). Pass 0 recomputes the softmax statistics, pass 1 the gradients;
+// the key/value tiles are the OUTER loop (loaded once per pass), every warp walks its 8 queries per tile.
 template <typename T, int D>
 __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
   constexpr int U = kBwdKT / 32;
+  constexpr int QPW = kBwdBlock / kBwdWarps;
   float* sK = bw_smem;                         // [KT][DP]
   float* sV = sK + kBwdKT * DP;                // [KT][DP]
-  float* sBias = sV + kBwdKT * DP;             // [warps][KT]  (each warp stages the row of its own query)
+  float* sQ = sV + kBwdKT * DP;                // [64][DP]  (pre-scaled by d^-1/2)
+  float* sdO = sQ + kBwdBlock * DP;            // [64][DP]
+  float* sdQ = sdO + kBwdBlock * DP;           // [64][DP]  gradient accumulator
+  float* sM = sdQ + kBwdBlock * DP;            // [64] running max
+  float* sL = sM + kBwdBlock;                  // [64] running sum
+  float* sDelta = sL + kBwdBlock;              // [64]
+  float* sBias = sDelta + kBwdBlock;           // [warps][KT]
   uint16_t* sPair = (uint16_t*)(sBias + kBwdWarps * kBwdKT);   // [warps][KT]
   float* sLut = (float*)(sPair + kBwdWarps * kBwdKT);          // [lut_size]
   float* sHist = sLut + a.lut_size;                            // [lut_size]
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kerne
   const int n = a.node_off[g + 1] - n0;
   const int q0 = blockIdx.x * kBwdBlock;
   if (q0 >= n) return;
+  const int nq = min(kBwdBlock, n - q0);
   const int ld = (n + 15) & ~15;
   const int C = a.hid, C3 = 3 * C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -217,7 +241,6 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kerne
   const T* out = (const T*)a.out + (int64_t)n0 * C;
   const uint16_t* pair = a.pair + a.mat_off[g];
   const float scale = rsqrtf((float)D);
-  const bool single = n <= kBwdKT;             // block-uniform
 
   pdl_launch_dependents();
   for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) {
@@ -225,118 +248,127 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dq_kerne
     sHist[i] = 0.f;
   }
   pdl_wait();
-  if (single) bwd_load_tile<T, D>(sK, sV, qkv + C + h * D, qkv + 2 * C + h * D, C3, C3, n, 1.f);
+  bwd_load_tile<T, D>(sQ, qkv + (int64_t)q0 * C3 + h * D, C3, nq, scale);
+  bwd_load_tile<T, D>(sdO, dout + (int64_t)q0 * C + h * D, C, nq, 1.f);
+  for (int i = threadIdx.x; i < kBwdBlock * DP; i += blockDim.x) sdQ[i] = 0.f;
+  for (int i = threadIdx.x; i < kBwdBlock; i += blockDim.x) { sM[i] = -INFINITY; sL[i] = 0.f; }
   __syncthreads();
+  // delta_i = dO_i . O_i
+  for (int lq = warp; lq < nq; lq += kBwdWarps) {
+    float t = 0.f;
+    for (int d = lane; d < D; d += 32) t += sdO[lq * DP + d] * to_float(out[(int64_t)(q0 + lq) * C + h * D + d]);
+    t = warp_sum(t);
+    if (lane == 0) sDelta[lq] = t;
+  }
 
   float* myBias = sBias + warp * kBwdKT;
   uint16_t* myPair = sPair + warp * kBwdKT;
-  for (int r = 0; r < kBwdBlock / kBwdWarps; ++r) {
-    const int qi = q0 + r * kBwdWarps + warp;
-    const bool ok = qi < n;                    // warp-uniform
-    if (single && !ok) continue;               // no block-level synchronisation below in the single-tile case
-    float q[D], dO[D], dq[D];
-    float delta = 0.f, m = -INFINITY, l = 0.f;
-    {
-      const int64_t row = ok ? qi : 0;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        q[d] = ok ? to_float(qkv[row * C3 + h * D + d]) * scale : 0.f;
-        dO[d] = ok ? to_float(dout[row * C + h * D + d]) : 0.f;
-        dq[d] = 0.f;
-        delta += dO[d] * (ok ? to_float(out[row * C + h * D + d]) : 0.f);
-      }
-    }
-    for (int pass = 0; pass < 2; ++pass) {
-      const float lse = m + __logf(l);         // only meaningful in pass 1
-      for (int k0 = 0; k0 < n; k0 += kBwdKT) {
-        const int kt = min(kBwdKT, n - k0);
-        if (!single) {
-          __syncthreads();
-          bwd_load_tile<T, D>(sK, sV, qkv + (int64_t)k0 * C3 + C + h * D, qkv + (int64_t)k0 * C3 + 2 * C + h * D, C3,
-                              C3, kt, 1.f);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k0 = 0; k0 < n; k0 += kBwdKT) {
+      const int kt = min(kBwdKT, n - k0);
+      __syncthreads();                         // previous tile fully consumed (and sDelta / statistics visible)
+      bwd_load_tile<T, D>(sK, qkv + (int64_t)k0 * C3 + C + h * D, C3, kt, 1.f);
+      bwd_load_tile<T, D>(sV, qkv + (int64_t)k0 * C3 + 2 * C + h * D, C3, kt, 1.f);
+      __syncthreads();
+      for (int r = 0; r < QPW; ++r) {
+        const int lq = r * kBwdWarps + warp;   // this warp owns local queries warp, warp+8, ...
+        if (lq >= nq) break;                   // warp-uniform
+        const int qi = q0 + lq;
+        for (int j = lane; j < kt; j += 32) {
+          const uint16_t p = pair[(int64_t)qi * ld + k0 + j];
+          myPair[j] = p;
+          myBias[j] = sLut[p];
         }
-        if (ok) {
-          for (int j = lane; j < kt; j += 32) {
-            const uint16_t p = pair[(int64_t)qi * ld + k0 + j];
-            myPair[j] = p;
-            myBias[j] = sLut[p];
-          }
-        }
-        if (!single) __syncthreads(); else __syncwarp();
-        if (ok) {
-          if (pass == 0) {
-            float mx = m;
-            float sv[U];
+        float q[D];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int j = lane + 32 * u;
-              float s_ = -INFINITY;
-              if (j < kt) {
-                s_ = myBias[j];
-#pragma unroll
-                for (int d = 0; d < D; ++d) s_ = fmaf(q[d], sK[j * DP + d], s_);
-              }
-              sv[u] = s_;
-              mx = fmaxf(mx, s_);
-            }
-            mx = warp_max(mx);
-            float sum = 0.f;
-#pragma unroll
-            for (int u = 0; u < U; ++u) sum += (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - mx);
-            sum = warp_sum(sum);
-            l = l * __expf(m - mx) + sum;
-            m = mx;
-          } else {
-#pragma unroll 2
-            for (int u = 0; u < U; ++u) {
-              const int j = lane + 32 * u;
-              if (j < kt) {
-                float s_ = myBias[j], dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                  s_ = fmaf(q[d], sK[j * DP + d], s_);
-                  dp = fmaf(dO[d], sV[j * DP + d], dp);
-                }
-                const float p = __expf(s_ - lse);
-                const float ds = p * (dp - delta);
-#pragma unroll
-                for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, sK[j * DP + d], dq[d]);
-                if (a.d_lut != nullptr) atomicAdd(sHist + myPair[j], ds);
-              }
-            }
-          }
-        }
+        for (int d = 0; d < D; ++d) q[d] = sQ[lq * DP + d];
         __syncwarp();
-      }
-    }
-    if (ok) {
-      const int64_t row = n0 + qi;
-      T* dst = (T*)a.d_qkv + row * C3 + h * D;
+        if (pass == 0) {
+          const float m_old = sM[lq];
+          float mx = m_old;
+          float sv[U];
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const float v = warp_sum(dq[d]) * scale;
-        if (lane == 0) dst[d] = from_float<T>(v);
-      }
-      if (lane == 0) {
-        a.lse[(int64_t)h * a.total_nodes + row] = m + __logf(l);
-        a.delta[(int64_t)h * a.total_nodes + row] = delta;
+          for (int u = 0; u < U; ++u) {
+            const int j = lane + 32 * u;
+            float s_ = -INFINITY;
+            if (j < kt) {
+              s_ = myBias[j];
+#pragma unroll
+              for (int d = 0; d < D; ++d) s_ = fmaf(q[d], sK[j * DP + d], s_);
+            }
+            sv[u] = s_;
+            mx = fmaxf(mx, s_);
+          }
+          mx = warp_max(mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int u = 0; u < U; ++u) sum += (sv[u] == -INFINITY) ? 0.f : __expf(sv[u] - mx);
+          sum = warp_sum(sum);
+          if (lane == 0) {
+            sL[lq] = sL[lq] * __expf(m_old - mx) + sum;
+            sM[lq] = mx;
+          }
+        } else {
+          const float lse = sM[lq] + __logf(sL[lq]);
+          const float delta = sDelta[lq];
+          float dO[D], dq[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) { dO[d] = sdO[lq * DP + d]; dq[d] = 0.f; }
+#pragma unroll 2
+          for (int u = 0; u < U; ++u) {
+            const int j = lane + 32 * u;
+            if (j < kt) {
+              float s_ = myBias[j], dp = 0.f;
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                s_ = fmaf(q[d], sK[j * DP + d], s_);
+                dp = fmaf(dO[d], sV[j * DP + d], dp);
+              }
+              const float p = __expf(s_ - lse);
+              const float ds = p * (dp - delta);
+#pragma unroll
+              for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, sK[j * DP + d], dq[d]);
+              if (a.d_lut != nullptr) atomicAdd(sHist + myPair[j], ds);
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const float v = warp_sum(dq[d]);
+            if (lane == 0) sdQ[lq * DP + d] += v;
+          }
+        }
+        __syncwarp();                          // bias row is overwritten by the next query
       }
     }
   }
   __syncthreads();
+  for (int idx = threadIdx.x; idx < nq * D; idx += blockDim.x) {
+    const int lq = idx / D, d = idx - lq * D;
+    ((T*)a.d_qkv)[(int64_t)(n0 + q0 + lq) * C3 + h * D + d] = from_float<T>(sdQ[lq * DP + d] * scale);
+  }
+  for (int lq = threadIdx.x; lq < nq; lq += blockDim.x) {
+    a.lse[(int64_t)h * a.total_nodes + n0 + q0 + lq] = sM[lq] + __logf(sL[lq]);
+    a.delta[(int64_t)h * a.total_nodes + n0 + q0 + lq] = sDelta[lq];
+  }
   if (a.d_lut != nullptr)
     for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x)
       if (sHist[i] != 0.f) atomicAdd(a.d_lut + (int64_t)h * a.lut_size + i, sHist[i]);
 }
 
+// Kernel B: one CTA = 64 keys of one (graph, head); query tiles are the outer loop.
 template <typename T, int D>
 __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kernel(const ghn3_attention_bwd_args a) {
   extern __shared__ float bw_smem[];
   constexpr int DP = D + 1;
   constexpr int U = kBwdKT / 32;
+  constexpr int KPW = kBwdBlock / kBwdWarps;
   float* sQ = bw_smem;                         // [QT][DP]   (pre-scaled by d^-1/2)
   float* sdO = sQ + kBwdKT * DP;               // [QT][DP]
-  float* sBias = sdO + kBwdKT * DP;            // [warps][QT]
+  float* sKk = sdO + kBwdKT * DP;              // [64][DP] keys owned by the CTA
+  float* sVk = sKk + kBwdBlock * DP;           // [64][DP]
+  float* sdK = sVk + kBwdBlock * DP;           // [64][DP]
+  float* sdV = sdK + kBwdBlock * DP;           // [64][DP]
+  float* sBias = sdV + kBwdBlock * DP;         // [warps][QT]
   float* sLse = sBias + kBwdWarps * kBwdKT;    // [QT]
   float* sDelta = sLse + kBwdKT;               // [QT]
   float* sLut = sDelta + kBwdKT;               // [lut_size]
@@ -346,6 +378,7 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kern
   const int n = a.node_off[g + 1] - n0;
   const int j0 = blockIdx.x * kBwdBlock;
   if (j0 >= n) return;
+  const int nk = min(kBwdBlock, n - j0);
   const int ld = (n + 15) & ~15;
   const int C = a.hid, C3 = 3 * C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,99 +386,88 @@ __global__ void __launch_bounds__(256, (D <= 24) ? 2 : 1) attention_bwd_dkv_kern
   const T* dout = (const T*)a.d_out + (int64_t)n0 * C;
   const uint16_t* pair = a.pair + a.mat_off[g];
   const float scale = rsqrtf((float)D);
-  const bool single = n <= kBwdKT;
   // pair[i][j] = spd_ij * V + spd_ji, so the column j of the bias is row j of `pair` with its two digits swapped
   int V = 1;
   while (V * V < a.lut_size) ++V;
 
-  auto load_queries = [&](int i0, int it) {
-    bwd_load_tile<T, D>(sQ, sdO, qkv + (int64_t)i0 * C3 + h * D, dout + (int64_t)i0 * C + h * D, C3, C, it, scale);
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
+  pdl_wait();
+  bwd_load_tile<T, D>(sKk, qkv + (int64_t)j0 * C3 + C + h * D, C3, nk, 1.f);
+  bwd_load_tile<T, D>(sVk, qkv + (int64_t)j0 * C3 + 2 * C + h * D, C3, nk, 1.f);
+  for (int i = threadIdx.x; i < 2 * kBwdBlock * DP; i += blockDim.x) sdK[i] = 0.f;     // sdK and sdV are adjacent
+
+  float* myBias = sBias + warp * kBwdKT;
+  for (int i0 = 0; i0 < n; i0 += kBwdKT) {
+    const int it = min(kBwdKT, n - i0);
+    __syncthreads();
+    bwd_load_tile<T, D>(sQ, qkv + (int64_t)i0 * C3 + h * D, C3, it, scale);
+    bwd_load_tile<T, D>(sdO, dout + (int64_t)i0 * C + h * D, C, it, 1.f);
     for (int i = threadIdx.x; i < it; i += blockDim.x) {
       sLse[i] = a.lse[(int64_t)h * a.total_nodes + n0 + i0 + i];
       sDelta[i] = a.delta[(int64_t)h * a.total_nodes + n0 + i0 + i];
     }
-  };
-
-  pdl_launch_dependents();
-  for (int i = threadIdx.x; i < a.lut_size; i += blockDim.x) sLut[i] = a.lut[(int64_t)h * a.lut_size + i];
-  pdl_wait();
-  if (single) load_queries(0, n);
-  __syncthreads();
-
-  float* myBias = sBias + warp * kBwdKT;
-  for (int r = 0; r < kBwdBlock / kBwdWarps; ++r) {
-    const int kj = j0 + r * kBwdWarps + warp;
-    const bool ok = kj < n;
-    if (single && !ok) continue;
-    float k[D], v[D], dk[D], dv[D];
-    {
-      const int64_t row = ok ? kj : 0;
+    __syncthreads();
+    for (int r = 0; r < KPW; ++r) {
+      const int lk = r * kBwdWarps + warp;
+      if (lk >= nk) break;
+      const int kj = j0 + lk;
+      for (int i = lane; i < it; i += 32) {
+        const int pt = pair[(int64_t)kj * ld + i0 + i];            // = spd_ji * V + spd_ij
+        myBias[i] = sLut[(pt % V) * V + pt / V];
+      }
+      float k[D], v[D], dk[D], dv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        k[d] = ok ? to_float(qkv[row * C3 + C + h * D + d]) : 0.f;
-        v[d] = ok ? to_float(qkv[row * C3 + 2 * C + h * D + d]) : 0.f;
-        dk[d] = 0.f;
-        dv[d] = 0.f;
-      }
-    }
-    for (int i0 = 0; i0 < n; i0 += kBwdKT) {
-      const int it = min(kBwdKT, n - i0);
-      if (!single) {
-        __syncthreads();
-        load_queries(i0, it);
-      }
-      if (ok) {
-        for (int i = lane; i < it; i += 32) {
-          const int pt = pair[(int64_t)kj * ld + i0 + i];          // = spd_ji * V + spd_ij
-          myBias[i] = sLut[(pt % V) * V + pt / V];
-        }
-      }
-      if (!single) __syncthreads(); else __syncwarp();
-      if (ok) {
+      for (int d = 0; d < D; ++d) { k[d] = sKk[lk * DP + d]; v[d] = sVk[lk * DP + d]; dk[d] = 0.f; dv[d] = 0.f; }
+      __syncwarp();
 #pragma unroll 2
-        for (int u = 0; u < U; ++u) {
-          const int i = lane + 32 * u;
-          if (i < it) {
-            float s_ = myBias[i], dp = 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int i = lane + 32 * u;
+        if (i < it) {
+          float s_ = myBias[i], dp = 0.f;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              s_ = fmaf(sQ[i * DP + d], k[d], s_);
-              dp = fmaf(sdO[i * DP + d], v[d], dp);
-            }
-            const float p = __expf(s_ - sLse[i]);
-            const float ds = p * (dp - sDelta[i]);
+          for (int d = 0; d < D; ++d) {
+            s_ = fmaf(sQ[i * DP + d], k[d], s_);
+            dp = fmaf(sdO[i * DP + d], v[d], dp);
+          }
+          const float p = __expf(s_ - sLse[i]);
+          const float ds = p * (dp - sDelta[i]);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              dv[d] = fmaf(p, sdO[i * DP + d], dv[d]);
-              dk[d] = fmaf(ds, sQ[i * DP + d], dk[d]);             // sQ already carries d^-1/2
-            }
+          for (int d = 0; d < D; ++d) {
+            dv[d] = fmaf(p, sdO[i * DP + d], dv[d]);
+            dk[d] = fmaf(ds, sQ[i * DP + d], dk[d]);               // sQ already carries d^-1/2
           }
         }
       }
-      __syncwarp();
-    }
-    if (ok) {
-      T* dst = (T*)a.d_qkv + (int64_t)(n0 + kj) * C3 + h * D;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const float vk = warp_sum(dk[d]);
         const float vv = warp_sum(dv[d]);
         if (lane == 0) {
-          dst[C + d] = from_float<T>(vk);
-          dst[2 * C + d] = from_float<T>(vv);
+          sdK[lk * DP + d] += vk;
+          sdV[lk * DP + d] += vv;
         }
       }
+      __syncwarp();
     }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nk * D; idx += blockDim.x) {
+    const int lk = idx / D, d = idx - lk * D;
+    T* dst = (T*)a.d_qkv + (int64_t)(n0 + j0 + lk) * C3 + h * D + d;
+    dst[C] = from_float<T>(sdK[lk * DP + d]);
+    dst[2 * C] = from_float<T>(sdV[lk * DP + d]);
   }
 }
 
 template <typename T, int D>
 static int launch_attention_bwd(const ghn3_attention_bwd_args* a, cudaStream_t stream) {
   constexpr int DP = D + 1;
-  const size_t smem_a = sizeof(float) * (2 * kBwdKT * DP + kBwdWarps * kBwdKT + 2 * a->lut_size) +
-                        sizeof(uint16_t) * kBwdWarps * kBwdKT;
-  const size_t smem_b = sizeof(float) * (2 * kBwdKT * DP + kBwdWarps * kBwdKT + 2 * kBwdKT + a->lut_size);
-  GHN3_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "ghn3_attention_bwd: look-up table too large");
+  const size_t smem_a = sizeof(float) * (2 * kBwdKT * DP + 3 * kBwdBlock * DP + 3 * kBwdBlock + kBwdWarps * kBwdKT +
+                                         2 * a->lut_size) + sizeof(uint16_t) * kBwdWarps * kBwdKT;
+  const size_t smem_b = sizeof(float) * (2 * kBwdKT * DP + 4 * kBwdBlock * DP + kBwdWarps * kBwdKT + 2 * kBwdKT +
+                                         a->lut_size);
+  GHN3_REQUIRE(smem_a <= 220 * 1024 && smem_b <= 220 * 1024, "ghn3_attention_bwd: look-up table too large");
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   GHN3_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   const dim3 grid((unsigned)ceil_div(a->max_nodes, kBwdBlock), (unsigned)a->heads, (unsigned)a->n_graphs);

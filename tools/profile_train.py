@@ -9,7 +9,7 @@ from ghn3_b200.weights import CONFIGS, procedural_state_dict
 ap = argparse.ArgumentParser()
 ap.add_argument('--cfg', default='ghn3xlm16')
 ap.add_argument('--dtype', default='bf16')
-ap.add_argument('--archs', default=','.join(bench.TRAIN_ARCHS))
+ap.add_argument('--archs', default='netgen', help="'netgen' = NetGenerator(0).sample(8), else comma-separated torchvision names")
 a = ap.parse_args()
 dev = torch.device('cuda')
 cfg = CONFIGS[a.cfg]
@@ -17,9 +17,15 @@ records = bench.load_records()
 ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=a.dtype)
 ghn.load_state_dict(procedural_state_dict(cfg, 0))
 ghn = ghn.to(dev).train()
-archs = a.archs.split(',')
-graphs = GraphBatch([Graph.from_record(records[x]) for x in archs], dense=True).to_device(dev)
-nets = [bench.build_model(x).to(dev) for x in archs]
+if a.archs == 'netgen':
+    from ghn3_b200.deepnets import NetGenerator
+    pairs = NetGenerator(seed=0).sample(8)
+    graphs = GraphBatch([g for _, g in pairs], dense=True).to_device(dev)
+    nets = [n.to(dev) for n, _ in pairs]
+else:
+    archs = a.archs.split(',')
+    graphs = GraphBatch([Graph.from_record(records[x]) for x in archs], dense=True).to_device(dev)
+    nets = [bench.build_model(x).to(dev) for x in archs]
 opt = torch.optim.AdamW(ghn.parameters(), lr=4e-4, weight_decay=1e-2)
 
 

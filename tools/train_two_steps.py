@@ -13,10 +13,12 @@ records = bench.load_records()
 ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
 ghn.load_state_dict(procedural_state_dict(cfg, 0))
 ghn = ghn.to(dev).train()
-archs = bench.TRAIN_ARCHS
-graphs = GraphBatch([Graph.from_record(records[x]) for x in archs], dense=True).to_device(dev)
-nets = [bench.build_model(x).to(dev) for x in archs]
-opt = torch.optim.AdamW(ghn.parameters(), lr=4e-4, weight_decay=1e-2, fused=True)
+from ghn3_b200.deepnets import NetGenerator
+from ghn3_b200.optim import FusedAdamW
+pairs = NetGenerator(seed=0).sample(bench.TRAIN_META_BATCH)          # the bench's training meta-batch
+graphs = GraphBatch([g for _, g in pairs], dense=True).to_device(dev)
+nets = [n.to(dev) for n, _ in pairs]
+opt = FusedAdamW(ghn, lr=4e-4, weight_decay=1e-2, max_grad_norm=5)
 for it in range(2):
     if it == 1:
         torch.cuda.synchronize()
@@ -24,7 +26,6 @@ for it in range(2):
     opt.zero_grad(set_to_none=True)
     ghn(nets, graphs, keep_grads=True, reduce_graph=True)
     (ghn.last_program.pred_flat.sum() * 1e-3).backward()
-    torch.nn.utils.clip_grad_norm_(ghn.parameters(), 5)
     opt.step()
     torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
