@@ -67,7 +67,7 @@ class GemmSimtArgs(C.Structure):
 class AttentionArgs(C.Structure):
     _fields_ = [('n_graphs', i32), ('hid', i32), ('heads', i32), ('max_nodes', i32), ('lut_size', i32),
                 ('node_off', vp), ('mat_off', vp), ('qkv', vp), ('dtype', i32), ('pair', vp), ('lut', vp),
-                ('out', vp)]
+                ('out', vp), ('lse2', vp), ('total_nodes', i32)]
 
 
 class LayerWeights(C.Structure):
@@ -159,7 +159,13 @@ class LayerNormBwdArgs(C.Structure):
 class AttentionBwdArgs(C.Structure):
     _fields_ = [('n_graphs', i32), ('hid', i32), ('heads', i32), ('max_nodes', i32), ('total_nodes', i32),
                 ('lut_size', i32), ('node_off', vp), ('mat_off', vp), ('qkv', vp), ('out', vp), ('d_out', vp),
-                ('dtype', i32), ('pair', vp), ('lut', vp), ('d_qkv', vp), ('d_lut', vp), ('lse', vp), ('delta', vp)]
+                ('dtype', i32), ('pair', vp), ('lut', vp), ('d_qkv', vp), ('d_lut', vp), ('lse', vp), ('delta', vp),
+                ('fwd_lse2', vp), ('ds_total', vp)]
+
+
+class LutBinArgs(C.Structure):
+    _fields_ = [('n_graphs', i32), ('heads', i32), ('max_nodes', i32), ('lut_size', i32), ('node_off', vp),
+                ('mat_off', vp), ('pair', vp), ('ds_total', vp), ('d_lut', vp)]
 
 
 class ScatterBwdArgs(C.Structure):
@@ -212,7 +218,7 @@ class MemsetArgs(C.Structure):
 
 class GraphormerTrainArgs(C.Structure):
     _fields_ = [('fwd', GraphormerArgs), ('xs', vp), ('xm', vp), ('h1', vp), ('qkv', vp), ('ao', vp), ('h2', vp),
-                ('u', vp), ('g', vp)]
+                ('u', vp), ('g', vp), ('lse2', vp)]
 
 
 class LayerWeightsT(C.Structure):
@@ -228,7 +234,8 @@ class GraphormerBwdArgs(C.Structure):
     _fields_ = [('saved', C.POINTER(GraphormerTrainArgs)), ('layers_t_host', C.POINTER(LayerWeightsT)),
                 ('grads_host', C.POINTER(LayerGrads)), ('d_ln_w', vp), ('d_ln_b', vp), ('d_dec_in', vp),
                 ('d_dec_dtype', i32), ('d_lut', vp), ('dx', vp), ('dxa', vp), ('dh', vp), ('dhf', vp), ('dqkv', vp),
-                ('dff', vp), ('ta', vp), ('tb', vp), ('m_pad', i32), ('lse', vp), ('delta', vp)]
+                ('dff', vp), ('ta', vp), ('tb', vp), ('m_pad', i32), ('lse', vp), ('delta', vp), ('ds_total', vp),
+                ('ds_total_bytes', i64)]
 
 
 assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
@@ -238,7 +245,7 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
-                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw']
+                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin']
 SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None

@@ -478,11 +478,14 @@ static int launch_attention_bwd(const ghn3_attention_bwd_args* a, cudaStream_t s
   return GHN3_OK;
 }
 
+int attention_bwd_mma_impl(const ghn3_attention_bwd_args* a, cudaStream_t stream);
+
 int attention_bwd_impl(const ghn3_attention_bwd_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_attention_bwd: null args");
   GHN3_REQUIRE(a->heads > 0 && a->hid % a->heads == 0, "ghn3_attention_bwd: hid must be divisible by heads");
   GHN3_REQUIRE(a->lse != nullptr && a->delta != nullptr, "ghn3_attention_bwd: lse / delta workspaces are required");
   if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
+  if (a->dtype == GHN3_BF16 && a->fwd_lse2 != nullptr) return attention_bwd_mma_impl(a, stream);
   const int D = a->hid / a->heads;
   const bool bf = a->dtype == GHN3_BF16;
 #define GHN3_ATTN_BWD_CASE(DV) \

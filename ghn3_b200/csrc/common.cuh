@@ -70,6 +70,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// mma.sync m16n8k16 bf16 x bf16 -> fp32 (flash-attention register layout) and bf16 pair packing
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+
 int num_sms();
 
 // Programmatic dependent launch (PDL): a kernel launched with launch_pdl may start while its predecessor in the

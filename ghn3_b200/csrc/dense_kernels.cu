@@ -255,18 +255,6 @@ __global__ void __launch_bounds__(kAttnWarps * 32, (D <= 24) ? 2 : 1) attention_
 // as 32-bit words straight from global memory, issued before the QK^T MMAs so their latency overlaps), softmax is
 // the usual online form with quad shuffles, P is re-packed in registers as the A operand of P.V.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-      "{%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *(uint32_t*)&v;
-}
-
 constexpr int kMmaKT = 256;      // keys staged per outer iteration
 constexpr int kMmaWarps = 8;
 constexpr int kMmaQT = 16 * kMmaWarps;       // queries per CTA
@@ -482,6 +470,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attention_mma_kernel(const ghn
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (a.lse2 != nullptr && tq == 0) {          // softmax statistics for the backward pass (log2 domain)
+    if (ok0) a.lse2[(int64_t)h * a.total_nodes + n0 + r0] = m0 + log2f(l0);
+    if (ok1) a.lse2[(int64_t)h * a.total_nodes + n0 + r1] = m1 + log2f(l1);
+  }
   __nv_bfloat16* out = (__nv_bfloat16*)a.out;
 #pragma unroll
   for (int i = 0; i < NT2; ++i) {

@@ -123,6 +123,8 @@ int graphormer_train_fwd_impl(const ghn3_graphormer_train_args* t, cudaStream_t 
     at_.n_graphs = f.n_graphs; at_.hid = C; at_.heads = f.heads; at_.max_nodes = f.max_nodes;
     at_.lut_size = f.lut_size; at_.node_off = f.node_off; at_.mat_off = f.mat_off;
     at_.qkv = qkv; at_.dtype = c.act_dt; at_.pair = f.pair; at_.lut = f.lut; at_.out = ao;
+    at_.total_nodes = M;
+    at_.lse2 = (t->lse2 != nullptr && c.act_dt == GHN3_BF16) ? t->lse2 + (size_t)l * f.heads * M : nullptr;
     GHN3_TRY(attention_impl(&at_, stream));
 
     GHN3_CUDA(cudaMemcpyAsync(xm, x, xbytes, cudaMemcpyDeviceToDevice, stream));
@@ -161,6 +163,9 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
   GHN3_REQUIRE(mp >= M && mp % 8 == 0, "ghn3_graphormer_bwd: m_pad must be a multiple of 8 and >= total_nodes");
   const ghn3_stream_t s_ = (ghn3_stream_t)stream;
 
+  // tensor-core attention backward: needs the forward's softmax statistics and the dS accumulation scratch
+  const bool mma_attn = adt == GHN3_BF16 && t->lse2 != nullptr && b->ds_total != nullptr;
+  if (mma_attn) GHN3_CUDA(cudaMemsetAsync(b->ds_total, 0, (size_t)b->ds_total_bytes, stream));
   // final LayerNorm: dx = LN'(xs[L]) . gather(d_dec_in)
   GHN3_CUDA(cudaMemsetAsync(b->dx, 0, sizeof(float) * (size_t)M * C, stream));
   {
@@ -224,6 +229,10 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
       ab.lut_size = f.lut_size; ab.node_off = f.node_off; ab.mat_off = f.mat_off;
       ab.qkv = qkv; ab.out = ao; ab.d_out = b->dh; ab.dtype = adt == GHN3_BF16 ? GHN3_BF16 : GHN3_F32;
       ab.pair = f.pair; ab.lut = f.lut; ab.d_qkv = b->dqkv; ab.d_lut = b->d_lut; ab.lse = b->lse; ab.delta = b->delta;
+      if (mma_attn) {
+        ab.fwd_lse2 = t->lse2 + (size_t)l * f.heads * M;
+        ab.ds_total = b->d_lut != nullptr ? b->ds_total : nullptr;
+      }
       GHN3_TRY(attention_bwd_impl(&ab, stream));
     }
     // ---- QKV projection: qkv = h1 Wqkv^T ----
@@ -241,6 +250,12 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
       lb.dx = b->dx; lb.accumulate = 1; lb.dgamma = gr.ln1_w; lb.dbeta = gr.ln1_b;
       GHN3_TRY(ghn3_layernorm_bwd(&lb, s_));
     }
+  }
+  if (mma_attn && b->d_lut != nullptr) {       // edge-bias gradient of all layers at once
+    ghn3_lut_bin_args lb = {};
+    lb.n_graphs = f.n_graphs; lb.heads = f.heads; lb.max_nodes = f.max_nodes; lb.lut_size = f.lut_size;
+    lb.node_off = f.node_off; lb.mat_off = f.mat_off; lb.pair = f.pair; lb.ds_total = b->ds_total; lb.d_lut = b->d_lut;
+    GHN3_TRY(ghn3_lut_bin(&lb, s_));
   }
   return GHN3_OK;
 }

@@ -553,7 +553,9 @@ class _Program:
             Lh = ghn.layers
             self.sv = dict(xm=E(Lh, N, C, dtype=torch.float32), h1=E(Lh, N, C), qkv=E(Lh, N, 3 * C), ao=E(Lh, N, C),
                            h2=E(Lh, N, C), u=E(Lh, N, 4 * C), g=E(Lh, N, 4 * C))
-            self.ta = L.GraphormerTrainArgs(fwd=self.ga, xs=L.ptr(self.xs),
+            # bf16: the tensor-core attention keeps its softmax statistics for the tensor-core backward
+            self.lse2 = E(Lh, H, N, dtype=torch.float32) if act == ops.BF16 else None
+            self.ta = L.GraphormerTrainArgs(fwd=self.ga, xs=L.ptr(self.xs), lse2=L.ptr(self.lse2),
                                             **{k_: L.ptr(v_) for k_, v_ in self.sv.items()})
             self.ga = self.ta.fwd            # the struct was copied by value: patch THIS copy in bind_pack
             self.ops.append(('graphormer', 'graphormer_train_fwd', self.ta))

@@ -234,13 +234,15 @@ def gemm_simt(a_ptr_tensor, sam, sak, b, sbn, sbk, bias, d, sdm, sdn, m, n, k, r
     return d
 
 
-def attention(qkv, pack, lut, hid, heads, dtype=BF16, out=None):
+def attention(qkv, pack, lut, hid, heads, dtype=BF16, out=None, lse2=None):
+    """lse2 (optional, bf16 path): [heads, nodes] fp32 tensor that receives the log2-domain softmax statistics."""
     _require_cuda(qkv, 'qkv')
     if out is None:
         out = torch.empty(qkv.shape[0], hid, dtype=TORCH_DTYPE[dtype], device=qkv.device)
     a = L.AttentionArgs(n_graphs=pack.n_graphs, hid=hid, heads=heads, max_nodes=pack.max_nodes,
                         lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']), mat_off=L.ptr(pack.d['mat_off']),
-                        qkv=L.ptr(qkv), dtype=dtype, pair=L.ptr(pack.pair), lut=L.ptr(lut), out=L.ptr(out))
+                        qkv=L.ptr(qkv), dtype=dtype, pair=L.ptr(pack.pair), lut=L.ptr(lut), out=L.ptr(out),
+                        lse2=L.ptr(lse2), total_nodes=qkv.shape[0])
     L.call('attention', a, L.current_stream())
     return out
 
@@ -311,11 +313,29 @@ def layernorm_bwd(x, gamma, dy, dx, dgamma, dbeta, accumulate=False, dy_row=None
     return dx
 
 
-def attention_bwd(qkv, out, d_out, pack, lut, hid, heads, d_lut=None):
+def attention_bwd(qkv, out, d_out, pack, lut, hid, heads, d_lut=None, fwd_lse2=None):
+    """fwd_lse2 (bf16 only): statistics kept by attention(..., lse2=...) -> tensor-core kernels; the edge-bias gradient
+    then goes through a dS accumulation buffer and one binning pass (as the training program does for all layers)."""
     _require_cuda(qkv, 'qkv')
     M = qkv.shape[0]
     d_qkv = torch.empty_like(qkv)
     ws = torch.empty(2, heads, M, dtype=torch.float32, device=qkv.device)
+    if fwd_lse2 is not None:
+        ds_total = None
+        if d_lut is not None:
+            ds_total = torch.zeros(int(pack.mat_off[-1]) * heads, dtype=torch.float32, device=qkv.device)
+        a = L.AttentionBwdArgs(n_graphs=pack.n_graphs, hid=hid, heads=heads, max_nodes=pack.max_nodes, total_nodes=M,
+                               lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']),
+                               mat_off=L.ptr(pack.d['mat_off']), qkv=L.ptr(qkv), out=L.ptr(out), d_out=L.ptr(d_out),
+                               dtype=_dt(qkv), pair=L.ptr(pack.pair), lut=L.ptr(lut), d_qkv=L.ptr(d_qkv), d_lut=None,
+                               lse=L.ptr(ws[0]), delta=L.ptr(ws[1]), fwd_lse2=L.ptr(fwd_lse2), ds_total=L.ptr(ds_total))
+        L.call('attention_bwd', a, L.current_stream())
+        if d_lut is not None:
+            b = L.LutBinArgs(n_graphs=pack.n_graphs, heads=heads, max_nodes=pack.max_nodes, lut_size=lut.shape[1],
+                             node_off=L.ptr(pack.d['node_off']), mat_off=L.ptr(pack.d['mat_off']),
+                             pair=L.ptr(pack.pair), ds_total=L.ptr(ds_total), d_lut=L.ptr(d_lut))
+            L.call('lut_bin', b, L.current_stream())
+        return d_qkv
     a = L.AttentionBwdArgs(n_graphs=pack.n_graphs, hid=hid, heads=heads, max_nodes=pack.max_nodes, total_nodes=M,
                            lut_size=lut.shape[1], node_off=L.ptr(pack.d['node_off']), mat_off=L.ptr(pack.d['mat_off']),
                            qkv=L.ptr(qkv), out=L.ptr(out), d_out=L.ptr(d_out), dtype=_dt(qkv), pair=L.ptr(pack.pair),

@@ -377,6 +377,11 @@ class _Backward:
         dev = prog.device
         vmax = pack.cutoff
         lut_size = (vmax + 1) ** 2
+        if prog.lse2 is not None:                  # tensor-core attention backward: dS accumulation scratch
+            need = int(pack.mat_off[-1]) * self.ghn.heads
+            if getattr(self, 'ds_total', None) is None or self.ds_total.numel() < need:
+                self.ds_total = torch.empty(max(need, 1), dtype=torch.float32, device=dev)
+            self.gb.ds_total, self.gb.ds_total_bytes = self.ds_total.data_ptr(), need * 4
         if self.d_lut is None or self.d_lut.shape[1] != lut_size:
             self.d_lut = torch.zeros(self.ghn.heads, lut_size, dtype=torch.float32, device=dev)
             self.lut_ws = torch.empty(4 * (vmax + 1) * self.ghn.hid, dtype=torch.float32, device=dev)

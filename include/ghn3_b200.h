@@ -257,6 +257,10 @@ typedef struct {
   const uint16_t* pair;
   const float* lut;          /* [H][lut_size] */
   void* out;                 /* [total_nodes][C] in dtype */
+  /* optional (GHN3_BF16 only): log2-domain softmax statistics m + log2(l) of every (head, node) row,
+   * [H][total_nodes] fp32, kept for ghn3_attention_bwd's tensor-core path */
+  float* lse2;
+  int32_t total_nodes;
 } ghn3_attention_args;
 
 int ghn3_attention(const ghn3_attention_args* args, ghn3_stream_t stream);
@@ -448,8 +452,26 @@ typedef struct {
   void* d_qkv;               /* out [M][3C] */
   float* d_lut;              /* += [H][lut_size], may be NULL */
   float* lse; float* delta;  /* workspaces [H][total_nodes] */
+  /* Tensor-core path (dtype GHN3_BF16 and fwd_lse2 != NULL): mma.sync kernels that take the softmax statistics the
+   * forward kept (ghn3_attention_args.lse2) instead of recomputing them. The edge-bias gradient is then NOT added to
+   * d_lut; dS is accumulated into ds_total (fp32, graph g / head h plane at mat_off[g] * heads + h * n_g * ld_g,
+   * caller-zeroed, may be NULL when the bias gradient is not wanted) and binned once by ghn3_lut_bin. */
+  const float* fwd_lse2;
+  float* ds_total;
 } ghn3_attention_bwd_args;
 int ghn3_attention_bwd(const ghn3_attention_bwd_args* args, ghn3_stream_t stream);
+
+/* d_lut[h][pair[i][j]] += ds_total[g][h][i][j]: the edge-bias gradient of ALL layers in one pass (the bias is shared by
+ * the layers, ghn3/graphormer.py:126-130). */
+typedef struct {
+  int32_t n_graphs, heads, max_nodes, lut_size;
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  const uint16_t* pair;
+  const float* ds_total;
+  float* d_lut;              /* += [H][lut_size] */
+} ghn3_lut_bin_args;
+int ghn3_lut_bin(const ghn3_lut_bin_args* args, ghn3_stream_t stream);
 
 /* Adjoint of ghn3_scatter: grads[i] is the gradient of the i-th target tensor (NULL: none), d_src[i] the fp32
  * gradient buffer parallel to descs[i].src (same indexing); contributions are added atomically. */
@@ -556,6 +578,7 @@ typedef struct {
   void* h2;                  /* [L][M][C]   LN2 output */
   void* u;                   /* [L][M][4C]  FFN pre-activation */
   void* g;                   /* [L][M][4C]  GELU(u) */
+  float* lse2;               /* optional [L][H][M] fp32: softmax statistics of the bf16 attention (log2 domain) */
 } ghn3_graphormer_train_args;
 int ghn3_graphormer_train_fwd(const ghn3_graphormer_train_args* args, ghn3_stream_t stream);
 
@@ -588,6 +611,9 @@ typedef struct {
   void* ta; void* tb;        /* [4C][m_pad] activation dtype (transposed operands of the wgrad GEMMs) */
   int32_t m_pad;             /* multiple of 8, >= total_nodes */
   float* lse; float* delta;  /* [H][M] */
+  float* ds_total;           /* optional [mat_total * H] fp32 scratch (zeroed by the call): with saved->lse2 it enables
+                                the tensor-core attention backward + one ghn3_lut_bin pass */
+  int64_t ds_total_bytes;
 } ghn3_graphormer_bwd_args;
 int ghn3_graphormer_bwd(const ghn3_graphormer_bwd_args* args, ghn3_stream_t stream);
 

@@ -128,8 +128,11 @@ def test_layernorm_bwd_row_gather():
 
 @pytest.mark.parametrize('cfg_name,archs', [('ghn3tiny', 'small'), ('ghn3tm8', 'small'), ('ghn3lm8', 'small'),
                                             ('ghn3xlm16', 'small'), ('ghn3xlm16', 'large'), ('ghn3tiny', 'large')])
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, 'bf16_mma'])
 def test_attention_bwd(cfg_name, archs, dtype):
+    mma = dtype == 'bf16_mma'                  # tensor-core kernels fed by the forward's softmax statistics
+    if mma:
+        dtype = torch.bfloat16
     cfg = CONFIGS[cfg_name]
     C_, H_ = cfg['hid'], cfg['heads']
     D = C_ // H_
@@ -142,10 +145,10 @@ def test_attention_bwd(cfg_name, archs, dtype):
     qkv = torch.randn(N, 3 * C_, device=DEV).to(dtype)
     d_out = torch.randn(N, C_, device=DEV).to(dtype)
     lut = (torch.randn(H_, 51 * 51, device=DEV) * 0.5)
-    out = ops.attention(qkv if dtype == torch.bfloat16 else qkv, pack, lut, C_, H_,
-                        dtype=ops.BF16 if dtype == torch.bfloat16 else ops.F32)
+    lse2 = torch.zeros(H_, N, device=DEV) if mma else None
+    out = ops.attention(qkv, pack, lut, C_, H_, dtype=ops.BF16 if dtype == torch.bfloat16 else ops.F32, lse2=lse2)
     d_lut = torch.zeros_like(lut)
-    d_qkv = ops.attention_bwd(qkv, out, d_out, pack, lut, C_, H_, d_lut=d_lut)
+    d_qkv = ops.attention_bwd(qkv, out, d_out, pack, lut, C_, H_, d_lut=d_lut, fwd_lse2=lse2)
     torch.cuda.synchronize()
 
     qf = qkv.float().clone().requires_grad_()
