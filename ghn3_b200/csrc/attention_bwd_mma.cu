@@ -16,6 +16,8 @@ namespace ghn3 {
 constexpr int kBmKT = 256;       // columns (keys for A, queries for B) staged per outer iteration
 constexpr int kBmWarps = 8;
 constexpr int kBmRows = 16 * kBmWarps;
+constexpr int kBmChunk = 32;     // columns per inner step: small enough for 2 CTAs per SM (register budget)
+constexpr int kBmNT = kBmChunk / 8, kBmK2 = kBmChunk / 16;
 constexpr float kLog2e = 1.44269504088896340736f;
 constexpr float kLn2 = 0.69314718055994530942f;
 
@@ -81,7 +83,7 @@ __device__ __forceinline__ void bm_row_frags(uint32_t (&fr)[BmDims<D>::KK][4], c
 }
 
 template <int D>
-__global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(const ghn3_attention_bwd_args a) {
+__global__ void __launch_bounds__(kBmWarps * 32, 2) attention_bwd_mma_dq_kernel(const ghn3_attention_bwd_args a) {
   using X = BmDims<D>;
   extern __shared__ __align__(16) uint8_t bm_smem[];
   __nv_bfloat16* sK = (__nv_bfloat16*)bm_smem;                  // [KT][DS]
@@ -149,6 +151,20 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(con
   const uint16_t* prow0 = pair + (int64_t)(ok0 ? r0 : q0) * ld;
   const uint16_t* prow1 = pair + (int64_t)(ok1 ? r1 : q0) * ld;
   float* dsp = a.ds_total != nullptr ? a.ds_total + a.mat_off[g] * a.heads + (int64_t)h * n * ld : nullptr;
+  // edge-bias indices of a 16 x 64 chunk (two columns per 32-bit word), fetched one chunk ahead of their use
+  uint32_t nw0[kBmNT], nw1[kBmNT];
+  auto load_pairs = [&](int cbase) {
+#pragma unroll
+    for (int nt = 0; nt < kBmNT; ++nt) {
+      const int col = cbase + nt * 8 + 2 * tq;
+      nw0[nt] = 0; nw1[nt] = 0;
+      if (warp_active && col < n) {
+        nw0[nt] = __ldg((const uint32_t*)(prow0 + col));
+        nw1[nt] = __ldg((const uint32_t*)(prow1 + col));
+      }
+    }
+  };
+  load_pairs(0);
 
   float o[X::NT2][4];
 #pragma unroll
@@ -161,27 +177,21 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(con
     bm_stage<D>(sV, nullptr, qkv + (int64_t)k0 * C3 + 2 * C + h * D, C3, kt, 1.f);
     __syncthreads();
     if (!warp_active) continue;
-    for (int c0 = 0; c0 < kt; c0 += 64) {
-      uint32_t pw0[8], pw1[8];
+    for (int c0 = 0; c0 < kt; c0 += kBmChunk) {
+      uint32_t pw0[kBmNT], pw1[kBmNT];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = k0 + c0 + nt * 8 + 2 * tq;
-        pw0[nt] = 0; pw1[nt] = 0;
-        if (col < n) {
-          pw0[nt] = __ldg((const uint32_t*)(prow0 + col));
-          pw1[nt] = __ldg((const uint32_t*)(prow1 + col));
-        }
-      }
-      float s[8][4], dp[8][4];
+      for (int nt = 0; nt < kBmNT; ++nt) { pw0[nt] = nw0[nt]; pw1[nt] = nw1[nt]; }
+      if (k0 + c0 + kBmChunk < n) load_pairs(k0 + c0 + kBmChunk);   // next chunk's indices: in flight during this chunk's MMAs
+      float s[kBmNT][4], dp[kBmNT][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBmNT; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
       }
 #pragma unroll
       for (int kk = 0; kk < X::KK; ++kk) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < kBmNT; ++nt) {
           const __nv_bfloat16* kp = sK + (c0 + nt * 8 + gq) * X::DS + kk * 16 + 2 * tq;
           mma_bf16_16816(s[nt], aq[kk], *(const uint32_t*)kp, *(const uint32_t*)(kp + 8));
           const __nv_bfloat16* vp = sV + (c0 + nt * 8 + gq) * X::DS + kk * 16 + 2 * tq;
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(con
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBmNT; ++nt) {
         const int col = k0 + c0 + nt * 8 + 2 * tq;
         const bool v0 = col < n, v1 = col + 1 < n;
         const float p00 = v0 ? exp2f(s[nt][0] + sLut[pw0[nt] & 0xFFFFu] - lse0) : 0.f;
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(con
         }
       }
 #pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
+      for (int k2 = 0; k2 < kBmK2; ++k2) {
         uint32_t ap[4];
         ap[0] = pack_bf16(s[2 * k2][0], s[2 * k2][1]);
         ap[1] = pack_bf16(s[2 * k2][2], s[2 * k2][3]);
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dq_kernel(con
 }
 
 template <int D>
-__global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dkv_kernel(const ghn3_attention_bwd_args a) {
+__global__ void __launch_bounds__(kBmWarps * 32, 2) attention_bwd_mma_dkv_kernel(const ghn3_attention_bwd_args a) {
   using X = BmDims<D>;
   extern __shared__ __align__(16) uint8_t bm_smem[];
   __nv_bfloat16* sQ = (__nv_bfloat16*)bm_smem;                  // [QT][DS]  q * d^-1/2 * log2(e), rounded as forward
@@ -286,6 +296,19 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dkv_kernel(co
   bm_row_frags<D>(av, qkv + 2 * C + h * D, C3, r0, r1, ok0, ok1, tq, 1.f);
   const uint16_t* prow0 = pair + (int64_t)(ok0 ? r0 : j0) * ld;
   const uint16_t* prow1 = pair + (int64_t)(ok1 ? r1 : j0) * ld;
+  uint32_t nw0[kBmNT], nw1[kBmNT];
+  auto load_pairs = [&](int cbase) {
+#pragma unroll
+    for (int nt = 0; nt < kBmNT; ++nt) {
+      const int col = cbase + nt * 8 + 2 * tq;
+      nw0[nt] = 0; nw1[nt] = 0;
+      if (warp_active && col < n) {
+        nw0[nt] = __ldg((const uint32_t*)(prow0 + col));
+        nw1[nt] = __ldg((const uint32_t*)(prow1 + col));
+      }
+    }
+  };
+  load_pairs(0);
 
   float ok_[X::NT2][4], ov[X::NT2][4];
 #pragma unroll
@@ -306,36 +329,30 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dkv_kernel(co
     }
     __syncthreads();
     if (!warp_active) continue;
-    for (int c0 = 0; c0 < it; c0 += 64) {
-      uint32_t pw0[8], pw1[8];
+    for (int c0 = 0; c0 < it; c0 += kBmChunk) {
+      uint32_t pw0[kBmNT], pw1[kBmNT];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = i0 + c0 + nt * 8 + 2 * tq;
-        pw0[nt] = 0; pw1[nt] = 0;
-        if (col < n) {
-          pw0[nt] = __ldg((const uint32_t*)(prow0 + col));
-          pw1[nt] = __ldg((const uint32_t*)(prow1 + col));
-        }
-      }
-      float s[8][4], dp[8][4];
+      for (int nt = 0; nt < kBmNT; ++nt) { pw0[nt] = nw0[nt]; pw1[nt] = nw1[nt]; }
+      if (i0 + c0 + kBmChunk < n) load_pairs(i0 + c0 + kBmChunk);
+      float s[kBmNT][4], dp[kBmNT][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBmNT; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
       }
 #pragma unroll
       for (int kk = 0; kk < X::KK; ++kk) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < kBmNT; ++nt) {
           const __nv_bfloat16* qp = sQ + (c0 + nt * 8 + gq) * X::DS + kk * 16 + 2 * tq;
           mma_bf16_16816(s[nt], ak[kk], *(const uint32_t*)qp, *(const uint32_t*)(qp + 8));
           const __nv_bfloat16* gp = sdO + (c0 + nt * 8 + gq) * X::DS + kk * 16 + 2 * tq;
           mma_bf16_16816(dp[nt], av[kk], *(const uint32_t*)gp, *(const uint32_t*)(gp + 8));
         }
       }
-      float p[8][4];
+      float p[kBmNT][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < kBmNT; ++nt) {
         const int lc = c0 + nt * 8 + 2 * tq;             // column inside the staged tile
         const bool v0 = i0 + lc < n, v1 = i0 + lc + 1 < n;
         const float le0 = sLse[lc], le1 = sLse[lc + 1], de0 = sDel[lc], de1 = sDel[lc + 1];
@@ -349,7 +366,7 @@ __global__ void __launch_bounds__(kBmWarps * 32) attention_bwd_mma_dkv_kernel(co
         s[nt][3] = p[nt][3] * (dp[nt][3] - de1);
       }
 #pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
+      for (int k2 = 0; k2 < kBmK2; ++k2) {
         uint32_t ap[4], as_[4];
         ap[0] = pack_bf16(p[2 * k2][0], p[2 * k2][1]);
         ap[1] = pack_bf16(p[2 * k2][2], p[2 * k2][3]);
