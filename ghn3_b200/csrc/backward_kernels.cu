@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invC = 1.f / (float)C;
+  float ga[kLnMaxT], ba[kLnMaxT];            // this lane's dgamma / dbeta partial sums over the rows of its warp
+#pragma unroll
+  for (int t = 0; t < kLnMaxT; ++t) { ga[t] = 0.f; ba[t] = 0.f; }
   for (int row = blockIdx.x * 8 + warp; row < a.rows; row += gridDim.x * 8) {
     const int64_t dyr = a.dy_row ? a.dy_row[row] : row;
     if (dyr < 0) continue;                     // no gradient reaches this row through this LayerNorm
@@ -146,8 +149,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
         gv[t] = g;
         s1 += g;
         s2 += g * xh;
-        atomicAdd(sG + c, dy * xh);
-        atomicAdd(sB + c, dy);
+        ga[t] += dy * xh;
+        ba[t] += dy;
       } else {
         gv[t] = 0.f;
       }
@@ -162,6 +165,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
         const float v = rstd * (gv[t] - s1 - xv[t] * s2);
         dx[c] = a.accumulate ? dx[c] + v : v;
       }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kLnMaxT; ++t) {
+    const int c = lane + 32 * t;
+    if (c < C) {
+      if (ga[t] != 0.f) atomicAdd(sG + c, ga[t]);
+      if (ba[t] != 0.f) atomicAdd(sB + c, ba[t]);
     }
   }
   __syncthreads();
@@ -942,7 +953,8 @@ extern "C" int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* a, ghn3_stream_
   GHN3_REQUIRE(a->hid > 0 && a->hid <= 32 * kLnMaxT, "ghn3_layernorm_bwd: hid must be <= 1024");
   GHN3_REQUIRE(a->x && a->gamma && a->dy && a->dx && a->dgamma && a->dbeta, "ghn3_layernorm_bwd: null pointer");
   if (a->rows <= 0) return GHN3_OK;
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 8), (int64_t)num_sms() * 2);
+  // few CTAs, several rows per warp: the per-column global atomics at the end scale with the CTA count
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 16), (int64_t)num_sms());
   GHN3_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), sizeof(float) * 2 * a->hid, stream, *a));
   GHN3_LAUNCH_CHECK("layernorm_bwd_kernel");
   return GHN3_OK;

@@ -22,14 +22,15 @@ def _loss_weights(tensors, seed=3):
     return [torch.randn(t.shape, generator=g) for t in tensors]
 
 
-def _cuda_grads(cfg_name, dtype, archs, recs, all_R):
+def _cuda_grads(cfg_name, dtype, archs, recs, all_R, predict_class_layers=True, weight_norm=True):
     cfg = CONFIGS[cfg_name]
-    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+    ghn = GHN3(**cfg, weight_norm=weight_norm, ve=True, compute_dtype=dtype)
     ghn.load_state_dict(procedural_state_dict(cfg, 0))
     ghn = ghn.to(DEV).train()
     models = [H.build_model(a).to(DEV) for a in archs]
     graphs = [Graph.from_record(r) for r in recs]
-    out = ghn(models if len(models) > 1 else models[0], graphs if len(graphs) > 1 else graphs[0], keep_grads=True)
+    out = ghn(models if len(models) > 1 else models[0], graphs if len(graphs) > 1 else graphs[0], keep_grads=True,
+              predict_class_layers=predict_class_layers)
     out = out if isinstance(out, list) else [out]
     loss = 0.
     for model, arch, Rs in zip(out, archs, all_R):
@@ -45,16 +46,19 @@ def _cuda_grads(cfg_name, dtype, archs, recs, all_R):
     return {k: p.grad for k, p in ghn.named_parameters()}, float(loss)
 
 
-def _run(cfg_name, archs, dtype):
+def _run(cfg_name, archs, dtype, **flags):
     cfg = CONFIGS[cfg_name]
     recs = [H.graph_records()[a] for a in archs]
-    sd_grads, all_R, ref_loss = _oracle_grads_named(cfg, archs, recs)
-    grads, loss = _cuda_grads(cfg_name, dtype, archs, recs, all_R)
+    sd_grads, all_R, ref_loss = _oracle_grads_named(cfg, archs, recs, **flags)
+    grads, loss = _cuda_grads(cfg_name, dtype, archs, recs, all_R, **flags)
     if not any(a.startswith('vit') for a in archs):      # ViT class-token rows are fresh random draws (nn.py:446)
         assert abs(loss - ref_loss) <= 5 * GTOL[dtype] * max(1.0, abs(ref_loss)), (loss, ref_loss)
     worst, bad = {}, {}
     for k, ref in sd_grads.items():
         g = grads[k]
+        if ref is None:                                   # tensor not on the path (e.g. class heads switched off)
+            assert g is None or float(g.abs().max()) == 0.0, k
+            continue
         assert g is not None, k
         g = g.float().cpu()
         denom = float(ref.abs().max())
@@ -93,7 +97,7 @@ def _run(cfg_name, archs, dtype):
     assert not bad, bad
 
 
-def _oracle_grads_named(cfg, archs, recs):
+def _oracle_grads_named(cfg, archs, recs, predict_class_layers=True, weight_norm=True):
     sd = {k: v.clone().requires_grad_(True) for k, v in procedural_state_dict(cfg, 0).items()}
     loss = 0.
     all_R = []
@@ -101,7 +105,7 @@ def _oracle_grads_named(cfg, archs, recs):
         model = H.build_model(arch)
         for n, m in model.named_modules():
             m.__dict__['_ghn3_name'] = n
-        out = O.predict_keep_grads(sd, cfg, model, O.graph_from_record(rec))
+        out = O.predict_keep_grads(sd, cfg, model, O.graph_from_record(rec), predict_class_layers, weight_norm)
         R = _loss_weights([t for _, _, t in out])
         all_R.append([(m, key, r) for (m, key, _), r in zip(out, R)])
         loss = loss + sum((t * r).sum() for (_, _, t), r in zip(out, R))
@@ -125,6 +129,51 @@ def test_tiny_gradients_batch_of_graphs(dtype):
 def test_tiny_gradients_deepnets_style_cell_network(dtype):
     """BASELINE config 5 targets: a NetGenerator-sampled cell network (per-cell node_info, `_n_cells` > 1)."""
     _run('ghn3tiny', ['cellnet7', 'cellnet1'], dtype)
+
+
+@pytest.mark.parametrize('flags', [dict(predict_class_layers=False), dict(weight_norm=False)])
+def test_tiny_gradients_forward_flags(flags):
+    """predict_class_layers=False removes the class heads from the graph of the loss (their GHN weights get no
+    gradient); weight_norm=False bypasses the fan-in scale / 2*sigmoid / tanh squashes (nn.py:516-517)."""
+    _run('ghn3tiny', ['resnet18', 'mobilenet_v3_small'], 'tf32', **flags)
+
+
+def test_sgd_steps_track_the_oracle():
+    """three plain-SGD steps through the CUDA path and through autograd on the oracle, same loss: the GHN weights must
+    stay together (end-to-end check of forward, backward, in-place weight refresh)."""
+    cfg = CONFIGS['ghn3tiny']
+    rec = H.graph_records()['resnet18']
+    lr = 5e-3
+    torch.manual_seed(11)
+    probe = H.build_model('resnet18')
+    R = {n: torch.randn(p.shape) for n, p in probe.named_parameters()}
+    # oracle
+    sd = {k: v.clone().requires_grad_(True) for k, v in procedural_state_dict(cfg, 0).items()}
+    for _ in range(3):
+        model = H.build_model('resnet18')
+        names = {id(m): n for n, m in model.named_modules()}
+        out = O.predict_keep_grads(sd, cfg, model, O.graph_from_record(rec))
+        loss = sum((t * R[(names[id(m)] + '.' if names[id(m)] else '') + key]).sum() for m, key, t in out)
+        grads = torch.autograd.grad(loss, list(sd.values()), allow_unused=True)
+        with torch.no_grad():
+            for v, g in zip(sd.values(), grads):
+                if g is not None:
+                    v -= lr * g
+    # CUDA
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    opt = torch.optim.SGD(ghn.parameters(), lr=lr)
+    graph = Graph.from_record(rec)
+    for _ in range(3):
+        model = ghn(H.build_model('resnet18').to(DEV), graph, keep_grads=True)
+        loss = sum((p * R[n].to(DEV)).sum() for n, p in model.named_parameters())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    for k, p in ghn.named_parameters():
+        ref = sd[k].detach()
+        assert float((p.detach().cpu() - ref).norm() / (ref.norm() + 1e-12)) < 1e-4, k
 
 
 def test_tm8_gradients_resnet50():
