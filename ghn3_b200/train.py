@@ -494,8 +494,14 @@ class _PredictFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
         prog.bind_pack(pack)
         total = out_meta['total']
-        pred = torch.zeros(total, dtype=torch.float32, device=prog.device)      # padding between slices stays 0
-        prog.point_descriptors_at(pred, out_meta, ghn.weight_norm)
+        # One flat buffer per program, reused by every step (like the saved activations): its address is stable, so
+        # the scatter descriptors are uploaded once -- a per-step pageable H2D copy would serialise host and device.
+        # The padding between slices is zeroed once and never written.
+        pred = getattr(prog, 'pred_buf', None)
+        if pred is None or pred.numel() != total or prog.pred_wn != bool(ghn.weight_norm):
+            pred = torch.zeros(total, dtype=torch.float32, device=prog.device)
+            prog.pred_buf, prog.pred_wn = pred, bool(ghn.weight_norm)
+            prog.point_descriptors_at(pred, out_meta, ghn.weight_norm)
         if prog.bp.n_tok_elems:
             prog.tok.normal_(mean=0.0, std=0.02)
         prog.run(getattr(ghn, '_profile', None))
