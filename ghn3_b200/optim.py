@@ -42,6 +42,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._ptrs_host, self._ptrs = None, None
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self._step = 0
+        self._checked = False
 
     def _param_table(self):
         ptrs = [p.data_ptr() for p in self._order]
@@ -56,9 +57,14 @@ class FusedAdamW(torch.optim.Optimizer):
         g0 = self._order[0].grad
         if g0 is not None:
             base = g0.data_ptr()
-            if all(p.grad is not None and p.grad.data_ptr() == base + int(o) * 4 and p.grad.is_contiguous()
-                   for p, o in zip(self._order, self._offs[:-1])):
+            # every gradient handed out by the backward pass is a slice of ONE buffer at the known offsets; the full
+            # check of all tensors runs on the first step, afterwards three sentinels (first, middle, last) suffice
+            idx = range(len(self._order)) if not self._checked else (0, len(self._order) // 2, len(self._order) - 1)
+            if all(self._order[i].grad is not None and self._order[i].grad.is_contiguous() and
+                   self._order[i].grad.data_ptr() == base + int(self._offs[i]) * 4 for i in idx):
+                self._checked = True
                 return base, None
+            self._checked = False
         if self._own_grads is None:
             self._own_grads = torch.zeros(self._total, dtype=torch.float32, device=self._dev)
         flat = self._own_grads

@@ -558,20 +558,28 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
         shifts = [int(s) for s in bp.desc_dst_shift]
         meta['out_index'] = [(index[i], shifts[i], bp.desc_targets[i][3] != 'tok') for i in range(len(index))]
         bp.out_meta = meta
-    outs = _PredictFn.apply(ghn, prog, graphs.pack, meta, meta['out_index'], *list(ghn.parameters()))
-    done = set()
-    for (module, attr), oi in zip(meta['targets'], meta['desc_out']):
-        key = (id(module), attr)
-        if key in done:
-            continue
-        done.add(key)
+    plist = ghn.__dict__.get('_param_list') or list(ghn.parameters())
+    outs = _PredictFn.apply(ghn, prog, graphs.pack, meta, meta['out_index'], *plist)
+    # assignment as in nn.py:526-545; the (module dict, parameter dict, attribute, output) table is built once
+    assign = meta.get('assign')
+    if assign is None:
+        assign, done = [], set()
+        for (module, attr), oi in zip(meta['targets'], meta['desc_out']):
+            key = (id(module), attr)
+            if key in done:
+                continue
+            done.add(key)
+            cur = module.__dict__.get(attr, module._parameters.get(attr) if hasattr(module, '_parameters') else None)
+            light = isinstance(cur, (list, tuple))         # light modules keep shapes, not parameters (nn.py:527-533)
+            assign.append((module if light else module.__dict__, None if light else module._parameters, attr, oi))
+        meta['assign'] = assign
+    for d, params, attr, oi in assign:
         t = outs[oi]
-        cur = module.__dict__.get(attr, module._parameters.get(attr) if hasattr(module, '_parameters') else None)
-        if isinstance(cur, (list, tuple)):                 # light modules keep shapes, not parameters (nn.py:527-533)
-            setattr(module, attr, t)
+        if params is None:
+            setattr(d, attr, t)
         else:
-            module.__dict__[attr] = t                      # nn.py:536-539
-            module._parameters[attr] = t
+            d[attr] = t                                    # nn.py:536-539
+            params[attr] = t
     ghn.last_program = prog
     # every predicted parameter is a slice of this flat tensor (same autograd node): a loss written on it, e.g. the
     # <p, R> stub of the GHN-only training benchmark, costs one kernel instead of one per parameter
