@@ -72,10 +72,14 @@ class AvgMeter:
 
 class Trainer:
     def __init__(self, model, opt='adamw', opt_args=None, scheduler=None, n_batches=None, grad_clip=5,
-                 device='cuda', log_interval=100, label_smoothing=0, predparam_wd=0, verbose=False, **unused):
+                 device='cuda', log_interval=100, label_smoothing=0, predparam_wd=0, verbose=False, amp=False,
+                 **unused):
         self.criterion = nn.CrossEntropyLoss(label_smoothing=label_smoothing)
         self.n_batches, self.grad_clip, self.device = n_batches, grad_clip, device
         self.log_interval, self.predparam_wd, self.verbose = log_interval, predparam_wd, verbose
+        # amp: the TARGET networks run under bf16 autocast (the reference uses fp16 autocast + GradScaler,
+        # trainer.py:269,343-379; bf16 needs no loss scaling). The GHN itself always computes in its compute_dtype.
+        self.amp = amp
         self.ddp = is_ddp()
         model.to(device)
         self._model = model
@@ -148,11 +152,12 @@ class Trainer:
             targets = targets.to(self.device, non_blocking=True)
             images = images.to(self.device, non_blocking=True)
             loss, logits = 0, []
-            for model in models:
-                out = model(images)
-                y = out[0] if isinstance(out, tuple) else out
-                loss = loss + self.criterion(y, targets)
-                logits.append(y.detach())
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
+                for model in models:
+                    out = model(images)
+                    y = out[0] if isinstance(out, tuple) else out
+                    loss = loss + self.criterion(y.float(), targets)
+                    logits.append(y.detach().float())
             logits = torch.stack(logits)
         if loss_predwd is not None:
             loss = loss + loss_predwd
