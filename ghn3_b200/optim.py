@@ -4,8 +4,6 @@ gradient buffer the hand-written backward pass produces. Replaces `nn.utils.clip
 `torch.optim.AdamW.step` of the reference's `Trainer.update` (ghn3/trainer.py:343-379): no per-tensor norm kernels, no
 host synchronisation, 7 HBM passes over the parameters' bytes instead of ~12.
 """
-import ctypes as ct
-
 import numpy as np
 import torch
 

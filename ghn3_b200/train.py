@@ -16,7 +16,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .plan import SRC_CLSB, SRC_CLSW, SRC_D1, SRC_TOK, SRC_WOUT
+from .plan import SRC_CLSB, SRC_CLSW, SRC_D1, SRC_WOUT
 
 OPC = {'graphormer_bwd': 8, 'transpose': 9, 'elementwise': 10, 'colsum': 11, 'layernorm_bwd': 12,
        'attention_bwd': 13, 'scatter_bwd': 14, 'node_features_bwd': 15, 'edge_lut_bwd': 16, 'fc_bwd': 17,
