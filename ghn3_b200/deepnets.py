@@ -233,5 +233,6 @@ class NetGenerator:
             graph = Graph(net)
             if device is not None:
                 net = net.to(device)
+            graph.net = net                    # as the reference's loader does (deepnets1m.py:139-142): GraphBatch.nets
             out.append((net, graph))
         return out
