@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ghn3_colsum_args a) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm backward (eps 1e-5): one warp per row, per-block shared accumulators for dgamma / dbeta
-constexpr int kLnMaxT = 32;       // hid <= 1024
-
+// kLnMaxT = ceil(hid / 32) rounded up to an instantiated size: the per-lane arrays stay in registers
+template <int kLnMaxT>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm_bwd_args a) {
   extern __shared__ float ln_smem[];
   const int C = a.hid;
@@ -987,12 +987,17 @@ extern "C" int ghn3_colsum(const ghn3_colsum_args* a, ghn3_stream_t stream_) {
 extern "C" int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* a, ghn3_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GHN3_REQUIRE(a != nullptr, "ghn3_layernorm_bwd: null args");
-  GHN3_REQUIRE(a->hid > 0 && a->hid <= 32 * kLnMaxT, "ghn3_layernorm_bwd: hid must be <= 1024");
+  GHN3_REQUIRE(a->hid > 0 && a->hid <= 1024, "ghn3_layernorm_bwd: hid must be <= 1024");
   GHN3_REQUIRE(a->x && a->gamma && a->dy && a->dx && a->dgamma && a->dbeta, "ghn3_layernorm_bwd: null pointer");
   if (a->rows <= 0) return GHN3_OK;
-  // few CTAs, several rows per warp: the per-column global atomics at the end scale with the CTA count
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 16), (int64_t)num_sms());
-  GHN3_CUDA(launch_pdl(layernorm_bwd_kernel, dim3(blocks), dim3(256), sizeof(float) * 2 * a->hid, stream, *a));
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 8), (int64_t)num_sms() * 3);
+  const size_t smem = sizeof(float) * 2 * a->hid;
+  const int t = (a->hid + 31) / 32;
+  if (t <= 4) GHN3_CUDA(launch_pdl(layernorm_bwd_kernel<4>, dim3(blocks), dim3(256), smem, stream, *a));
+  else if (t <= 8) GHN3_CUDA(launch_pdl(layernorm_bwd_kernel<8>, dim3(blocks), dim3(256), smem, stream, *a));
+  else if (t <= 12) GHN3_CUDA(launch_pdl(layernorm_bwd_kernel<12>, dim3(blocks), dim3(256), smem, stream, *a));
+  else if (t <= 16) GHN3_CUDA(launch_pdl(layernorm_bwd_kernel<16>, dim3(blocks), dim3(256), smem, stream, *a));
+  else GHN3_CUDA(launch_pdl(layernorm_bwd_kernel<32>, dim3(blocks), dim3(256), smem, stream, *a));
   GHN3_LAUNCH_CHECK("layernorm_bwd_kernel");
   return GHN3_OK;
 }
