@@ -519,7 +519,23 @@ class _PredictFn(torch.autograd.Function):
                                'program; its saved activations have been overwritten')
         if prog.bwd is None:
             prog.bwd = _Backward(prog, ghn)
-        gviews = prog.bwd.run(grads[:-1], ctx.out_index, grads[-1], ctx.slices)
+        bwd = prog.bwd
+        # ghn.direct_grads (set by Trainer, whose step is loss.backward() after zero_grad(set_to_none=True)): the
+        # parameters' .grad become views of the backward pass's flat buffer directly. Returning them through autograd
+        # instead makes AccumulateGrad clone all 2.6 GB (the views are shared) and the fused optimizer gather them
+        # back into a flat buffer. Off by default because torch.autograd.grad() needs the returned values.
+        direct = bool(getattr(ghn, 'direct_grads', False)) and all(p.grad is None for p in bwd.params)
+        if not direct:
+            lo = bwd.gflat.data_ptr()
+            hi = lo + bwd.gflat.numel() * 4
+            for p in bwd.params:                # accumulated gradients must not live in the buffer we are about to clear
+                if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+                    p.grad = p.grad.clone()
+        gviews = bwd.run(grads[:-1], ctx.out_index, grads[-1], ctx.slices)
+        if direct:
+            for p, v in zip(bwd.params, gviews):
+                p.grad = v
+            return (None,) * (5 + len(gviews))
         return (None, None, None, None, None) + tuple(gviews)
 
 

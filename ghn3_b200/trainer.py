@@ -83,6 +83,7 @@ class Trainer:
         self.ddp = is_ddp()
         model.to(device)
         self._model = model
+        model.direct_grads = True          # .grad = views of the backward pass's flat buffer (see train._PredictFn)
         if self.ddp:
             enable_grad_sync(model)
         opt_args = dict(opt_args or {})

@@ -304,3 +304,36 @@ def test_fused_adamw_matches_torch_clip_and_adamw():
     before = [p.detach().clone() for p in a.parameters()]
     opt_a.step()
     assert all(not torch.equal(x, p) for x, p in zip(before, a.parameters()))
+
+
+def test_gradient_accumulation_and_direct_grads():
+    """two backward passes without zeroing add up (autograd accumulation, also when .grad aliases the backward's own
+    buffer); with ghn.direct_grads the .grad tensors are views of that buffer and equal the autograd-returned ones."""
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    graph = Graph.from_record(H.graph_records()['resnet18'])
+
+    def backward():
+        model = ghn(H.build_model('resnet18').to(DEV), graph, keep_grads=True)
+        torch.manual_seed(3)
+        sum((p * torch.randn_like(p)).sum() for p in model.parameters()).backward()
+    names = [n for n, _ in ghn.named_parameters()]
+    noise = lambda n: n.endswith('proj_e.2.bias')                # exact gradient 0: rounding noise only
+    backward()
+    g1 = [p.grad.clone() for p in ghn.parameters()]
+    backward()                                                   # accumulates
+    for n, p, a in zip(names, ghn.parameters(), g1):
+        assert noise(n) or H.max_rel_err(p.grad, 2 * a) < 1e-4, n
+    ghn.zero_grad(set_to_none=True)
+    ghn.direct_grads = True
+    backward()
+    flat = ghn.last_program.bwd.gflat
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+    for (n, p), a in zip(ghn.named_parameters(), g1):
+        assert lo <= p.grad.data_ptr() < hi, n
+        assert noise(n) or H.max_rel_err(p.grad, a) < 1e-4, n
+    backward()                                                   # accumulation on top of aliased gradients still works
+    for n, p, a in zip(names, ghn.parameters(), g1):
+        assert noise(n) or H.max_rel_err(p.grad, 2 * a) < 1e-4, n
