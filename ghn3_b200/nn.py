@@ -324,6 +324,7 @@ class GHN3(GHN):
 
     def _run_refresh(self, w):
         """Re-derives every device copy from the current parameter values (same buffers, same addresses)."""
+        self.flush()                             # overlapped predictions may still be reading the old copies
         ops_ = w['refresh_ops']
         if ops_:
             seq = w['refresh_seq']
@@ -454,12 +455,27 @@ class GHN3(GHN):
         prog.bind_pack(pack)
         prog.refresh_targets(self.weight_norm)
         prof = getattr(self, '_profile', None)
-        if bp.n_tok_elems:
-            # class-token rows of ViT positional encodings: fresh N(0, 0.02) draws as in nn.py:446
-            prog.tok.normal_(mean=0.0, std=0.02)
-        prog.run(prof)
+        prog.run(prof, overlap=bool(getattr(self, 'overlap_scatter', False)) and prof is None)
         self.last_program = prog
         return prog.emb
+
+    def result_stream(self):
+        """The stream on which the last prediction's parameters (and predicted_sumsq) become final: the side stream in
+        `overlap_scatter` mode, else the current stream. Work that consumes them without stalling the next prediction
+        (e.g. param_norms + a D2H copy) can be enqueued there: `with torch.cuda.stream(ghn.result_stream()): ...`."""
+        prog = getattr(self, 'last_program', None)
+        if prog is not None and getattr(prog, 'ev_scatter', None) is not None:
+            return prog.side
+        return torch.cuda.current_stream()
+
+    def flush(self):
+        """With `overlap_scatter` the final tile/normalise/scatter kernel of a prediction runs on a side stream so that
+        it overlaps the next prediction's Graphormer stack; flush() makes the current stream wait for it. Call it
+        before the predicted parameters are used (or timed)."""
+        prog = getattr(self, 'last_program', None)
+        ev = getattr(prog, 'ev_scatter', None) if prog is not None else None
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def param_norms(self, nets):
         """Total L2 norm of each network's parameters after the last forward call (the reference's norm_check metric,
@@ -691,6 +707,8 @@ class _Program:
                 # reference semantics (nn.py:548): param.data is replaced by a tensor on the GHN's device
                 p.data = torch.empty(tuple(p.shape), dtype=torch.float32, device=device)
                 ptrs[i] = p.data_ptr()
+        if getattr(self, 'ev_scatter', None) is not None:      # an overlapped scatter may still read the table
+            torch.cuda.current_stream().wait_event(self.ev_scatter)
         desc = self.desc_host
         desc['dst'] = ptrs + self.bp.desc_dst_shift
         if not weight_norm:
@@ -714,11 +732,61 @@ class _Program:
         self.desc_dev.copy_(torch.from_numpy(desc.view(np.uint8).reshape(-1)))
         self.last_ptrs = None
 
-    def run(self, prof=None):
+    def run(self, prof=None, overlap=False):
         stream = L.current_stream()
-        if prof is None:
-            L.check(L.load().ghn3_run_sequence(self.seq, len(self.ops), ct.c_void_p(stream)), 'ghn3_run_sequence')
+        lib = L.load()
+        cur = torch.cuda.current_stream()
+        ev_prev = getattr(self, 'ev_scatter', None)
+        draw_tok = self.bp.n_tok_elems > 0       # ViT class-token rows: fresh N(0, 0.02) draws as in nn.py:446
+        if prof is None and not (overlap and self.n_desc):
+            if ev_prev is not None:              # an earlier overlapped call: its scatter still reads our buffers
+                cur.wait_event(ev_prev)
+                self.ev_scatter = None
+            if draw_tok:
+                self.tok.normal_(mean=0.0, std=0.02)
+            L.check(lib.ghn3_run_sequence(self.seq, len(self.ops), ct.c_void_p(stream)), 'ghn3_run_sequence')
             return
+        if prof is None:
+            # Overlapped form: [node features, Graphormer] -> wait for the PREVIOUS call's scatter (it reads the decoder
+            # outputs this call is about to overwrite) -> decoders -> scatter on a side stream. Successive predictions
+            # are independent, so the HBM-write-bound scatter of call k runs under the latency-bound Graphormer of
+            # call k+1. The caller must use GHN3.flush() before touching the predicted parameters.
+            if getattr(self, 'side', None) is None:
+                # the Graphormer + decoders run on a HIGH-priority stream, the scatter on a normal one: when the two
+                # compete for SM slots the block scheduler serves the latency-bound chain first
+                self.hi = torch.cuda.Stream(device=self.device, priority=-1)
+                self.side = torch.cuda.Stream(device=self.device)
+                self.first_dec = next(i for i, (st_, _, _) in enumerate(self.ops) if st_ not in ('node_features',
+                                                                                                'graphormer'))
+                self.ev_ready = torch.cuda.Event()
+            hi, side = self.hi, self.side
+            n_ops, i_dec, i_sc = len(self.ops), self.first_dec, len(self.ops) - 1
+            at = lambda i: ct.c_void_p(ct.addressof(self.seq) + i * ct.sizeof(L.SeqOp))
+            ev_in = torch.cuda.Event()
+            ev_in.record(cur)                    # the graph pack was uploaded / derived on the caller's stream
+            hi.wait_event(ev_in)
+            self.bound_pack.record_stream(hi)
+            L.check(lib.ghn3_run_sequence(at(0), i_dec, ct.c_void_p(hi.cuda_stream)), 'ghn3_run_sequence (graphormer)')
+            if ev_prev is not None:
+                hi.wait_event(ev_prev)
+            if draw_tok:
+                with torch.cuda.stream(hi):
+                    self.tok.normal_(mean=0.0, std=0.02)
+            L.check(lib.ghn3_run_sequence(at(i_dec), i_sc - i_dec, ct.c_void_p(hi.cuda_stream)),
+                    'ghn3_run_sequence (decoders)')
+            self.ev_ready.record(hi)
+            side.wait_event(self.ev_ready)
+            L.check(lib.ghn3_run_sequence(at(i_sc), n_ops - i_sc, ct.c_void_p(side.cuda_stream)),
+                    'ghn3_run_sequence (scatter)')
+            ev = torch.cuda.Event()
+            ev.record(side)
+            self.ev_scatter = ev
+            return
+        if ev_prev is not None:
+            cur.wait_event(ev_prev)
+            self.ev_scatter = None
+        if draw_tok:
+            self.tok.normal_(mean=0.0, std=0.02)
 
         def mark(name):
             ev = torch.cuda.Event(enable_timing=True)

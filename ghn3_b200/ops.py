@@ -111,6 +111,15 @@ class GraphPack:
         self.op_dev = v.get('op')
         self.pair = self.deg_in = self.deg_out = self.dist0 = None
 
+    def record_stream(self, stream):
+        """Tells the caching allocator that `stream` reads this pack's buffers (they were allocated on another one)."""
+        if getattr(self, '_recorded', None) is stream:
+            return
+        for t in (self._blob.dev, self.spd, self.pair, self.deg_in, self.deg_out, self.dist0, getattr(self, '_bits', None)):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(stream)
+        self._recorded = stream
+
     def clone_for_upload(self, device=None):
         """A new pack with the same (immutable) host-side layout: only the H2D copy and the kernels are repeated."""
         import copy as _copy

@@ -263,3 +263,42 @@ def test_empty_and_single_node_inputs():
     ghn, cfg = make_ghn('ghn3tiny', 'bf16')
     with torch.no_grad():
         assert ghn([], []) == []
+
+
+def test_overlap_scatter_mode_gives_the_same_parameters():
+    """GHN3.overlap_scatter: the scatter of call k runs on a side stream under the Graphormer of call k+1; after
+    flush() the parameters of every call equal those of the serial mode (same buffers reused across calls)."""
+    ghn, cfg = make_ghn('ghn3tiny', 'tf32')
+    archs = ['resnet18', 'vit_b_32', 'squeezenet1_1']
+    graphs = {a: Graph.from_record(H.graph_records()[a]) for a in archs}
+    ref = {}
+    with torch.no_grad():
+        for a in archs:
+            m = ghn(H.build_model(a).to(DEV), graphs[a])
+            ref[a] = {n: p.detach().clone() for n, p in m.named_parameters()}
+        ghn.overlap_scatter = True
+        models = {a: H.build_model(a).to(DEV) for a in archs}
+        for rep in range(3):                                   # same programs back to back: buffers are reused
+            for a in archs:
+                ghn(models[a], graphs[a])
+        norms = {}
+        with torch.cuda.stream(ghn.result_stream()):
+            norms[archs[-1]] = ghn.param_norms([models[archs[-1]]]).clone()
+        ghn.flush()
+        torch.cuda.synchronize()
+    for a in archs:
+        for n, p in models[a].named_parameters():
+            if n.endswith('pos_embedding'):
+                p, r = p[:, 1:], ref[a][n][:, 1:]              # class-token row is a fresh random draw
+            else:
+                r = ref[a][n]
+            assert H.max_rel_err(p, r) < 1e-4, (a, n)
+    last = archs[-1]
+    total = torch.sqrt(sum((p.double() ** 2).sum() for p in models[last].parameters()))
+    assert abs(float(norms[last][0]) - float(total)) / float(total) < 1e-5
+    ghn.overlap_scatter = False
+    with torch.no_grad():
+        m = ghn(H.build_model('resnet18').to(DEV), graphs['resnet18'])     # back to the serial mode
+    torch.cuda.synchronize()
+    for n, p in m.named_parameters():
+        assert H.max_rel_err(p, ref['resnet18'][n]) < 1e-4, n
