@@ -82,7 +82,7 @@ class GraphormerArgs(C.Structure):
                 ('node_off', vp), ('mat_off', vp), ('pair', vp), ('lut', vp), ('x', vp),
                 ('h', vp), ('qkv', vp), ('ff', vp),
                 ('dec_in', vp), ('dec_dtype', i32), ('dst_row', vp), ('emb_f32', vp), ('ln_counters', vp),
-                ('h2', vp), ('tf32_x3', i32)]
+                ('h2', vp), ('tf32_x3', i32), ('skip_final_ln', i32)]
 
 
 class ScatterDesc(C.Structure):

@@ -104,6 +104,7 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
     }
     if ((rc = gemm_impl(&ff2, stream)) != GHN3_OK) return rc;
   }
+  if (a->skip_final_ln) return GHN3_OK;
   if (a->ln_w != nullptr) {
     ghn3_layernorm_args ln = {};
     ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = a->ln_w; ln.beta = a->ln_b;
@@ -148,6 +149,7 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
       case GHN3_OP_EDGE_LUT_BWD: rc = ghn3_edge_lut_bwd((const ghn3_edge_lut_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_FC_BWD: rc = ghn3_fc_bwd((const ghn3_fc_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_RELU_TRANSPOSE_BWD: rc = ghn3_relu_transpose_bwd((const ghn3_relu_transpose_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_LAYERNORM: rc = ghn3_layernorm((const ghn3_layernorm_args*)ops[i].args, stream); break;
       case GHN3_OP_EXPAND_COLS: rc = ghn3_expand_cols((const ghn3_expand_args*)ops[i].args, stream); break;
       case GHN3_OP_MEMSET: {
         const ghn3_memset_args* m = (const ghn3_memset_args*)ops[i].args;

@@ -1034,7 +1034,10 @@ static int launch_gemm_persistent(const CUtensorMap& ma, const CUtensorMap& mb, 
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const dim3 grid((unsigned)std::min(n_tiles, num_sms()));
+  // GHN3_PERSISTENT_CTAS < #SMs leaves SMs free for a latency-bound kernel chain running concurrently on another
+  // stream (the weight-streaming GEMMs stay HBM-bound with ~2/3 of the SMs)
+  static const int cap = getenv("GHN3_PERSISTENT_CTAS") ? std::max(1, atoi(getenv("GHN3_PERSISTENT_CTAS"))) : 1 << 30;
+  const dim3 grid((unsigned)std::min(std::min(n_tiles, num_sms()), cap));
   GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap, kX3>, grid, dim3(gemm_threads<kX3>()), (size_t)smem, stream, ma, mb,
                        ka));
   GHN3_LAUNCH_CHECK("gemm_tcgen05_persistent_kernel");

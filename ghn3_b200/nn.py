@@ -523,7 +523,7 @@ class _Program:
     once; per call only the graph-pack pointers and (if they moved) the target-parameter addresses are patched.
     """
     OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6,
-          'graphormer_train_fwd': 7}
+          'graphormer_train_fwd': 7, 'layernorm': 21}
 
     def __init__(self, ghn, w, bp, device, want_emb, train=False):
         self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
@@ -576,7 +576,14 @@ class _Program:
             self.ga = self.ta.fwd            # the struct was copied by value: patch THIS copy in bind_pack
             self.ops.append(('graphormer', 'graphormer_train_fwd', self.ta))
         else:
+            # the final LayerNorm (-> decoder input rows) is its own op so that the overlapped mode can order it after
+            # the previous call's decoders
+            self.ga.skip_final_ln = 1
             self.ops.append(('graphormer', 'graphormer_stack', self.ga))
+            self.final_ln = L.LayerNormArgs(rows=N, hid=C, x=L.ptr(self.x), gamma=L.ptr(w['ln_w']), beta=L.ptr(w['ln_b']),
+                                            out=L.ptr(self.dec_in), out_dtype=act, dst_row=L.ptr(st['dst_row']),
+                                            out_f32=L.ptr(self.emb))
+            self.ops.append(('graphormer', 'layernorm', self.final_ln))
         bufs = {}
         self.rts = []
 
@@ -752,32 +759,43 @@ class _Program:
             # are independent, so the HBM-write-bound scatter of call k runs under the latency-bound Graphormer of
             # call k+1. The caller must use GHN3.flush() before touching the predicted parameters.
             if getattr(self, 'side', None) is None:
-                # the Graphormer + decoders run on a HIGH-priority stream, the scatter on a normal one: when the two
+                # the Graphormer stack runs on a HIGH-priority stream, decoders + scatter on a normal one: when the two
                 # compete for SM slots the block scheduler serves the latency-bound chain first
                 self.hi = torch.cuda.Stream(device=self.device, priority=-1)
                 self.side = torch.cuda.Stream(device=self.device)
-                self.first_dec = next(i for i, (st_, _, _) in enumerate(self.ops) if st_ not in ('node_features',
-                                                                                                'graphormer'))
-                self.ev_ready = torch.cuda.Event()
+                self.i_ln = next(i for i, (_, name_, _) in enumerate(self.ops) if name_ == 'layernorm')
+                self.ev_a = torch.cuda.Event()
+                self.ev_dec = None
             hi, side = self.hi, self.side
-            n_ops, i_dec, i_sc = len(self.ops), self.first_dec, len(self.ops) - 1
+            n_ops, i_ln, i_sc = len(self.ops), self.i_ln, len(self.ops) - 1
+            split = self.ghn.__dict__.get('overlap_decoders', True)      # False: only the scatter leaves the main chain
             at = lambda i: ct.c_void_p(ct.addressof(self.seq) + i * ct.sizeof(L.SeqOp))
+            run = lambda i0, i1, st_, what: L.check(lib.ghn3_run_sequence(at(i0), i1 - i0, ct.c_void_p(st_.cuda_stream)),
+                                                    'ghn3_run_sequence (%s)' % what)
             ev_in = torch.cuda.Event()
             ev_in.record(cur)                    # the graph pack was uploaded / derived on the caller's stream
             hi.wait_event(ev_in)
             self.bound_pack.record_stream(hi)
-            L.check(lib.ghn3_run_sequence(at(0), i_dec, ct.c_void_p(hi.cuda_stream)), 'ghn3_run_sequence (graphormer)')
-            if ev_prev is not None:
-                hi.wait_event(ev_prev)
+            run(0, i_ln, hi, 'graphormer')
+            # the final LayerNorm overwrites the decoder input rows: the previous call's decoders must have read them
+            if self.ev_dec is not None:
+                hi.wait_event(self.ev_dec)
+            run(i_ln, i_ln + 1, hi, 'final layernorm')
+            if not split:
+                if ev_prev is not None:
+                    hi.wait_event(ev_prev)
+                run(i_ln + 1, i_sc, hi, 'decoders')
+            self.ev_a.record(hi)
+            side.wait_event(self.ev_a)
+            if split:
+                run(i_ln + 1, i_sc, side, 'decoders')        # ordered after the previous scatter by the stream itself
+            ev_dec = torch.cuda.Event()
+            ev_dec.record(side)
+            self.ev_dec = ev_dec
             if draw_tok:
-                with torch.cuda.stream(hi):
+                with torch.cuda.stream(side):
                     self.tok.normal_(mean=0.0, std=0.02)
-            L.check(lib.ghn3_run_sequence(at(i_dec), i_sc - i_dec, ct.c_void_p(hi.cuda_stream)),
-                    'ghn3_run_sequence (decoders)')
-            self.ev_ready.record(hi)
-            side.wait_event(self.ev_ready)
-            L.check(lib.ghn3_run_sequence(at(i_sc), n_ops - i_sc, ct.c_void_p(side.cuda_stream)),
-                    'ghn3_run_sequence (scatter)')
+            run(i_sc, n_ops, side, 'scatter')
             ev = torch.cuda.Event()
             ev.record(side)
             self.ev_scatter = ev

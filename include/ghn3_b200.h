@@ -304,6 +304,8 @@ typedef struct {
   void* h2;                                /* [total_nodes][C] in dtype, needed when ln_counters is given */
   int32_t tf32_x3;                         /* dtype TF32 only: activations stay un-rounded fp32, GEMMs use the
                                               3-term compensated tf32 mode (~fp32 accuracy) */
+  int32_t skip_final_ln;                   /* 1: stop after the last layer; the caller runs the final LayerNorm itself
+                                              (ghn3_layernorm with dst_row), e.g. on another stream */
 } ghn3_graphormer_args;
 
 int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream);
@@ -626,7 +628,7 @@ enum ghn3_opcode {
   GHN3_OP_GRAPHORMER_TRAIN_FWD = 7, GHN3_OP_GRAPHORMER_BWD = 8, GHN3_OP_TRANSPOSE = 9, GHN3_OP_ELEMENTWISE = 10,
   GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
   GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18,
-  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20
+  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21
 };
 /* GHN3_OP_MEMSET: args points to a ghn3_memset_args; clears `bytes` bytes at `ptr` (cudaMemsetAsync). */
 typedef struct { void* ptr; int64_t bytes; } ghn3_memset_args;
