@@ -236,3 +236,50 @@ dist.destroy_process_group()
                         '--master-addr', '127.0.0.1', '--master-port', '29532', str(script)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_flat_gradient_layout_and_conv2_block_lists():
+    """Host logic of the training path: [decoder | rest] gradient layout with 16-byte aligned slices, and the sparse-K
+    block lists of the conv.2 backward GEMMs cover every non-zero block of the column-expanded operands."""
+    from ghn3_b200.nn import GHN3
+    from ghn3_b200.train import flat_layout, _conv2_k_blocks
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True)
+    params, order, offs, early = flat_layout(ghn)
+    assert len(order) == len(params) == len(list(ghn.state_dict())) and {id(p) for p in order} == {id(p) for p in params}
+    assert all(int(o) % 4 == 0 for o in offs) and int(offs[-1]) >= sum(p.numel() for p in params)
+    n_early = sum(p.numel() for m in (ghn.decoder, ghn.decoder_1d, ghn.bias_class) for p in m.parameters())
+    assert early >= n_early and early < int(offs[-1])
+    dec_ids = {id(p) for m in (ghn.decoder, ghn.decoder_1d, ghn.bias_class) for p in m.parameters()}
+    k = len(dec_ids)
+    assert {id(p) for p in order[:k]} == dec_ids                      # decoder-side tensors first
+
+    ms1, KF = 24, 24 * 24
+    segs = [(20, 24, 0, 130, 0), (7, 5, 130, 9, 0), (3, 1, 139, 200, 0)]
+    R = 339
+    X = np.zeros((R, KF), bool)
+    for (o, ii, r0, rows, _) in segs:
+        for a in range(o):
+            X[r0:r0 + rows, a * ms1:a * ms1 + ii] = True
+    for bk in (64, 32):
+        (dl, do), (wl, wo) = _conv2_k_blocks(segs, R, KF, ms1, bk, 'cpu')
+        for mt in range(-(-R // 128)):
+            need = set((np.nonzero(X[mt * 128:(mt + 1) * 128].any(0))[0] // bk).tolist())
+            assert need <= set(dl[do[mt]:do[mt + 1]].tolist())
+        for ct_ in range(-(-KF // 128)):
+            need = set((np.nonzero(X[:, ct_ * 128:(ct_ + 1) * 128].any(1))[0] // bk).tolist())
+            assert need <= set(wl[wo[ct_]:wo[ct_ + 1]].tolist())
+        assert len(dl) < (-(-R // 128)) * (KF // bk)                  # and they do skip something
+
+
+def test_net_generator_is_deterministic_and_within_the_design_space():
+    from ghn3_b200.deepnets import NetGenerator, CHANNELS, OPS
+    a, b = NetGenerator(seed=3), NetGenerator(seed=3)
+    for _ in range(4):
+        na, nb = a.sample_net(), b.sample_net()
+        assert na.net_args == nb.net_args
+        g = na.net_args
+        assert 4 <= g['n_cells'] <= 18 and g['C'] in CHANNELS and g['stem_type'] in (0, 1) and g['fc_layers'] in (1, 2)
+        assert all(op in OPS and op != 'none' for cell in ('normal', 'reduce') for (op, _, _) in g['genotype'][cell])
+        assert sum(p.numel() for p in na.parameters()) <= a.max_params
+    assert NetGenerator(seed=4).sample_net().net_args != NetGenerator(seed=3).sample_net().net_args
