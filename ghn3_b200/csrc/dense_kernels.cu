@@ -3,6 +3,8 @@
 //   ghn3_attention   reference ghn3/graphormer.py:121-140 (QK^T * d^-1/2 + edge bias, softmax, PV), flash-style:
 //                    no (B,H,N,N) logits and no (B,N,N,H) bias tensor are ever materialised
 //   ghn3_gemm_simt   classification heads (ghn3/nn.py:757-758, 294) whose operands are transposed views
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ghn3 {
@@ -522,6 +524,8 @@ static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
   return GHN3_OK;
 }
 
+int attention_split_impl(const ghn3_attention_args* a, cudaStream_t stream);
+
 int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_attention: null args");
   GHN3_REQUIRE(a->heads > 0 && a->hid % a->heads == 0, "ghn3_attention: hid must be divisible by heads");
@@ -529,6 +533,15 @@ int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
   const int D = a->hid / a->heads;
   const bool bf = a->dtype == GHN3_BF16;
+  if (!bf) {
+    // fp32 storage: split-bf16 tensor-core kernel (attention_split.cu); the CUDA-core kernel below remains for the
+    // head dims it does not cover and as a cross-check (GHN3_NO_SPLIT_ATTN=1)
+    static const bool no_split = getenv("GHN3_NO_SPLIT_ATTN") != nullptr;
+    if (!no_split) {
+      const int rc = attention_split_impl(a, stream);
+      if (rc != GHN3_ERR_UNSUPPORTED) return rc;
+    }
+  }
 #define GHN3_ATTN_CASE(DV)                                                     \
   if (D == DV) return bf ? launch_attention_mma<DV>(a, stream) : launch_attention<float, DV>(a, stream);
   GHN3_ATTN_CASE(4)
