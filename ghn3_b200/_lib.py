@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, 'libghn3_b200.so')
 
 BF16, TF32, F32 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-SCATTER_CHUNK = 8192
+SCATTER_CHUNK = 16384
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 

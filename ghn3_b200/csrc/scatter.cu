@@ -38,8 +38,9 @@ __device__ __forceinline__ float fetch_bilinear(const ghn3_scatter_desc& d, int 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
-// One CTA per 4096-element chunk of one target tensor; a thread handles 4 consecutive target elements per step
-// (one 16-byte store), 4 steps. All index arithmetic is 32-bit with multiply-high divisions; the descriptor lives in
+// One CTA per GHN3_SCATTER_CHUNK-element chunk of one target tensor; a thread handles 4 consecutive target elements
+// per step (one 16-byte store). 16384-element chunks: with 8192 the isolated kernel is as fast, but the twice as many
+// CTAs interfere much more with the next call's Graphormer chain in the overlapped mode (1.65 -> 1.47 ms per step). All index arithmetic is 32-bit with multiply-high divisions; the descriptor lives in
 // registers.
 __device__ __forceinline__ void block_sumsq(float acc, double* out) {
   __shared__ float part[8];

@@ -255,7 +255,7 @@ DESC_DT = np.dtype([('dst', 'u8'), ('src', 'u8'), ('numel', 'i8'), ('chunk0', 'i
                    [(n_, 'u4') for n_ in ('m_t1', 's_t1', 'm_t2', 's_t2', 'm_t3', 's_t3', 'm_so', 's_so', 'm_si', 's_si')] +
                    [('norm_slot', 'i4'), ('reserved', 'i4')])
 assert PROBLEM_DT.itemsize == 32 and DESC_DT.itemsize == 136
-SCATTER_CHUNK = 8192
+SCATTER_CHUNK = 16384
 SRC_WOUT, SRC_D1, SRC_CLSW, SRC_CLSB, SRC_TOK = 0, 1, 2, 3, 4      # which device buffer a descriptor reads
 import os as _os
 C2_DENSE_BLOCK_N = int(_os.environ.get('GHN3_C2_BLOCK_N', '128'))    # N tile of the dense conv.2 launch

@@ -340,7 +340,7 @@ typedef struct {
   int32_t reserved;
 } ghn3_scatter_desc;       /* 136 bytes; numel < 2^31 */
 
-#define GHN3_SCATTER_CHUNK 8192
+#define GHN3_SCATTER_CHUNK 16384
 
 typedef struct {
   const ghn3_scatter_desc* descs;   /* device [n_descs] */
