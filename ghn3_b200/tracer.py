@@ -16,6 +16,7 @@ O(N * degree) host work. Verified bit-exact (ops, edges, node_info) against grap
 torchvision classification models (tests/golden/graphs_tv.json.gz).
 """
 import copy
+import os
 
 import networkx as nx
 import numpy as np
@@ -85,15 +86,45 @@ def _cell_index(name, n_cells):
 # ----------------------------------------------------------------------------------------------------------------
 # 1. autograd walk
 # ----------------------------------------------------------------------------------------------------------------
-def _autograd_graph(model, input_sz):
+def _forward_for_graph(model, input_sz):
+    """Runs the model once to obtain the autograd graph. First choice: a META forward -- parameters and buffers are
+    replaced by meta tensors through torch.func.functional_call, so no arithmetic is done and the model (weights,
+    BatchNorm statistics) is left untouched; the graph and every size are the same. Models whose forward needs real
+    values (data-dependent control flow) fall back to the real forward of the reference (graph.py:400-420).
+    Returns (outputs, owner: id(leaf tensor) -> (parameter name, module))."""
+    mods = dict(model.named_modules())
+    if not hasattr(model, 'get_var') and os.environ.get('GHN3_TRACE_META', '1') != '0':
+        try:
+            meta, owner, seen = {}, {}, {}
+            for mod_name, mod in mods.items():
+                for p_name, p in mod.named_parameters(recurse=False):
+                    if p is None:
+                        continue
+                    full = (mod_name + '.' if mod_name else '') + p_name
+                    if id(p) not in seen:                                  # shared parameters stay shared
+                        seen[id(p)] = torch.empty_like(p, device='meta', requires_grad=True)
+                        owner[id(seen[id(p)])] = (mod_name + '.' + p_name, mod)
+                    meta[full] = seen[id(p)]
+            for b_name, b in model.named_buffers():
+                meta[b_name] = torch.empty_like(b, device='meta')
+            with torch.enable_grad():
+                out = torch.func.functional_call(model, meta, (torch.empty(2, *input_sz, device='meta'),))
+            return out, owner, list(seen.values())
+        except Exception:                                                  # noqa: BLE001 -- any meta-kernel gap
+            pass
     owner = {}
-    for mod_name, mod in model.named_modules():
+    for mod_name, mod in mods.items():
         for p_name, p in mod.named_parameters(recurse=False):
             if p is not None and id(p) not in owner:
                 owner[id(p)] = (mod_name + '.' + p_name, mod)
     device = next(model.parameters()).device
     with torch.enable_grad():
         out = model.get_var() if hasattr(model, 'get_var') else model(torch.randn(2, *input_sz, device=device))
+    return out, owner, None
+
+
+def _autograd_graph(model, input_sz):
+    out, owner, _keepalive = _forward_for_graph(model, input_sz)
     if isinstance(out, dict):
         out = list(out.values())
     if not isinstance(out, (tuple, list)):
