@@ -283,3 +283,21 @@ def test_net_generator_is_deterministic_and_within_the_design_space():
         assert all(op in OPS and op != 'none' for cell in ('normal', 'reduce') for (op, _, _) in g['genotype'][cell])
         assert sum(p.numel() for p in na.parameters()) <= a.max_params
     assert NetGenerator(seed=4).sample_net().net_args != NetGenerator(seed=3).sample_net().net_args
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host cores only and prints ONE JSON line with the contract's keys."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=900, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'config', 'e2e',
+              'cpu_baseline', 'impl'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'models/s' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in d['config']
