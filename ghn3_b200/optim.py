@@ -91,6 +91,26 @@ class FusedAdamW(torch.optim.Optimizer):
         L.call('adamw', a, L.current_stream())
         return loss
 
+    def state_dict(self):
+        """Optimizer state for checkpoints (reference trainer.py:419-426 stores `optimizer.state_dict()`): the two flat
+        moment buffers, in the [decoder | rest] layout of ghn3_b200.train.flat_layout, and the step count."""
+        d = super().state_dict()
+        d['flat'] = {'exp_avg': self.exp_avg.detach().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().clone(),
+                     'step': self._step}
+        return d
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop('flat', None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            if flat['exp_avg'].numel() != self._total:
+                raise ValueError('FusedAdamW: checkpoint moments have %d elements, expected %d'
+                                 % (flat['exp_avg'].numel(), self._total))
+            self.exp_avg.copy_(flat['exp_avg'])
+            self.exp_avg_sq.copy_(flat['exp_avg_sq'])
+            self._step = int(flat['step'])
+
     def grad_norm(self):
         """Global gradient norm seen by the last step (device tensor, float64) when clipping is enabled."""
         return self._sumsq.sqrt()

@@ -111,6 +111,21 @@ class Trainer:
         self.skipped_updates = 0
         self.reset_metrics()
 
+    def save(self, path, epoch=0, step=0, config=None):
+        """Checkpoint in the reference's layout (trainer.py:413-426): {'state_dict', 'optimizer', 'epoch', 'step',
+        **config}; `from_pretrained(path)` loads it back. Rank 0 only under torch.distributed."""
+        if self.ddp:
+            import torch.distributed as dist
+            if dist.get_rank() != 0:
+                return
+        self._model.flush()
+        sd = {'state_dict': self._model.state_dict(), 'optimizer': self._optimizer.state_dict(), 'epoch': epoch,
+              'step': step}
+        sd.update(config or {'config': {k: self._model.config[k] for k in ('max_shape', 'num_classes', 'hid', 'heads',
+                                                                          'layers', 'layernorm')} |
+                             {'weight_norm': self._model.weight_norm, 've': self._model.ve}})
+        torch.save(sd, path)
+
     def reset_metrics(self, epoch=0):
         self._step = 0
         self.metrics = {'loss': AvgMeter(), 'top1': AvgMeter(), 'top5': AvgMeter()}

@@ -337,3 +337,33 @@ def test_gradient_accumulation_and_direct_grads():
     backward()                                                   # accumulation on top of aliased gradients still works
     for n, p, a in zip(names, ghn.parameters(), g1):
         assert noise(n) or H.max_rel_err(p.grad, 2 * a) < 1e-4, n
+
+
+def test_trainer_checkpoint_round_trip(tmp_path):
+    """Trainer.save writes the reference's checkpoint layout; from_pretrained + FusedAdamW.load_state_dict resume it:
+    the resumed run takes the same next step."""
+    from ghn3_b200 import Trainer, GraphBatch, from_pretrained
+    cfg = CONFIGS['ghn3tiny']
+
+    def batch():
+        return GraphBatch([Graph.from_record(H.graph_records()['resnet18'])], dense=True)
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    tr = Trainer(ghn, opt='adamw', opt_args={'lr': 1e-3, 'weight_decay': 1e-2}, grad_clip=5, device=DEV)
+    loss_fn = lambda models: ghn.last_program.pred_flat.square().sum() * 1e-3
+    for _ in range(2):
+        tr.update(None, None, graphs=batch(), models=[H.build_model('resnet18').to(DEV)], loss_fn=loss_fn)
+    path = str(tmp_path / 'checkpoint.pt')
+    tr.save(path, epoch=1, step=2)
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    assert {'state_dict', 'optimizer', 'epoch', 'step', 'config'} <= set(ck) and ck['step'] == 2
+    ghn2 = from_pretrained(path, compute_dtype='tf32')
+    assert ghn2.config['hid'] == cfg['hid'] and ghn2.weight_norm and ghn2.ve
+    tr2 = Trainer(ghn2, opt='adamw', opt_args={'lr': 1e-3, 'weight_decay': 1e-2}, grad_clip=5, device=DEV)
+    tr2._optimizer.load_state_dict(ck['optimizer'])
+    loss_fn2 = lambda models: ghn2.last_program.pred_flat.square().sum() * 1e-3
+    tr.update(None, None, graphs=batch(), models=[H.build_model('resnet18').to(DEV)], loss_fn=loss_fn)
+    tr2.update(None, None, graphs=batch(), models=[H.build_model('resnet18').to(DEV)], loss_fn=loss_fn2)
+    torch.cuda.synchronize()
+    for (n, a), b in zip(ghn.named_parameters(), ghn2.parameters()):
+        assert H.max_rel_err(a, b) < 1e-4, n
