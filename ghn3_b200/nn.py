@@ -471,7 +471,7 @@ class GHN3(GHN):
     def flush(self):
         """With `overlap_scatter` the final tile/normalise/scatter kernel of a prediction runs on a side stream so that
         it overlaps the next prediction's Graphormer stack; flush() makes the current stream wait for it. Call it
-        before the predicted parameters are used (or timed)."""
+        before the predicted parameters (or returned embeddings) are used or timed."""
         prog = getattr(self, 'last_program', None)
         ev = getattr(prog, 'ev_scatter', None) if prog is not None else None
         if ev is not None:
