@@ -361,7 +361,7 @@ class GHN3(GHN):
             return ([], torch.empty(0, self.hid, device=device)) if return_embeddings else []
 
         if graphs is None:
-            graphs = GraphBatch([Graph(net, ve_cutoff=50 if self.ve else 1) for net in nets], dense=True)
+            graphs = GraphBatch([self._traced_graph(net) for net in nets], dense=True)
         elif not isinstance(graphs, GraphBatch):
             graphs = GraphBatch(list(graphs) if isinstance(graphs, (list, tuple)) else [graphs], dense=True)
         if not graphs.on_device(device):
@@ -400,6 +400,19 @@ class GHN3(GHN):
         return (out, emb) if return_embeddings else out
 
     # ------------------------------------------------------------------------------------------------------------
+    def _traced_graph(self, net):
+        """Graph(net) with a per-model cache keyed by an architecture signature (module classes + parameter names and
+        shapes): `ghn(model)` called again on the same architecture does not re-trace it."""
+        cutoff = 50 if self.ve else 1
+        sig = (cutoff, tuple((n, type(m).__name__) for n, m in net.named_modules()),
+               tuple((n, tuple(p.shape)) for n, p in net.named_parameters()))
+        hit = net.__dict__.get('_ghn3_b200_graph')
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        g = Graph(net, ve_cutoff=cutoff)
+        net.__dict__['_ghn3_b200_graph'] = (sig, g)
+        return g
+
     def _batch_plan(self, graphs, nets, predict_class_layers, reduce_graph):
         plans = []
         for graph, net in zip(graphs.graphs, nets):

@@ -302,3 +302,22 @@ def test_overlap_scatter_mode_gives_the_same_parameters():
     torch.cuda.synchronize()
     for n, p in m.named_parameters():
         assert H.max_rel_err(p, ref['resnet18'][n]) < 1e-4, n
+
+
+def test_traced_graph_is_cached_per_architecture():
+    """ghn(model) without graphs traces once per architecture signature; a structural change re-traces."""
+    import torch.nn as nn
+    ghn, cfg = make_ghn('ghn3tiny', 'tf32')
+    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                        nn.Linear(8, 10)).to(DEV)
+    net.expected_input_sz = 32
+    with torch.no_grad():
+        ghn(net)
+        g1 = net.__dict__['_ghn3_b200_graph'][1]
+        ghn(net)
+        assert net.__dict__['_ghn3_b200_graph'][1] is g1
+        net[5] = nn.Linear(8, 12).to(DEV)
+        ghn(net)
+        assert net.__dict__['_ghn3_b200_graph'][1] is not g1
+    torch.cuda.synchronize()
+    assert net[5].weight.shape == (12, 8) and torch.isfinite(net[5].weight).all()
