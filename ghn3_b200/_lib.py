@@ -85,6 +85,13 @@ class GraphormerArgs(C.Structure):
                 ('h2', vp), ('tf32_x3', i32), ('skip_final_ln', i32)]
 
 
+class GraphormerFusedArgs(C.Structure):
+    _fields_ = [('hid', i32), ('heads', i32), ('layers', i32), ('w_qkv', vp), ('w_out', vp), ('w_ff1', vp),
+                ('w_ff2', vp), ('layers_dev', vp), ('n_graphs', i32), ('total_nodes', i32), ('max_nodes', i32),
+                ('lut_size', i32), ('node_off', vp), ('mat_off', vp), ('pair', vp), ('lut', vp), ('x', vp),
+                ('ao', vp), ('qkv', vp), ('ff', vp), ('sync', vp), ('stop_after', i32), ('max_ctas', i32)]
+
+
 class ScatterDesc(C.Structure):
     _fields_ = [('dst', vp), ('src', vp), ('numel', i64), ('chunk0', i64), ('t1', i32), ('t2', i32), ('t3', i32),
                 ('so', i32), ('si', i32), ('ld', i32), ('ca', i32), ('ra', i32), ('kh_src', i32), ('kw_src', i32),
@@ -242,7 +249,8 @@ assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
 
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
-           'ghn3_graphormer_stack', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence']
+           'ghn3_graphormer_stack', 'ghn3_graphormer_fused', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence',
+           'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
                  'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin']
@@ -267,9 +275,11 @@ def load(build_if_missing=True):
             raise RuntimeError('ghn3_b200: %s does not export %s' % (LIB_PATH, s))
     lib.ghn3_last_error.restype = C.c_char_p
     lib.ghn3_launch_count.restype = C.c_int64
-    for s in SYMBOLS[3:15] + TRAIN_SYMBOLS:
+    for s in SYMBOLS[3:16] + TRAIN_SYMBOLS:
         getattr(lib, s).restype = C.c_int
         getattr(lib, s).argtypes = [C.c_void_p, C.c_void_p]
+    lib.ghn3_graphormer_fused_sync_ints.restype = C.c_int64
+    lib.ghn3_graphormer_fused_sync_ints.argtypes = [C.c_int32]
     lib.ghn3_run_sequence.restype = C.c_int
     lib.ghn3_run_sequence.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.ghn3_convert_f32.restype = C.c_int

@@ -364,3 +364,45 @@ def edge_lut_bwd(edge_embed, w1, b1, w2, d_lut, vmax, grads):
                          d_b2=L.ptr(grads['b2']))
     L.call('edge_lut_bwd', a, L.current_stream())
     return grads
+
+
+class FusedGraphormer:
+    """Workspace + argument struct of ghn3_graphormer_fused (the persistent Graphormer-stack kernel, bf16) for one
+    (stacked weights, total_nodes). `wstack` = dict of bf16 tensors w_qkv [L*3C, C], w_out [L*C, C], w_ff1 [L*4C, C],
+    w_ff2 [L*C, 4C]; `layers_dev` = uint8 device tensor holding the ghn3_layer_weights table (fp32 vectors)."""
+
+    def __init__(self, hid, heads, layers, wstack, layers_dev, total_nodes, device, x=None):
+        N, C = total_nodes, hid
+        self.wstack, self.layers_dev = wstack, layers_dev
+        E = lambda *s, dtype=torch.bfloat16: torch.empty(*s, dtype=dtype, device=device)
+        self.x = E(N, C, dtype=torch.float32) if x is None else x
+        self.ao, self.qkv, self.ff = E(N, C), E(2, N, 3 * C), E(N, 4 * C)
+        self.sync = torch.zeros(int(L.load().ghn3_graphormer_fused_sync_ints(N)), dtype=torch.int32, device=device)
+        self.args = L.GraphormerFusedArgs(hid=C, heads=heads, layers=layers, w_qkv=L.ptr(wstack['w_qkv']),
+                                          w_out=L.ptr(wstack['w_out']), w_ff1=L.ptr(wstack['w_ff1']),
+                                          w_ff2=L.ptr(wstack['w_ff2']), layers_dev=L.ptr(layers_dev), total_nodes=N,
+                                          x=L.ptr(self.x), ao=L.ptr(self.ao), qkv=L.ptr(self.qkv), ff=L.ptr(self.ff),
+                                          sync=L.ptr(self.sync))
+
+    def bind(self, pack, lut):
+        a = self.args
+        a.n_graphs, a.max_nodes, a.lut_size = pack.n_graphs, pack.max_nodes, lut.shape[1]
+        a.node_off, a.mat_off = L.ptr(pack.d['node_off']), L.ptr(pack.d['mat_off'])
+        a.pair, a.lut = L.ptr(pack.pair), L.ptr(lut)
+        self._keep = (pack, lut)
+
+    def run(self, stop_after=0, max_ctas=0):
+        self.args.stop_after, self.args.max_ctas = stop_after, max_ctas
+        L.call('graphormer_fused', self.args, L.current_stream())
+        return self.x
+
+
+def layer_table(layer_tensors, device):
+    """Uploads a ghn3_layer_weights table: `layer_tensors` = list (per layer) of dicts name -> tensor."""
+    import ctypes as ct
+    tab = (L.LayerWeights * len(layer_tensors))()
+    for l, t in enumerate(layer_tensors):
+        for k, v in t.items():
+            setattr(tab[l], k, v.data_ptr())
+    raw = np.frombuffer(bytes(tab), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)

@@ -311,6 +311,43 @@ typedef struct {
 int ghn3_graphormer_stack(const ghn3_graphormer_args* args, ghn3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * (3c) The same L Graphormer layers (ghn3/graphormer.py:119-142,208-248; ghn3/nn.py:258-261) as ONE persistent
+ * kernel for small batches (total_nodes up to a few thousand), bf16 operands. One CTA per SM walks the layers; per
+ * layer five stages of tiles -- LN1+QKV GEMM, attention, out-proj (+residual), LN2+FFN1 (+GELU), FFN2 (+residual,
+ * split-K) -- whose only synchronisation is a set of per-16-row arrival counters in global memory (no grid barrier,
+ * no kernel boundary). GEMM tiles are 128 weight rows (UMMA M) x rb activation rows (UMMA N) on tcgen05 with the
+ * accumulator in TMEM; weight blocks stream through a TMA ring that runs ahead of the dependencies; LayerNorm is the
+ * prologue of the GEMM that consumes it; attention is the flash-style mma.sync kernel of (3b).
+ * Weights of all layers are stacked along rows so that four TMA descriptors cover the stack. The final LayerNorm
+ * is NOT included (run ghn3_layernorm afterwards).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t hid, heads, layers;
+  const void* w_qkv;                       /* bf16 [layers*3C][C] */
+  const void* w_out;                       /* bf16 [layers*C][C]  */
+  const void* w_ff1;                       /* bf16 [layers*4C][C] */
+  const void* w_ff2;                       /* bf16 [layers*C][4C] */
+  const ghn3_layer_weights* layers_dev;    /* DEVICE array [layers]: only the fp32 vectors (ln*, b_*) are read */
+  int32_t n_graphs, total_nodes, max_nodes, lut_size;
+  const int32_t* node_off;
+  const int64_t* mat_off;
+  const uint16_t* pair;
+  const float* lut;
+  float* x;                  /* in/out [total_nodes][C] fp32 residual stream */
+  void* ao;                  /* bf16 [total_nodes][C]      attention output            */
+  void* qkv;                 /* bf16 [2][total_nodes][3C]  (double-buffered by layer)  */
+  void* ff;                  /* bf16 [total_nodes][4C]                                 */
+  int32_t* sync;             /* int32 [ghn3_graphormer_fused_sync_ints(total_nodes)] arrival counters (zeroed here) */
+  int32_t stop_after;        /* bring-up aid: > 0 stops after that many stages (5 per layer); 0 = run everything */
+  int32_t max_ctas;          /* 0 = one CTA per SM */
+} ghn3_graphormer_fused_args;
+
+int64_t ghn3_graphormer_fused_sync_ints(int32_t total_nodes);
+int ghn3_graphormer_fused(const ghn3_graphormer_fused_args* args, ghn3_stream_t stream);
+/* bring-up aid: [n_ctas][1024][3] int64 (tag, clock64, globaltimer) records per CTA; NULL switches tracing off */
+int ghn3_debug_fused_trace(void* device_buffer);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * (4b) Tile / slice / normalise / scatter -- replaces _tile_params + _normalize + _set_params
  * (ghn3/nn.py:422-506, 554-592, 508-552): every predicted tensor of a model is written straight into the target
  * parameter storage by ONE launch driven by a descriptor table.
