@@ -149,6 +149,7 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
       case GHN3_OP_EDGE_LUT_BWD: rc = ghn3_edge_lut_bwd((const ghn3_edge_lut_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_FC_BWD: rc = ghn3_fc_bwd((const ghn3_fc_bwd_args*)ops[i].args, stream); break;
       case GHN3_OP_RELU_TRANSPOSE_BWD: rc = ghn3_relu_transpose_bwd((const ghn3_relu_transpose_bwd_args*)ops[i].args, stream); break;
+      case GHN3_OP_GRAPHORMER_FUSED: rc = ghn3_graphormer_fused((const ghn3_graphormer_fused_args*)ops[i].args, stream); break;
       case GHN3_OP_LAYERNORM: rc = ghn3_layernorm((const ghn3_layernorm_args*)ops[i].args, stream); break;
       case GHN3_OP_EXPAND_COLS: rc = ghn3_expand_cols((const ghn3_expand_args*)ops[i].args, stream); break;
       case GHN3_OP_MEMSET: {

@@ -38,6 +38,14 @@ DTYPES = {'bf16': (ops.BF16, False), 'tf32': (ops.TF32, True), 'tf32x1': (ops.TF
 # LayerNorm launch (58 CTAs, ~3 us with programmatic dependent launch) does not.
 FUSE_LN = bool(int(__import__('os').environ.get('GHN3_FUSE_LN', '0')))
 
+# The Graphormer stack as ONE persistent kernel (ghn3_graphormer_fused, csrc/graphormer_fused.cu) for bf16 predictions of
+# small batches. Parity-tested (tests/test_fused_gpu.py, test_predict_gpu.py) and on par with the 7-launches-per-layer
+# chain in isolation (1.04 vs 1.03 ms at 457 nodes, profiles/r2_fused_graphormer_trace.txt), but it holds every SM
+# (one 205 KB CTA each), so the decoders of the previous call cannot run beside it: OFF by default, `ghn.fused_graphormer
+# = True` or GHN3_FUSED=1 turns it on.
+FUSED_DEFAULT = bool(int(__import__('os').environ.get('GHN3_FUSED', '0')))
+FUSED_MAX_NODES = int(__import__('os').environ.get('GHN3_FUSED_MAX_NODES', '1024'))
+
 
 def log(*a, **k):
     print(*a, **k)
@@ -257,11 +265,11 @@ class GHN3(GHN):
 
         refresh_ops = []                                   # (entry point, args): replayed by ONE ghn3_run_sequence call
 
-        def cv(p):
+        def cv(p, out=None):
             if x3:                                         # x3 keeps the fp32 master weights
                 return f(p)
             src = f(p)
-            buf = ops.convert(src, dt)
+            buf = ops.convert(src, dt, out=out)
             if src.data_ptr() == p.data_ptr():             # aliasing fp32 parameter: a prebuilt conversion op
                 refresh_ops.append(('elementwise', L.ElementwiseArgs(op=L.EW_COPY, n=src.numel(), a=src.data_ptr(),
                                                                      a_dtype=ops.F32, b=None, b_dtype=0,
@@ -288,15 +296,34 @@ class GHN3(GHN):
         refresh.append(refresh_luts)
         layers = (L.LayerWeights * self.layers)()
         keep = []
+        # bf16 GEMM weights of all layers stacked along rows: four TMA descriptors cover the stack (fused kernel); the
+        # per-layer tensors used everywhere else are views of the stacks
+        stacks = None
+        if not x3 and dt == ops.BF16:
+            Ln = self.layers
+            stacks = {'w_qkv': torch.empty(Ln * 3 * C, C, dtype=torch.bfloat16, device=dev),
+                      'w_out': torch.empty(Ln * C, C, dtype=torch.bfloat16, device=dev),
+                      'w_ff1': torch.empty(Ln * 4 * C, C, dtype=torch.bfloat16, device=dev),
+                      'w_ff2': torch.empty(Ln * C, 4 * C, dtype=torch.bfloat16, device=dev)}
+
+        def cvs(p, kind, l):
+            if stacks is None:
+                return cv(p)
+            rows = p.shape[0]
+            return cv(p, out=stacks[kind][l * rows:(l + 1) * rows])
         for l, layer in enumerate(self.gnn):
-            t = dict(ln1_w=f(layer.ln1.weight), ln1_b=f(layer.ln1.bias), w_qkv=cv(layer.attn.to_qkv.weight),
-                     w_out=cv(layer.attn.to_out[0].weight), b_out=f(layer.attn.to_out[0].bias),
-                     ln2_w=f(layer.ln2.weight), ln2_b=f(layer.ln2.bias), w_ff1=cv(layer.ff.net[0].weight),
-                     b_ff1=f(layer.ff.net[0].bias), w_ff2=cv(layer.ff.net[3].weight), b_ff2=f(layer.ff.net[3].bias))
+            t = dict(ln1_w=f(layer.ln1.weight), ln1_b=f(layer.ln1.bias), w_qkv=cvs(layer.attn.to_qkv.weight, 'w_qkv', l),
+                     w_out=cvs(layer.attn.to_out[0].weight, 'w_out', l), b_out=f(layer.attn.to_out[0].bias),
+                     ln2_w=f(layer.ln2.weight), ln2_b=f(layer.ln2.bias), w_ff1=cvs(layer.ff.net[0].weight, 'w_ff1', l),
+                     b_ff1=f(layer.ff.net[0].bias), w_ff2=cvs(layer.ff.net[3].weight, 'w_ff2', l),
+                     b_ff2=f(layer.ff.net[3].bias))
             keep.append(t)
             for k, v in t.items():
                 setattr(layers[l], k, v.data_ptr())
         w['layers'], w['layers_keep'] = layers, keep
+        w['wstack'] = stacks
+        # the same table on the device (the fused kernel reads the fp32 vectors' addresses from it)
+        w['layers_dev'] = torch.from_numpy(np.frombuffer(bytes(layers), dtype=np.uint8).copy()).to(dev)
         w['ln_w'], w['ln_b'] = f(self.ln.weight), f(self.ln.bias)
         dec = self.decoder
         # fc weight repacked position-major: [c*S*S + p][k] -> [p][c][k], so one decoder-grid position is one
@@ -324,7 +351,7 @@ class GHN3(GHN):
 
     def _run_refresh(self, w):
         """Re-derives every device copy from the current parameter values (same buffers, same addresses)."""
-        self.flush()                             # overlapped predictions may still be reading the old copies
+        self.flush_all()                         # overlapped predictions may still be reading the old copies
         ops_ = w['refresh_ops']
         if ops_:
             seq = w['refresh_seq']
@@ -461,16 +488,44 @@ class GHN3(GHN):
     def _run(self, w, pack, bp, return_embeddings):
         """Executes the device program of this (batch plan, weight version): ONE C call enqueues every kernel."""
         device = self.embed.weight.device
-        prog = getattr(bp, 'program', None)
-        if prog is None or prog.w is not w or prog.device != device or prog.want_emb != bool(return_embeddings):
-            prog = _Program(self, w, bp, device, bool(return_embeddings))
-            bp.program = prog
+        prof = getattr(self, '_profile', None)
+        overlap = bool(getattr(self, 'overlap_scatter', False)) and prof is None
+        # `pipeline_depth` (overlapped mode only): that many programs -- each with its own activation buffers and its own
+        # high-priority stream -- take successive calls on the same batch plan in turn, so the latency-bound Graphormer
+        # chains of calls k and k+1 run side by side; decoders + scatter of every call stay ordered on ONE side stream
+        depth = max(1, int(getattr(self, 'pipeline_depth', 1))) if overlap else 1
+        progs = bp.__dict__.setdefault('programs', [])
+        want = bool(return_embeddings)
+        if any(p_.w is not w or p_.device != device or p_.want_emb != want for p_ in progs):
+            self.flush_all()
+            del progs[:]
+        slot = bp.__dict__.get('next_slot', 0) % depth
+        while len(progs) <= slot:
+            progs.append(_Program(self, w, bp, device, want, slot=len(progs)))
+        prog = progs[slot]
+        bp.next_slot = slot + 1
+        bp.program = prog
         prog.bind_pack(pack)
         prog.refresh_targets(self.weight_norm)
-        prof = getattr(self, '_profile', None)
-        prog.run(prof, overlap=bool(getattr(self, 'overlap_scatter', False)) and prof is None)
+        prog.run(prof, overlap=overlap)
         self.last_program = prog
         return prog.emb
+
+    def _overlap_streams(self, device, slot):
+        """(high-priority stream of program slot `slot`, the one side stream every program's decoders + scatter use)."""
+        ov = self.__dict__.setdefault('_ov_streams', {})
+        st = ov.get(device)
+        if st is None:
+            st = ov[device] = {'side': torch.cuda.Stream(device=device), 'hi': []}
+        while len(st['hi']) <= slot:
+            st['hi'].append(torch.cuda.Stream(device=device, priority=-1))
+        return st['hi'][slot], st['side']
+
+    def flush_all(self):
+        """Waits (on the current stream) for every overlapped prediction in flight, whatever program ran it."""
+        for st in self.__dict__.get('_ov_streams', {}).values():
+            for strm in [st['side']] + st['hi']:
+                torch.cuda.current_stream().wait_stream(strm)
 
     def result_stream(self):
         """The stream on which the last prediction's parameters (and predicted_sumsq) become final: the side stream in
@@ -536,11 +591,12 @@ class _Program:
     once; per call only the graph-pack pointers and (if they moved) the target-parameter addresses are patched.
     """
     OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6,
-          'graphormer_train_fwd': 7, 'layernorm': 21}
+          'graphormer_train_fwd': 7, 'layernorm': 21, 'graphormer_fused': 22}
 
-    def __init__(self, ghn, w, bp, device, want_emb, train=False):
+    def __init__(self, ghn, w, bp, device, want_emb, train=False, slot=0):
         self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
         self.train = train
+        self.slot = slot
         dt, x3, act = w['dtype'], w['x3'], w['act']
         tdt = ops.TORCH_DTYPE[dt]
         C, H = ghn.hid, ghn.heads
@@ -592,7 +648,15 @@ class _Program:
             # the final LayerNorm (-> decoder input rows) is its own op so that the overlapped mode can order it after
             # the previous call's decoders
             self.ga.skip_final_ln = 1
-            self.ops.append(('graphormer', 'graphormer_stack', self.ga))
+            D = C // H
+            self.fused = None
+            if (getattr(ghn, 'fused_graphormer', FUSED_DEFAULT) and dt == ops.BF16 and not x3
+                    and w['wstack'] is not None and N <= FUSED_MAX_NODES and C % 64 == 0 and C <= 384
+                    and D in (8, 16, 24) and len(bp.plans) <= 256):
+                self.fused = ops.FusedGraphormer(C, H, ghn.layers, w['wstack'], w['layers_dev'], N, device, x=self.x)
+                self.ops.append(('graphormer', 'graphormer_fused', self.fused.args))
+            else:
+                self.ops.append(('graphormer', 'graphormer_stack', self.ga))
             self.final_ln = L.LayerNormArgs(rows=N, hid=C, x=L.ptr(self.x), gamma=L.ptr(w['ln_w']), beta=L.ptr(w['ln_b']),
                                             out=L.ptr(self.dec_in), out_dtype=act, dst_row=L.ptr(st['dst_row']),
                                             out_f32=L.ptr(self.emb))
@@ -702,6 +766,8 @@ class _Program:
         ga.n_graphs, ga.max_nodes, ga.lut_size = pack.n_graphs, pack.max_nodes, lut.shape[1]
         ga.node_off, ga.mat_off = L.ptr(pack.d['node_off']), L.ptr(pack.d['mat_off'])
         ga.pair, ga.lut = L.ptr(pack.pair), L.ptr(lut)
+        if getattr(self, 'fused', None) is not None:
+            self.fused.bind(pack, lut)
         self.bound_pack = pack
 
     def refresh_targets(self, weight_norm):
@@ -758,6 +824,8 @@ class _Program:
         cur = torch.cuda.current_stream()
         ev_prev = getattr(self, 'ev_scatter', None)
         draw_tok = self.bp.n_tok_elems > 0       # ViT class-token rows: fresh N(0, 0.02) draws as in nn.py:446
+        if not (prof is None and overlap and self.n_desc):
+            self.ghn.flush_all()                 # earlier overlapped calls (any program slot) write the same targets
         if prof is None and not (overlap and self.n_desc):
             if ev_prev is not None:              # an earlier overlapped call: its scatter still reads our buffers
                 cur.wait_event(ev_prev)
@@ -772,10 +840,10 @@ class _Program:
             # are independent, so the HBM-write-bound scatter of call k runs under the latency-bound Graphormer of
             # call k+1. The caller must use GHN3.flush() before touching the predicted parameters.
             if getattr(self, 'side', None) is None:
-                # the Graphormer stack runs on a HIGH-priority stream, decoders + scatter on a normal one: when the two
-                # compete for SM slots the block scheduler serves the latency-bound chain first
-                self.hi = torch.cuda.Stream(device=self.device, priority=-1)
-                self.side = torch.cuda.Stream(device=self.device)
+                # the Graphormer stack runs on a HIGH-priority stream (one per program slot), decoders + scatter on a
+                # normal one shared by all programs (their scatters write the same targets: stream order = call order):
+                # when the two compete for SM slots the block scheduler serves the latency-bound chain first
+                self.hi, self.side = self.ghn._overlap_streams(self.device, self.slot)
                 self.i_ln = next(i for i, (_, name_, _) in enumerate(self.ops) if name_ == 'layernorm')
                 self.ev_a = torch.cuda.Event()
                 self.ev_dec = None

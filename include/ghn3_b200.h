@@ -665,7 +665,7 @@ enum ghn3_opcode {
   GHN3_OP_GRAPHORMER_TRAIN_FWD = 7, GHN3_OP_GRAPHORMER_BWD = 8, GHN3_OP_TRANSPOSE = 9, GHN3_OP_ELEMENTWISE = 10,
   GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
   GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18,
-  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21
+  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21, GHN3_OP_GRAPHORMER_FUSED = 22
 };
 /* GHN3_OP_MEMSET: args points to a ghn3_memset_args; clears `bytes` bytes at `ptr` (cudaMemsetAsync). */
 typedef struct { void* ptr; int64_t bytes; } ghn3_memset_args;

@@ -19,15 +19,16 @@ DEV = 'cuda'
 TOL = {'tf32': 1e-3, 'tf32x1': 4e-3, 'bf16': 2e-2}
 
 
-def make_ghn(cfg_name, dtype):
+def make_ghn(cfg_name, dtype, fused=False):
     cfg = CONFIGS[cfg_name]
     ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
     ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn.fused_graphormer = fused
     return ghn.to(DEV).eval(), cfg
 
 
-def run_case(cfg_name, archs, dtype, check_logits=True):
-    ghn, cfg = make_ghn(cfg_name, dtype)
+def run_case(cfg_name, archs, dtype, check_logits=True, fused=False):
+    ghn, cfg = make_ghn(cfg_name, dtype, fused)
     sd = procedural_state_dict(cfg, 0)
     recs = [H.graph_records()[a] for a in archs]
     models = [H.build_model(a).to(DEV) for a in archs]
@@ -36,6 +37,7 @@ def run_case(cfg_name, archs, dtype, check_logits=True):
         out, emb = ghn(models if len(models) > 1 else models[0], graphs if len(graphs) > 1 else graphs[0],
                        return_embeddings=True)
     torch.cuda.synchronize()
+    assert (ghn.last_program.fused is not None) == fused, 'fused Graphormer kernel not on the path that was asked for'
     out = out if isinstance(out, list) else [out]
     off = 0
     worst = {}
@@ -145,6 +147,13 @@ def test_cpu_model_gets_device_params_and_no_cpu_fallback():
 def test_xl_bench_models(arch, dtype):
     """BASELINE.json config 2: ghn3xlm16 (random-init) on ViT-B/16 and ConvNeXt-Base."""
     run_case('ghn3xlm16', [arch], dtype)
+
+
+@pytest.mark.parametrize('cfg_name,archs', [('ghn3tm8', ['resnet50']), ('ghn3lm8', ['resnet18', 'swin_v2_t']),
+                                            ('ghn3xlm16', ['vit_b_16', 'convnext_base'])])
+def test_fused_graphormer_end_to_end(cfg_name, archs):
+    """ghn.fused_graphormer = True: the persistent one-kernel Graphormer stack on the prediction path (bf16)."""
+    run_case(cfg_name, archs, 'bf16', check_logits=False, fused=True)
 
 
 def test_trace_on_the_fly_graphs_none():
