@@ -216,7 +216,13 @@ class AdamWArgs(C.Structure):
     _fields_ = [('params', vp), ('grads', vp), ('exp_avg', vp), ('exp_avg_sq', vp), ('offsets', vp), ('numels', vp),
                 ('chunk0', vp), ('chunk_tensor', vp), ('n_chunks', i64), ('total', i64), ('lr', f32), ('beta1', f32),
                 ('beta2', f32), ('eps', f32), ('weight_decay', f32), ('bias_correction1', f32),
-                ('bias_correction2', f32), ('max_norm', f32), ('sumsq', vp)]
+                ('bias_correction2', f32), ('max_norm', f32), ('sumsq', vp), ('loss', vp), ('skipped', vp)]
+
+
+class SegnormArgs(C.Structure):
+    _fields_ = [('src', vp), ('seg_off', vp), ('seg_numel', vp), ('chunk0', vp), ('chunk_seg', vp), ('n_chunks', i64),
+                ('n_segs', i32), ('mode', i32), ('sumsq', vp), ('total', vp), ('grad', vp), ('gscale', vp),
+                ('coef', f32)]
 
 
 class MemsetArgs(C.Structure):
@@ -253,7 +259,7 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
-                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin']
+                 'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin', 'ghn3_segnorm']
 SYMBOLS_ALL = SYMBOLS + TRAIN_SYMBOLS
 
 _lib = None

@@ -904,6 +904,15 @@ __global__ void __launch_bounds__(256) adamw_kernel(const ghn3_adamw_args a) {
   float* __restrict__ m = a.exp_avg + off;
   float* __restrict__ v = a.exp_avg_sq + off;
   float coef = 1.f;
+  if (a.skipped != nullptr) {
+    // non-finite guard: fminf(1, NaN) = 1 and inf * 0 = NaN would otherwise poison the parameters and both moments
+    const double ss = *a.sumsq;
+    const bool bad = !(ss == ss) || ss > 1e300 || (a.loss != nullptr && !isfinite(*a.loss));
+    if (bad) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.skipped, 1);
+      return;
+    }
+  }
   if (a.max_norm > 0.f) {
     const float norm = sqrtf((float)*a.sumsq);
     coef = fminf(1.f, a.max_norm / (norm + 1e-6f));        // nn.utils.clip_grad_norm_
@@ -944,9 +953,77 @@ __global__ void __launch_bounds__(256) adamw_kernel(const ghn3_adamw_args a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frobenius-norm regulariser of the predicted parameters (ghn3_segnorm): one pass for the per-tensor sums of squares,
+// one tiny kernel for the total, one pass for the gradient -- instead of one torch.norm (+ its backward) per tensor.
+__global__ void __launch_bounds__(256) segnorm_sumsq_kernel(const ghn3_segnorm_args a) {
+  const int s = a.chunk_seg[blockIdx.x];
+  const int64_t n = a.seg_numel[s];
+  const int64_t c0 = ((int64_t)blockIdx.x - a.chunk0[s]) * GHN3_ADAMW_CHUNK;
+  const int64_t c1 = min(c0 + (int64_t)GHN3_ADAMW_CHUNK, n);
+  const float* __restrict__ v = a.src + a.seg_off[s];
+  float acc = 0.f;
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += 256) acc = fmaf(v[i], v[i], acc);
+  double d = (double)warp_sum(acc);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(a.sumsq + s, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) segnorm_total_kernel(const ghn3_segnorm_args a) {
+  double acc = 0;
+  for (int s = threadIdx.x; s < a.n_segs; s += 256) acc += sqrt(a.sumsq[s]);
+  __shared__ double part[256];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.total = (float)(part[0] * (double)a.coef);
+}
+
+__global__ void __launch_bounds__(256) segnorm_grad_kernel(const ghn3_segnorm_args a) {
+  const int s = a.chunk_seg[blockIdx.x];
+  const int64_t n = a.seg_numel[s];
+  const int64_t c0 = ((int64_t)blockIdx.x - a.chunk0[s]) * GHN3_ADAMW_CHUNK;
+  const int64_t c1 = min(c0 + (int64_t)GHN3_ADAMW_CHUNK, n);
+  const double ss = a.sumsq[s];
+  if (!(ss > 0)) return;                                  // d||p|| / dp is taken as 0 at p = 0
+  const float k = (a.gscale ? *a.gscale : 1.f) * a.coef * (float)(1.0 / sqrt(ss));
+  const float* __restrict__ v = a.src + a.seg_off[s];
+  float* __restrict__ g = a.grad + a.seg_off[s];
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += 256) g[i] = fmaf(k, v[i], g[i]);
+}
+
 }  // namespace ghn3
 
 using namespace ghn3;
+
+extern "C" int ghn3_segnorm(const ghn3_segnorm_args* a, ghn3_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GHN3_REQUIRE(a != nullptr, "ghn3_segnorm: null args");
+  if (a->n_chunks <= 0 || a->n_segs <= 0) return GHN3_OK;
+  GHN3_REQUIRE(a->src && a->seg_off && a->seg_numel && a->chunk0 && a->chunk_seg && a->sumsq, "ghn3_segnorm: null pointer");
+  if (a->mode == 0) {
+    GHN3_REQUIRE(a->total != nullptr, "ghn3_segnorm: mode 0 needs `total`");
+    GHN3_CUDA(cudaMemsetAsync(a->sumsq, 0, sizeof(double) * (size_t)a->n_segs, stream));
+    segnorm_sumsq_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(*a);
+    GHN3_LAUNCH_CHECK("segnorm_sumsq_kernel");
+    segnorm_total_kernel<<<1, 256, 0, stream>>>(*a);
+    GHN3_LAUNCH_CHECK("segnorm_total_kernel");
+  } else {
+    GHN3_REQUIRE(a->grad != nullptr, "ghn3_segnorm: mode 1 needs `grad`");
+    segnorm_grad_kernel<<<(unsigned)a->n_chunks, 256, 0, stream>>>(*a);
+    GHN3_LAUNCH_CHECK("segnorm_grad_kernel");
+  }
+  return GHN3_OK;
+}
 
 extern "C" int ghn3_transpose(const ghn3_transpose_args* a, ghn3_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1099,8 +1176,8 @@ extern "C" int ghn3_adamw(const ghn3_adamw_args* a, ghn3_stream_t stream_) {
   GHN3_REQUIRE(a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->offsets && a->numels && a->chunk0 &&
                    a->chunk_tensor, "ghn3_adamw: null pointer");
   GHN3_REQUIRE(a->bias_correction1 > 0.f && a->bias_correction2 > 0.f, "ghn3_adamw: bias corrections must be positive");
-  if (a->max_norm > 0.f) {
-    GHN3_REQUIRE(a->sumsq != nullptr, "ghn3_adamw: max_norm > 0 needs the sumsq scratch double");
+  if (a->max_norm > 0.f || a->skipped != nullptr) {
+    GHN3_REQUIRE(a->sumsq != nullptr, "ghn3_adamw: clipping / the non-finite guard need the sumsq scratch double");
     GHN3_CUDA(cudaMemsetAsync(a->sumsq, 0, sizeof(double), stream));
     sumsq_flat_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(a->grads, a->total, a->sumsq);
     GHN3_LAUNCH_CHECK("sumsq_flat_kernel");

@@ -459,8 +459,27 @@ class GHN3(GHN):
         if bp is None or any(a is not b for a, b in zip(bp.plans, plans)):
             bp = BatchPlan(plans, self.config)
             self._plan_cache[key] = bp
-            while len(self._plan_cache) > 1024:
-                self._plan_cache.popitem(last=False)
+            # A batch plan owns its device programs (activation workspaces; in training the saved activations of every
+            # layer, the prediction buffer and a full-size flat gradient buffer) and pins its target networks. Meta-batches
+            # of real GHN training never repeat, so only the few most recent plans are kept: `plan_cache_size` (default 4
+            # in training mode, 1024 plans for inference, where programs are small and loops over a fixed model zoo
+            # do repeat).
+            limit = getattr(self, 'plan_cache_size', None)
+            if limit is None:
+                limit = 4 if self.training else 1024
+            while len(self._plan_cache) > max(1, int(limit)):
+                _, old = self._plan_cache.popitem(last=False)
+                # drop the programs' buffers explicitly: program -> pred_flat -> grad_fn -> ctx -> program is a cycle
+                # through C++ autograd nodes that the garbage collector does not see
+                progs = list(old.__dict__.get('programs', [])) + [old.__dict__.get('program'),
+                                                                   old.__dict__.get('train_program')]
+                for attr in ('program', 'programs', 'train_program', 'dev', 'out_meta'):
+                    old.__dict__.pop(attr, None)
+                for prog in progs:
+                    if prog is not None and prog is not self.__dict__.get('last_program'):
+                        prog.__dict__.clear()
+        else:
+            self._plan_cache.move_to_end(key)
         return bp
 
     def _static_device(self, bp, device):

@@ -39,6 +39,10 @@ class FusedAdamW(torch.optim.Optimizer):
                             chunk_tensor=to_dev(np.repeat(np.arange(len(order), dtype=np.int32), chunks)))
         self._ptrs_host, self._ptrs = None, None
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # non-finite guard (ghn3_adamw_args.skipped): updates skipped on the device because |g|^2 or the loss was not
+        # finite; `loss_for_guard` may be set to a device scalar before step()
+        self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_for_guard = None
         self._step = 0
         self._checked = False
 
@@ -87,7 +91,14 @@ class FusedAdamW(torch.optim.Optimizer):
                         chunk_tensor=t['chunk_tensor'].data_ptr(), n_chunks=self._n_chunks, total=self._total,
                         lr=g['lr'], beta1=b1, beta2=b2, eps=g['eps'], weight_decay=g['weight_decay'],
                         bias_correction1=1.0 - b1 ** self._step, bias_correction2=1.0 - b2 ** self._step,
-                        max_norm=float(g['max_grad_norm'] or 0.0), sumsq=self._sumsq.data_ptr())
+                        max_norm=float(g['max_grad_norm'] or 0.0), sumsq=self._sumsq.data_ptr(),
+                        skipped=self.skipped.data_ptr())
+        lg = self.loss_for_guard
+        if lg is not None:
+            lg = lg.detach().reshape(-1)[:1].float().contiguous()
+            a.loss = lg.data_ptr()
+            self._loss_keep = lg
+            self.loss_for_guard = None
         L.call('adamw', a, L.current_stream())
         return loss
 

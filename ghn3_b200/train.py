@@ -126,7 +126,13 @@ class _Backward:
         # ---- fp32 gradient of every GHN parameter: one flat buffer, views per parameter ----
         params, order, offs, self.early_elems = flat_layout(ghn)
         self.params = params
-        self.gflat = Z(int(offs[-1]))
+        # ONE flat gradient buffer per (GHN, device), shared by the backward programs of every batch plan (2.6 GB at
+        # ghn3xlm16): meta-batches never repeat in real training, so a buffer per plan would grow without bound
+        shared = ghn.__dict__.setdefault('_shared_gflat', {})
+        gf = shared.get(dev)
+        if gf is None or gf.numel() != int(offs[-1]):
+            gf = shared[dev] = Z(int(offs[-1]))
+        self.gflat = gf
         gof = {id(p): self.gflat[int(o):int(o) + p.numel()].view(p.shape) for o, p in zip(offs[:-1], order)}
         self.gviews = [gof[id(p)] for p in params]
         G = lambda p: gof[id(p)]
@@ -601,3 +607,59 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
     # <p, R> stub of the GHN-only training benchmark, costs one kernel instead of one per parameter
     prog.pred_flat = outs[-1]
     return prog.emb
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _PredWd(torch.autograd.Function):
+    """predparam_wd * sum_p ||p||_F over the predicted parameters (reference ghn3/trainer.py:288-294) evaluated on the
+    flat buffer that holds them all: two kernel passes forward (ghn3_segnorm mode 0), one backward (mode 1), instead
+    of a torch.norm + its backward per tensor."""
+
+    @staticmethod
+    def forward(ctx, pred_flat, tables, coef):
+        dev = pred_flat.device
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        a = L.SegnormArgs(src=pred_flat.data_ptr(), seg_off=tables['off'].data_ptr(),
+                          seg_numel=tables['numel'].data_ptr(), chunk0=tables['chunk0'].data_ptr(),
+                          chunk_seg=tables['chunk_seg'].data_ptr(), n_chunks=tables['n_chunks'],
+                          n_segs=tables['n_segs'], mode=0, sumsq=tables['sumsq'].data_ptr(), total=out.data_ptr(),
+                          coef=float(coef))
+        L.call('segnorm', a, L.current_stream())
+        ctx.tables, ctx.coef = tables, float(coef)
+        ctx.save_for_backward(pred_flat)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred_flat, = ctx.saved_tensors
+        t = ctx.tables
+        grad = torch.zeros_like(pred_flat)
+        gs = g.detach().float().contiguous()
+        a = L.SegnormArgs(src=pred_flat.data_ptr(), seg_off=t['off'].data_ptr(), seg_numel=t['numel'].data_ptr(),
+                          chunk0=t['chunk0'].data_ptr(), chunk_seg=t['chunk_seg'].data_ptr(), n_chunks=t['n_chunks'],
+                          n_segs=t['n_segs'], mode=1, sumsq=t['sumsq'].data_ptr(), grad=grad.data_ptr(),
+                          gscale=gs.data_ptr(), coef=ctx.coef)
+        L.call('segnorm', a, L.current_stream())
+        ctx.keep = gs
+        return grad, None, None
+
+
+def predicted_param_decay(ghn, coef):
+    """coef * sum over the predicted parameter tensors of the last keep_grads forward of their Frobenius norms, as a
+    differentiable device scalar."""
+    prog = ghn.last_program
+    meta = prog.bp.out_meta
+    tables = meta.get('segnorm')
+    if tables is None or tables['device'] != prog.device:
+        CH = 8192
+        offs = np.array([o for (o, n, _) in meta['slices']], dtype=np.int64)
+        numels = np.array([n for (o, n, _) in meta['slices']], dtype=np.int64)
+        chunks = (numels + CH - 1) // CH
+        chunk0 = np.concatenate([[0], np.cumsum(chunks)[:-1]]).astype(np.int64)
+        to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(prog.device)
+        tables = {'off': to_dev(offs), 'numel': to_dev(numels), 'chunk0': to_dev(chunk0),
+                  'chunk_seg': to_dev(np.repeat(np.arange(len(offs), dtype=np.int32), chunks)),
+                  'n_chunks': int(chunks.sum()), 'n_segs': len(offs), 'device': prog.device,
+                  'sumsq': torch.zeros(len(offs), dtype=torch.float64, device=prog.device)}
+        meta['segnorm'] = tables
+    return _PredWd.apply(prog.pred_flat, tables, coef)

@@ -87,11 +87,23 @@ class Trainer:
         if self.ddp:
             enable_grad_sync(model)
         opt_args = dict(opt_args or {})
+        if self.ddp:
+            # DistributedDataParallel broadcasts rank 0's parameters and buffers at construction (reference
+            # trainer.py:136); ranks built from different seeds would otherwise diverge silently
+            import torch.distributed as dist
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, 0)
+            if hasattr(model, 'weights_updated'):
+                model.weights_updated()
         params = [p for p in model.parameters() if p.requires_grad]
         self._fused_clip = False
         if isinstance(opt, str):
             name = opt.lower()
-            if name == 'adamw' and opt_args.pop('fused_clip', True) and hasattr(model, 'decoder_1d'):
+            fused_clip = opt_args.pop('fused_clip', True)
+            if name != 'sgd':
+                opt_args.pop('momentum', None)              # as the reference does for adam / adamw (trainer.py:176)
+            if name == 'adamw' and fused_clip and hasattr(model, 'decoder_1d'):
                 # clipping + AdamW in one pass over the backward pass's flat gradient buffer (ghn3_adamw)
                 from .optim import FusedAdamW
                 self._optimizer = FusedAdamW(model, max_grad_norm=grad_clip, **opt_args)
@@ -106,7 +118,8 @@ class Trainer:
                 raise NotImplementedError(opt)
         else:
             self._optimizer = opt
-        self._scheduler = scheduler
+        self._scheduler = self._make_scheduler(scheduler, unused.get('scheduler_args'), unused.get('epochs', 300),
+                                               opt_args.get('lr'))
         self._step = 0
         self.skipped_updates = 0
         self.reset_metrics()
@@ -119,6 +132,7 @@ class Trainer:
             if dist.get_rank() != 0:
                 return
         self._model.flush()
+        self.check_finite()                    # never checkpoint a state whose last steps were non-finite
         sd = {'state_dict': self._model.state_dict(), 'optimizer': self._optimizer.state_dict(), 'epoch': epoch,
               'step': step}
         sd.update(config or {'config': {k: self._model.config[k] for k in ('max_shape', 'num_classes', 'hid', 'heads',
@@ -135,6 +149,37 @@ class Trainer:
     def scheduler_step(self):
         if self._scheduler is not None:
             self._scheduler.step()
+
+    def _make_scheduler(self, scheduler, scheduler_args, epochs, lr):
+        """Scheduler objects pass through; the reference's strings (trainer.py:180-207: 'cosine-warmup[-steps5-init_lr1e-5]',
+        'cosine', 'step', 'mstep') are built here over the (fused) optimizer."""
+        if scheduler is None or not isinstance(scheduler, str):
+            return scheduler
+        import math
+        from torch.optim.lr_scheduler import CosineAnnealingLR, LambdaLR, MultiStepLR, StepLR
+        if scheduler.startswith('cosine-warmup'):
+            def parse_arg(arg, default):
+                p = scheduler.find(arg)
+                if p <= 0:
+                    return default
+                p_end = scheduler[p:].find('-')
+                return float(scheduler[p + len(arg):len(scheduler) if p_end == -1 else p + p_end])
+            warmup_steps = int(parse_arg('steps', 5))
+            warmup_lr = parse_arg('init_lr', 1e-5) / lr
+
+            def lr_lambda(step):
+                if step < warmup_steps - 1:
+                    return warmup_lr + (1 - warmup_lr) * step / max(warmup_steps - 1, 1)
+                progress = float(step - warmup_steps) / float(max(1, epochs - warmup_steps))
+                return max(0.0, 0.5 * (1. + math.cos(math.pi * progress)))
+            return LambdaLR(self._optimizer, lr_lambda=lr_lambda)
+        if scheduler == 'cosine':
+            return CosineAnnealingLR(self._optimizer, epochs)
+        if scheduler == 'step':
+            return StepLR(self._optimizer, **(scheduler_args or {}))
+        if scheduler == 'mstep':
+            return MultiStepLR(self._optimizer, **(scheduler_args or {}))
+        raise NotImplementedError('scheduler %r (the reference knows cosine-warmup*, cosine, step, mstep)' % scheduler)
 
     # ------------------------------------------------------------------------------------------------------------
     def update(self, images, targets, graphs=None, models=None, loss_fn=None):
@@ -156,11 +201,10 @@ class Trainer:
         models = models if isinstance(models, (list, tuple)) else [models]
         loss_predwd = None
         if self.predparam_wd > 0:
-            total = 0
-            for m in models:
-                for p in m.parameters():
-                    total = total + torch.norm(p, p='fro')
-            loss_predwd = self.predparam_wd * total
+            # predparam_wd * sum_p ||p||_F (trainer.py:288-294) over the predicted tensors, on the device: three kernel
+            # passes over the flat prediction buffer instead of one torch.norm (+ backward) per tensor
+            from .train import predicted_param_decay
+            loss_predwd = predicted_param_decay(ghn, self.predparam_wd)
         logits = None
         if loss_fn is not None:
             loss = loss_fn(models)
@@ -181,6 +225,11 @@ class Trainer:
         loss.backward()                                             # GHN adjoint + gradient all-reduce inside
         if self.grad_clip > 0 and not self._fused_clip:
             nn.utils.clip_grad_norm_([p for g in self._optimizer.param_groups for p in g['params']], self.grad_clip)
+        if self._fused_clip and not self.ddp:
+            # non-finite guard on the device (reference trainer.py:240-257 checks the loss before the update): the
+            # fused step skips parameters AND moments when |g|^2 or the loss is not finite. Under data parallelism only
+            # |g|^2 of the averaged gradient is used, so that every rank takes the same decision.
+            self._optimizer.loss_for_guard = loss
         self._optimizer.step()
 
         # metrics: one packed device tensor, one all-reduce, one host read
@@ -207,9 +256,22 @@ class Trainer:
         if logits is not None:
             self.metrics['top1'].update(packed[i], n)
             self.metrics['top5'].update(packed[i + 1], n)
-        if (self._step + 1) % max(self.log_interval, 1) == 0:       # the reference checks every step (trainer.py:240)
-            avg = self.metrics['loss'].avg
-            if avg != avg:
-                raise RuntimeError('the loss is NaN at step %d, unable to proceed' % self._step)
+        if (self._step + 1) % max(self.log_interval, 1) == 0:
+            # The update itself is guarded on the device every step; here (one host read per log interval) the count of
+            # skipped updates is fetched and, as in the reference (trainer.py:240-257), a single process stops on a NaN
+            # loss while data-parallel runs keep going with the poisoned steps skipped.
+            self.check_finite()
         self._step += 1
         return self.metrics
+
+    def check_finite(self):
+        """Reads the device-side skip counter (one synchronisation); raises outside data parallelism if updates were
+        skipped because the loss / gradients were not finite."""
+        if self._fused_clip:
+            self.skipped_updates = int(self._optimizer.skipped.item())
+        avg = self.metrics['loss'].avg
+        if (avg != avg or self.skipped_updates > 0) and not self.ddp:
+            raise RuntimeError('the loss is NaN (or the gradients are not finite) at step %d: %d update(s) were skipped '
+                               'on the device; unable to proceed. Restarting from the last checkpoint may help.'
+                               % (self._step, self.skipped_updates))
+        return self.skipped_updates

@@ -601,8 +601,33 @@ typedef struct {
   int64_t n_chunks; int64_t total;   /* total = elements of the flat buffers */
   float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_norm;
   double* sumsq;
+  /* Non-finite guard (reference trainer.py:240-257 skips / raises on a NaN loss BEFORE the update): when `skipped` is
+   * given, |g|^2 is always computed and the whole step -- parameters AND both moments -- is skipped on the device if
+   * |g|^2 or *loss (optional, one device float) is not finite; *skipped is incremented. No host synchronisation.
+   * Under data parallelism the gradients are already averaged over ranks, so every rank takes the same decision. */
+  const float* loss;
+  int32_t* skipped;
 } ghn3_adamw_args;
 int ghn3_adamw(const ghn3_adamw_args* args, ghn3_stream_t stream);
+
+/* Predicted-parameter regularisation of the training loss (reference ghn3/trainer.py:288-294:
+ * loss += predparam_wd * sum_p ||p||_F over the predicted tensors) on the flat buffer that holds every predicted
+ * parameter of the meta-batch: segment s = elements [seg_off[s], seg_off[s] + seg_numel[s]). Chunk tables as in
+ * ghn3_adamw (GHN3_ADAMW_CHUNK elements per chunk).
+ *   mode 0 (forward) : sumsq[s] = sum v^2 (double), then *total = coef * sum_s sqrt(sumsq[s])
+ *   mode 1 (backward): grad[i] += (*gscale) * coef * src[i] / sqrt(sumsq[s])   (0 where the norm is 0) */
+typedef struct {
+  const float* src;
+  const int64_t* seg_off; const int64_t* seg_numel; const int64_t* chunk0;   /* device [n_segs] */
+  const int32_t* chunk_seg;                                                  /* device [n_chunks] */
+  int64_t n_chunks; int32_t n_segs; int32_t mode;
+  double* sumsq;             /* device [n_segs] */
+  float* total;              /* mode 0: one device float */
+  float* grad;               /* mode 1: flat, same layout as src */
+  const float* gscale;       /* mode 1: one device float (upstream gradient), NULL = 1 */
+  float coef;
+} ghn3_segnorm_args;
+int ghn3_segnorm(const ghn3_segnorm_args* args, ghn3_stream_t stream);
 
 /* Graphormer stack, training flavour. ghn3_graphormer_train_fwd computes the same function as ghn3_graphormer_stack
  * (fwd.x is ignored: the input node features are xs[0]) but keeps every activation of every layer;

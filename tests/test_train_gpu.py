@@ -367,3 +367,79 @@ def test_trainer_checkpoint_round_trip(tmp_path):
     torch.cuda.synchronize()
     for (n, a), b in zip(ghn.named_parameters(), ghn2.parameters()):
         assert H.max_rel_err(a, b) < 1e-4, n
+
+
+def test_predparam_wd_on_device_matches_per_tensor_norms():
+    """Trainer's predparam_wd term (reference trainer.py:288-294) via ghn3_segnorm: value and gradient against
+    torch.norm on every predicted tensor."""
+    from ghn3_b200.train import predicted_param_decay
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    models = ghn([H.build_model('resnet18').to(DEV), H.build_model('squeezenet1_1').to(DEV)],
+                 [Graph.from_record(H.graph_records()[a]) for a in ('resnet18', 'squeezenet1_1')], keep_grads=True)
+    prog = ghn.last_program
+    flat = prog.pred_flat.detach().clone().requires_grad_(True)
+    ref = 0.
+    for (o, n, shape) in prog.bp.out_meta['slices']:
+        ref = ref + torch.norm(flat[o:o + n].view(shape), p='fro')
+    ref = 3e-5 * ref
+    gref, = torch.autograd.grad(ref * 2.5, flat)
+    val = predicted_param_decay(ghn, 3e-5)
+    g, = torch.autograd.grad(val * 2.5, prog.pred_flat, retain_graph=True)
+    torch.cuda.synchronize()
+    assert abs(float(val) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert H.max_rel_err(g, gref) < 1e-5
+
+
+def test_nonfinite_loss_skips_the_update_on_the_device():
+    """A NaN loss must not touch parameters or Adam moments (fminf(1, NaN) = 1 poisoned everything); the
+    skip is counted on the device and surfaces at the next check / save."""
+    from ghn3_b200 import Trainer, GraphBatch
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    tr = Trainer(ghn, opt='adamw', opt_args={'lr': 1e-3, 'weight_decay': 1e-2, 'momentum': 0.9}, grad_clip=5,
+                 device=DEV, predparam_wd=3e-5, scheduler='cosine-warmup-steps2', epochs=10)
+    batch = lambda: GraphBatch([Graph.from_record(H.graph_records()['resnet18'])], dense=True)
+    good = lambda models: ghn.last_program.pred_flat.square().sum() * 1e-3
+    tr.update(None, None, graphs=batch(), models=[H.build_model('resnet18').to(DEV)], loss_fn=good)
+    tr.scheduler_step()
+    before = [p.detach().clone() for p in ghn.parameters()]
+    m_before = tr._optimizer.exp_avg.clone()
+    bad = lambda models: ghn.last_program.pred_flat.square().sum() * float('nan')
+    tr.update(None, None, graphs=batch(), models=[H.build_model('resnet18').to(DEV)], loss_fn=bad)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, p.detach()) for a, p in zip(before, ghn.parameters()))
+    assert torch.equal(m_before, tr._optimizer.exp_avg)
+    assert int(tr._optimizer.skipped.item()) == 1
+    with pytest.raises(RuntimeError):
+        tr.check_finite()
+    assert tr.skipped_updates == 1
+    assert 'loss_predwd' in tr.metrics
+
+
+def test_streaming_distinct_meta_batches_keeps_memory_bounded():
+    """real GHN training never repeats a meta-batch; plans / programs / backward workspaces of old batches
+    must be released (small LRU), not kept for 1024 batches."""
+    from ghn3_b200 import Trainer, GraphBatch
+    cfg = CONFIGS['ghn3tiny']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    tr = Trainer(ghn, opt='adamw', opt_args={'lr': 1e-4, 'weight_decay': 1e-2}, grad_clip=5, device=DEV)
+    loss_fn = lambda models: ghn.last_program.pred_flat.square().sum() * 1e-3
+    archs = ['resnet18', 'squeezenet1_1', 'mobilenet_v3_small', 'alexnet', 'shufflenet_v2_x0_5', 'mnasnet0_5']
+    peak = []
+    for it in range(36):
+        a = archs[it % len(archs)]
+        # fresh model AND fresh graph objects every step: nothing can be served from a cache
+        g = GraphBatch([Graph.from_record(H.graph_records()[a])], dense=True)
+        tr.update(None, None, graphs=g, models=[H.build_model(a).to(DEV)], loss_fn=loss_fn)
+        if it % 6 == 5:
+            torch.cuda.synchronize()
+            import gc
+            gc.collect()
+            peak.append(torch.cuda.memory_allocated())
+    assert len(ghn._plan_cache) <= 4
+    assert peak[-1] <= peak[1] * 1.10 + (8 << 20), peak        # flat after the first passes, not growing per step
