@@ -105,14 +105,12 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
     if ((rc = gemm_impl(&ff2, stream)) != GHN3_OK) return rc;
   }
   if (a->skip_final_ln) return GHN3_OK;
-  if (a->ln_w != nullptr) {
+  {
+    // ln_w == NULL (layernorm=False, ghn3/nn.py:262): the same kernel in its identity form -- conversion + row scatter
     ghn3_layernorm_args ln = {};
-    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = a->ln_w; ln.beta = a->ln_b;
+    ln.rows = M; ln.hid = C; ln.x = a->x; ln.gamma = a->ln_w; ln.beta = a->ln_w ? a->ln_b : nullptr;
     ln.out = a->dec_in; ln.out_dtype = a->dec_dtype; ln.dst_row = a->dst_row; ln.out_f32 = a->emb_f32;
     if ((rc = layernorm_impl(&ln, stream)) != GHN3_OK) return rc;
-  } else {
-    set_error("ghn3_graphormer_stack: layernorm=False is not supported by the CUDA path");
-    return GHN3_ERR_UNSUPPORTED;
   }
   return GHN3_OK;
 }

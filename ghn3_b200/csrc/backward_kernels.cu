@@ -155,6 +155,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
   for (int row = blockIdx.x * 8 + warp; row < a.rows; row += gridDim.x * 8) {
     const int64_t dyr = a.dy_row ? a.dy_row[row] : row;
     if (dyr < 0) continue;                     // no gradient reaches this row through this LayerNorm
+    if (a.gamma == nullptr) {                  // identity form (layernorm=False): dx (+)= dy
+      float* dxi = a.dx + (int64_t)row * C;
+      for (int c = lane; c < C; c += 32) {
+        const float dy = ld_f(a.dy, dyr * C + c, a.dy_dtype);
+        dxi[c] = a.accumulate ? dxi[c] + dy : dy;
+      }
+      continue;
+    }
     const float* x = a.x + (int64_t)row * C;
     float xv[kLnMaxT], gv[kLnMaxT];
     float sum = 0.f;
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const ghn3_layernorm
     }
   }
   __syncthreads();
+  if (a.gamma == nullptr) return;              // identity form: nothing to accumulate
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (sG[c] != 0.f) atomicAdd(a.dgamma + c, sG[c]);
     if (sB[c] != 0.f) atomicAdd(a.dbeta + c, sB[c]);
@@ -1065,7 +1074,8 @@ extern "C" int ghn3_layernorm_bwd(const ghn3_layernorm_bwd_args* a, ghn3_stream_
   cudaStream_t stream = (cudaStream_t)stream_;
   GHN3_REQUIRE(a != nullptr, "ghn3_layernorm_bwd: null args");
   GHN3_REQUIRE(a->hid > 0 && a->hid <= 1024, "ghn3_layernorm_bwd: hid must be <= 1024");
-  GHN3_REQUIRE(a->x && a->gamma && a->dy && a->dx && a->dgamma && a->dbeta, "ghn3_layernorm_bwd: null pointer");
+  GHN3_REQUIRE(a->dy && a->dx && (a->gamma == nullptr || (a->x && a->dgamma && a->dbeta)),
+               "ghn3_layernorm_bwd: null pointer");
   if (a->rows <= 0) return GHN3_OK;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(a->rows, 8), (int64_t)num_sms() * 3);
   const size_t smem = sizeof(float) * 2 * a->hid;

@@ -97,7 +97,6 @@ int graphormer_train_fwd_impl(const ghn3_graphormer_train_args* t, cudaStream_t 
   GHN3_TRY(make_ctx(f, stream, &c, "ghn3_graphormer_train_fwd"));
   GHN3_REQUIRE(t->xs && t->xm && t->h1 && t->qkv && t->ao && t->h2 && t->u && t->g,
                "ghn3_graphormer_train_fwd: every saved-activation buffer is required");
-  GHN3_REQUIRE(f.ln_w != nullptr, "ghn3_graphormer_train_fwd: layernorm=False is not supported");
   if (c.M <= 0) return GHN3_OK;
   const int C = c.C, M = c.M;
   const size_t xbytes = sizeof(float) * (size_t)M * C;
@@ -142,7 +141,8 @@ int graphormer_train_fwd_impl(const ghn3_graphormer_train_args* t, cudaStream_t 
     GHN3_TRY(gemm_impl(&g4, stream));
   }
   ghn3_layernorm_args ln = {};
-  ln.rows = M; ln.hid = C; ln.x = t->xs + (size_t)f.layers * M * C; ln.gamma = f.ln_w; ln.beta = f.ln_b;
+  ln.rows = M; ln.hid = C; ln.x = t->xs + (size_t)f.layers * M * C; ln.gamma = f.ln_w;
+  ln.beta = f.ln_w ? f.ln_b : nullptr;                     // ln_w == NULL: identity form (layernorm=False)
   ln.out = f.dec_in; ln.out_dtype = f.dec_dtype; ln.dst_row = f.dst_row; ln.out_f32 = f.emb_f32;
   GHN3_TRY(layernorm_impl(&ln, stream));
   return GHN3_OK;
@@ -154,7 +154,7 @@ int graphormer_bwd_impl(const ghn3_graphormer_bwd_args* b, cudaStream_t stream) 
   const ghn3_graphormer_args& f = t->fwd;
   Ctx c;
   GHN3_TRY(make_ctx(f, stream, &c, "ghn3_graphormer_bwd"));
-  GHN3_REQUIRE(b->layers_t_host && b->grads_host && b->d_ln_w && b->d_ln_b && b->d_dec_in && b->dx && b->dxa &&
+  GHN3_REQUIRE(b->layers_t_host && b->grads_host && (f.ln_w == nullptr || (b->d_ln_w && b->d_ln_b)) && b->d_dec_in && b->dx && b->dxa &&
                    b->dh && b->dhf && b->dqkv && b->dff && b->ta && b->tb && b->lse && b->delta,
                "ghn3_graphormer_bwd: null pointer");
   if (c.M <= 0) return GHN3_OK;

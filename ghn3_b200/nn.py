@@ -242,8 +242,6 @@ class GHN3(GHN):
         dev = self.embed.weight.device
         if dev.type != 'cuda':
             raise RuntimeError('ghn3_b200: the GHN must be on a CUDA device (got %s); there is no CPU path' % dev)
-        if not self.layernorm:
-            raise NotImplementedError('ghn3_b200: layernorm=False GHNs are not supported by the CUDA path')
         self.fix_embed_layers()
         if self._dev is not None and self._dev['compute_dtype'] == self.compute_dtype and self._dev['ptrs'] == \
                 [p.data_ptr() for p in self._param_list]:
@@ -324,7 +322,8 @@ class GHN3(GHN):
         w['wstack'] = stacks
         # the same table on the device (the fused kernel reads the fp32 vectors' addresses from it)
         w['layers_dev'] = torch.from_numpy(np.frombuffer(bytes(layers), dtype=np.uint8).copy()).to(dev)
-        w['ln_w'], w['ln_b'] = f(self.ln.weight), f(self.ln.bias)
+        # layernorm=False (nn.py:262): no final LayerNorm -- the kernel runs in its identity form (NULL gamma / beta)
+        w['ln_w'], w['ln_b'] = (f(self.ln.weight), f(self.ln.bias)) if self.layernorm else (None, None)
         dec = self.decoder
         # fc weight repacked position-major: [c*S*S + p][k] -> [p][c][k], so one decoder-grid position is one
         # contiguous [4C, C] block and a crop window is a set of row ranges (nn.py:738-745)
@@ -800,14 +799,19 @@ class _Program:
             p = module._parameters.get(attr)
             if p is None:
                 p = getattr(module, attr)
+            if not isinstance(p, torch.Tensor):
+                raise RuntimeError('ghn3_b200: target %s.%s holds a shape, not a tensor: parameter-free (light) modules '
+                                   'can only receive predictions with keep_grads=True (reference nn.py:530-546)'
+                                   % (type(module).__name__, attr))
             ptrs[i] = p.data_ptr()
         if self.last_ptrs is not None and np.array_equal(ptrs, self.last_ptrs):
             return
         for i, (module, attr, shape, view) in enumerate(self.bp.desc_targets):
             p = getattr(module, attr)
             if not isinstance(p, torch.Tensor):
-                raise RuntimeError('ghn3_b200: target %s.%s is not a tensor (light modules need keep_grads=True, '
-                                   'which the CUDA path does not support yet)' % (type(module).__name__, attr))
+                raise RuntimeError('ghn3_b200: target %s.%s holds a shape, not a tensor: parameter-free (light) modules '
+                                   'can only receive predictions with keep_grads=True (reference nn.py:530-546)'
+                                   % (type(module).__name__, attr))
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
                 # reference semantics (nn.py:548): param.data is replaced by a tensor on the GHN's device
                 p.data = torch.empty(tuple(p.shape), dtype=torch.float32, device=device)

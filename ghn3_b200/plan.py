@@ -130,7 +130,7 @@ class ShapeIndexer:
 # ----------------------------------------------------------------------------------------------------------------
 # per-model plan
 # ----------------------------------------------------------------------------------------------------------------
-KIND_CONV, KIND_CLS_W, KIND_1D, KIND_CLS_B = 0, 1, 2, 3
+KIND_CONV, KIND_CLS_W, KIND_1D, KIND_CLS_B, KIND_3D = 0, 1, 2, 3, 4
 
 
 class NodeTask:
@@ -178,8 +178,13 @@ class ModelPlan:
                 elif len(key) == 2:
                     t.kind = KIND_CLS_B if key[1] < 0 else KIND_1D
                 elif len(key) == 3:
-                    raise NotImplementedError('3-D shape group %s (decoder_1d path of nn.py:287-289) is not '
-                                              'supported by the CUDA path' % (key,))
+                    # 3-D tensors that are not positional encodings (nn.py:287-289,672: "e.g. layer_scale"): the
+                    # 2*ms values of decoder_1d, first dimension cropped, last dimension tiled. The reference's
+                    # _tile_params only yields the target shape for (o <= 2 ms, 1, k) (its repeat() calls are 4-D).
+                    if tsz[1] != 1 or tsz[0] > 2 * max(ms[0], ms[1]):
+                        raise NotImplementedError('3-D target of shape %s: the reference (nn.py:438-488) only handles '
+                                                  '(o <= 2*max_shape, 1, k)' % (tuple(tsz),))
+                    t.kind = KIND_3D
                 else:
                     t.kind, t.o_need, t.i_need = KIND_CONV, min(key[0], ms[0]), min(key[1], ms[1])
                     self._window(t, key[2], key[3], S)
@@ -493,6 +498,11 @@ class BatchPlan:
                 add(mod, param_attr(mod, False), tsz, SRC_CLSB, ((r - n_plain) * 2 + 1) * ncls, so=ncls, ca=1, mode=2)
                 continue
             row_off = r * 2 * max_ch
+            if t.kind == KIND_3D:
+                # element (a, 0, c) = d1[a] * sqrt(1 / k): rows a, columns c (t1 = k), source column stride 0
+                add(mod, param_attr(mod, is_w), tsz, SRC_D1, row_off, t1=int(tsz[1] * tsz[2]), so=2 * max_ch, si=1, ca=1,
+                    scale=scale_for(tsz), mode=0)
+                continue
             if is_w:
                 add(mod, param_attr(mod, True), tsz, SRC_D1, row_off, so=max_ch, ca=1, mode=1)
                 if getattr(mod, 'bias', None) is not None:
@@ -505,7 +515,9 @@ class BatchPlan:
         self.desc_src_buf = np.array([s_[0] for s_ in srcs], dtype=np.int64)
         self.desc_src_off = np.array([s_[1] for s_ in srcs], dtype=np.uint64)
         # rows 1.. of a ViT pos_embedding start one row (D floats) after the parameter's base address
-        self.desc_dst_shift = np.array([getattr(tg[0], tg[1]).shape[-1] * 4 if tg[3] == 'body' else 0
+        def last_dim(p):
+            return (p[-1] if isinstance(p, (list, tuple)) else p.shape[-1])
+        self.desc_dst_shift = np.array([last_dim(getattr(tg[0], tg[1])) * 4 if tg[3] == 'body' else 0
                                         for tg in targets], dtype=np.uint64)
         chunks = (self.desc_static['numel'] + SCATTER_CHUNK - 1) // SCATTER_CHUNK
         self.desc_static['chunk0'] = np.concatenate([[0], np.cumsum(chunks)[:-1]]) if len(chunks) else []

@@ -339,7 +339,8 @@ class _Backward:
         self.wt = wt
         self.d_lut = None                      # allocated when the pack (cutoff) is known
         self.gb = L.GraphormerBwdArgs(saved=ct.pointer(prog.ta), layers_t_host=wt['layers'], grads_host=self.lgr,
-                                      d_ln_w=G(ghn.ln.weight).data_ptr(), d_ln_b=G(ghn.ln.bias).data_ptr(),
+                                      d_ln_w=G(ghn.ln.weight).data_ptr() if ghn.layernorm else None,
+                                      d_ln_b=G(ghn.ln.bias).data_ptr() if ghn.layernorm else None,
                                       d_dec_in=L.ptr(self.ddec), d_dec_dtype=F32, d_lut=None, dx=L.ptr(self.dx),
                                       m_pad=mp, **{k: L.ptr(v) for k, v in ws.items()})
         add('graphormer_bwd', self.gb)

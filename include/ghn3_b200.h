@@ -142,8 +142,8 @@ int ghn3_edge_lut(const ghn3_edge_lut_args* args, ghn3_stream_t stream);
 typedef struct {
   int32_t rows, hid;
   const float* x;
-  const float* gamma;
-  const float* beta;
+  const float* gamma;        /* NULL (with beta NULL): identity -- no normalisation, only the conversion / row scatter */
+  const float* beta;         /*   (GHNs built with layernorm=False, ghn3/nn.py:262) */
   void* out;                 /* [*, C] in out_dtype (GHN3_BF16 / GHN3_TF32 / GHN3_F32) */
   int32_t out_dtype;
   const int32_t* dst_row;    /* optional [rows] */
@@ -464,7 +464,7 @@ int ghn3_colsum(const ghn3_colsum_args* args, ghn3_stream_t stream);
 typedef struct {
   int32_t rows, hid;
   const float* x;            /* forward input [rows][C] */
-  const float* gamma;
+  const float* gamma;        /* NULL: adjoint of the identity form (dx (+)= dy through dy_row; dgamma / dbeta unused) */
   const void* dy; int32_t dy_dtype;
   const int32_t* dy_row;
   float* dx;                 /* [rows][C] fp32 */

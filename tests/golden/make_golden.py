@@ -14,7 +14,7 @@ only the committed outputs:
 
   graphs_cellnets.json.gz  the same for the first 8 networks of ghn3_b200.deepnets.NetGenerator(seed=0)
 
-Usage:  python tests/golden/make_golden.py graphs | cellnets | preds | all
+Usage:  python tests/golden/make_golden.py graphs | cellnets | msa | preds | all
 """
 import gzip
 import inspect
@@ -121,6 +121,29 @@ def make_cellnet_graphs(n=8, seed=0):
     print('wrote %d cell-network graphs' % len(out))
 
 
+def make_msa_graphs(n=3, seed=5):
+    """graphs_cellnets_msa.json.gz: the reference's tracer on the first `n` networks of
+    NetGenerator(seed, with_msa=True) that contain the 'msa' primitive (ghn3/ops.py:302)."""
+    from ghn3_b200.deepnets import NetGenerator
+    gen = NetGenerator(seed=seed, with_msa=True, max_params=8e6)
+    out, picked, i = {}, [], -1
+    while len(out) < n:
+        net = gen.sample_net()
+        i += 1
+        g = net.net_args['genotype']
+        if not any(e[0] == 'msa' for e in g['normal'] + g['reduce']):
+            continue
+        net.expected_input_sz = 64
+        rec = graph_record('cellnet_msa%d' % len(out), model=net)
+        out['cellnet_msa%d' % len(out)] = rec
+        picked.append(i)
+        print('%3d msa cellnet N=%4d edges=%4d nnz=%6d max=%2d trace=%.2fs' % (
+            i, rec['n'], len(rec['edges']), rec['spd_nnz'], rec['spd_max'], rec['trace_sec']), flush=True)
+    with gzip.open(os.path.join(HERE, 'graphs_cellnets_msa.json.gz'), 'wt') as f:
+        json.dump({'seed': seed, 'stream_index': picked, 'graphs': out}, f, separators=(',', ':'))
+    print('wrote %d msa cell-network graphs' % len(out))
+
+
 def fingerprint(t):
     t = t.detach().double().reshape(-1)
     n = t.numel()
@@ -171,6 +194,8 @@ if __name__ == '__main__':
         make_graphs()
     if what in ('cellnets', 'all'):
         make_cellnet_graphs()
+    if what in ('msa', 'all'):
+        make_msa_graphs()
     if what in ('preds', 'all'):
         make_preds()
     if what.startswith('pred:'):                      # one case, e.g. pred:ghn3tiny:cellnet7

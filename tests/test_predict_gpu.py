@@ -330,3 +330,65 @@ def test_traced_graph_is_cached_per_architecture():
         assert net.__dict__['_ghn3_b200_graph'][1] is not g1
     torch.cuda.synchronize()
     assert net[5].weight.shape == (12, 8) and torch.isfinite(net[5].weight).all()
+
+
+def test_layernorm_false_ghn():
+    """GHN3(layernorm=False) (reference nn.py:262): no final LayerNorm -- the kernel runs in its identity form."""
+    cfg = dict(CONFIGS['ghn3tiny'], layernorm=False)
+    sd = procedural_state_dict(cfg, 0)
+    assert 'ln.weight' not in sd
+    rec = H.graph_records()['resnet18']
+    for dtype in ('tf32', 'bf16'):
+        ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+        ghn.load_state_dict(sd)
+        ghn = ghn.to(DEV).eval()
+        model = H.build_model('resnet18').to(DEV)
+        with torch.no_grad():
+            _, emb = ghn(model, Graph.from_record(rec), return_embeddings=True)
+        torch.cuda.synchronize()
+        ref = H.build_model('resnet18')
+        _, ref_emb, _ = O.predict(sd, cfg, ref, O.graph_from_record(rec))
+        assert H.max_rel_err(emb, ref_emb) < TOL[dtype]
+        for (n, p), (_, r) in zip(model.named_parameters(), ref.named_parameters()):
+            assert H.max_rel_err(p, r) < TOL[dtype], (dtype, n)
+
+
+class _Scale3D(torch.nn.Module):
+    """A module whose weight is 3-D and not a positional encoding: (o, 1, k) -- the decoder_1d branch of nn.py:287-289."""
+
+    def __init__(self, o, k):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.zeros(o, 1, k))
+
+
+class _Net3D(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.scale = _Scale3D(24, 7)
+        self.wide = _Scale3D(60, 3)           # o > ms: both halves of the decoder_1d output are used
+        self.fc = torch.nn.Linear(24, 1000)
+
+
+def test_three_dimensional_shape_group():
+    """3-D shape groups (reference nn.py:287-289,672, 'e.g. layer_scale'): predicted by decoder_1d, first dimension
+    cropped, last dimension tiled, fan-in scale; against the oracle on a hand-made graph."""
+    cfg = CONFIGS['ghn3tiny']
+    sd = procedural_state_dict(cfg, 0)
+    rec = {'n': 5, 'ops': [9, 4, 4, 4, 10], 'edges': [[0, 1], [1, 2], [2, 3], [3, 4]],
+           'node_info': [[[1, 'scale.weight', 'conv', [24, 1, 7], False, False],
+                          [2, 'wide.weight', 'conv', [60, 1, 3], False, False],
+                          [3, 'fc.weight', 'conv', [1000, 24], True, False],
+                          [4, 'fc.bias', 'bias', [1000], False, True]]]}
+    for dtype in ('tf32', 'bf16'):
+        ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+        ghn.load_state_dict(sd)
+        ghn = ghn.to(DEV).eval()
+        model = _Net3D().to(DEV)
+        with torch.no_grad():
+            ghn(model, Graph.from_record(rec))
+        torch.cuda.synchronize()
+        ref = _Net3D()
+        O.predict(sd, cfg, ref, O.graph_from_record(rec))
+        for (n, p), (_, r) in zip(model.named_parameters(), ref.named_parameters()):
+            assert float(r.abs().max()) > 0, n
+            assert H.max_rel_err(p, r) < TOL[dtype], (dtype, n, H.max_rel_err(p, r))

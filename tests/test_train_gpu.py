@@ -443,3 +443,67 @@ def test_streaming_distinct_meta_batches_keeps_memory_bounded():
             peak.append(torch.cuda.memory_allocated())
     assert len(ghn._plan_cache) <= 4
     assert peak[-1] <= peak[1] * 1.10 + (8 << 20), peak        # flat after the first passes, not growing per step
+
+
+def test_light_networks_with_msa_keep_grads():
+    """Parameter-free target networks (CellNetLight = the role of the reference's NetworkLight, ops.py:93-101,
+    light_ops.py:236-259) incl. the 'msa' primitive: with keep_grads=True the predicted tensors replace the shape
+    placeholders, equal the ones predicted for the ordinary twin, and the image loss back-propagates into the GHN."""
+    from ghn3_b200.deepnets import CellNetLight, NetGenerator
+    cfg = CONFIGS['ghn3tm8']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(procedural_state_dict(cfg, 0))
+    ghn = ghn.to(DEV).train()
+    gen = NetGenerator(seed=5, with_msa=True, max_params=8e6)
+    net = gen.sample_net()                                   # stream index 0 contains 'msa' (tests/golden fixture)
+    assert any(e[0] == 'msa' for e in net.net_args['genotype']['normal'] + net.net_args['genotype']['reduce'])
+    net.expected_input_sz = 64
+    graph = Graph(net)
+    light = CellNetLight(**net.net_args)
+    assert list(light.parameters()) == []
+    with pytest.raises(RuntimeError):                        # reference nn.py:546: light targets need keep_grads
+        ghn(light, graph, keep_grads=False)
+    full = ghn(net.to(DEV), graph, keep_grads=True)
+    want = {n: p.detach().clone() for n, p in full.named_parameters()}
+    light = ghn(light, graph, keep_grads=True)
+    got = dict(light.named_parameters())
+    assert set(got) == set(want) and len(got) > 50
+    for n, p in got.items():
+        assert p.grad_fn is not None or p.requires_grad, n
+        assert H.max_rel_err(p, want[n]) < 1e-5, n
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    y = light(x)
+    assert y.shape == (4, 1000) and torch.isfinite(y).all()
+    torch.nn.functional.cross_entropy(y, torch.randint(0, 1000, (4,), device=DEV)).backward()
+    torch.cuda.synchronize()
+    gn = {k: float(p.grad.norm()) for k, p in ghn.named_parameters() if p.grad is not None}
+    assert len(gn) == len(list(ghn.parameters())) and all(v == v for v in gn.values())
+    assert gn['decoder.conv.2.weight'] > 0 and gn['gnn.0.attn.to_qkv.weight'] > 0
+    # a Trainer step over light networks (the reference's training configuration)
+    from ghn3_b200 import GraphBatch, Trainer
+    tr = Trainer(ghn, opt='adamw', opt_args={'lr': 1e-4, 'weight_decay': 1e-2}, grad_clip=5, device=DEV,
+                 predparam_wd=3e-5)
+    gl = NetGenerator(seed=5, with_msa=True, max_params=8e6, light=True).sample(2)
+    gb = GraphBatch([g for _, g in gl], dense=True)
+    m = tr.update(torch.randn(4, 3, 64, 64), torch.randint(0, 1000, (4,)), graphs=gb, models=[n_ for n_, _ in gl])
+    assert m['loss'].avg == m['loss'].avg and tr.check_finite() == 0
+
+
+def test_layernorm_false_gradients():
+    cfg = dict(CONFIGS['ghn3tiny'], layernorm=False)
+    sd = procedural_state_dict(cfg, 0)
+    rec = H.graph_records()['resnet18']
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='tf32')
+    ghn.load_state_dict(sd)
+    ghn = ghn.to(DEV).train()
+    model = ghn(H.build_model('resnet18').to(DEV), Graph.from_record(rec), keep_grads=True)
+    sum(p.sum() for p in model.parameters()).backward()
+    torch.cuda.synchronize()
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.predict_keep_grads(sd_g, cfg, H.build_model('resnet18'), O.graph_from_record(rec))
+    sum(t.sum() for _, _, t in out).backward()
+    for k, p in ghn.named_parameters():
+        r = sd_g[k].grad
+        if k.endswith('proj_e.2.bias') or r is None or float(r.abs().max()) == 0.0:
+            continue
+        assert float((p.grad.cpu() - r).norm() / r.norm()) < 3e-3, k
