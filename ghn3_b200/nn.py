@@ -344,7 +344,34 @@ class GHN3(GHN):
         w['d1_w1'], w['d1_b1'] = cv(self.decoder_1d.fc[2].weight), f(self.decoder_1d.fc[2].bias)
         w['bc_w'], w['bc_b'] = f(self.bias_class[1].weight), f(self.bias_class[1].bias)
         self._dev = w
+        self._compute_cache_io(w)
         return w
+
+    _CACHED = ('fc_w', 'c0_w', 'c2_w', 'cls_w', 'd1_w0', 'd1_w1')
+
+    def _compute_cache_io(self, w):
+        """Reads (if valid) or writes the compute-dtype weight copies beside the checkpoint (from_pretrained(...,
+        cache_compute_copy=True)). Validity = same checkpoint size / mtime, same dtype, same tensor shapes."""
+        path = self.__dict__.get('_compute_cache_path')
+        if path is None or w['x3']:
+            return
+        import os
+        tensors = {k: w[k] for k in self._CACHED}
+        if w['wstack'] is not None:
+            tensors.update({'stack.' + k: v for k, v in w['wstack'].items()})
+        key = list(self._compute_cache_key) + [self.compute_dtype] + [list(t.shape) for t in tensors.values()]
+        if os.path.exists(path):
+            try:
+                blob = torch.load(path, map_location='cpu', weights_only=False)
+                if blob.get('key') == key:
+                    for k, t in tensors.items():
+                        t.copy_(blob['tensors'][k])
+                    self.__dict__['_compute_cache_hit'] = True
+                    return
+            except Exception:
+                pass
+        torch.save({'key': key, 'tensors': {k: t.cpu() for k, t in tensors.items()}}, path)
+        self.__dict__['_compute_cache_hit'] = False
 
     _REFRESH_OPC = {'elementwise': 10, 'transpose': 9}
 
@@ -925,6 +952,36 @@ class _Program:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Checkpoints released without a 'config' entry: the GHN hyper-parameters are read off the tensors. One rule per
+# hyper-parameter: (name test, value from the tensor); the checkpoint schema is the reference's (nn.py:59-99).
+_CONFIG_RULES = (
+    ('num_classes', lambda n: 'class_layer_predictor' in n, lambda p: p.shape[0]),
+    ('layernorm', lambda n: n.endswith('ln.weight'), lambda p: True),
+    ('hid', lambda n: n.endswith('embed.weight'), lambda p: p.shape[-1]),
+    ('max_ch', lambda n: n.endswith('decoder.conv.2.weight'), lambda p: int(p.shape[0] ** 0.5)),
+    ('spatial', lambda n: n.endswith('shape_enc.embed_spatial.weight'), lambda p: 11 if p.shape[0] == 9 else 16),
+    ('pretrained', lambda n: 'centrality_embed_in' in n and 'gnn.' not in n, lambda p: True),
+)
+
+
+def infer_config(state_dict, overrides=None):
+    """GHN3 constructor arguments from a bare state_dict. `overrides` (popped): defaults for what no tensor settles."""
+    kw = overrides if overrides is not None else {}
+    found = {'num_classes': kw.pop('num_classes', 10), 'hid': kw.pop('hid', 32), 'layernorm': kw.pop('layernorm', False),
+             'pretrained': kw.pop('pretrained', False), 'max_ch': kw.pop('max_shape', 64), 'spatial': None}
+    layers = kw.pop('layers', 0)
+    for name, p in state_dict.items():
+        for key, test, value in _CONFIG_RULES:
+            if test(name):
+                found[key] = value(p)
+        layers += int(name.endswith('ln1.weight') and 'gnn.' in name)      # one ln1 per Graphormer layer
+    s = found['spatial'] or (16 if found['num_classes'] >= 1000 else 11)   # decoder grid: 16 for ImageNet GHNs
+    ms = found['max_ch']
+    return {'hid': found['hid'], 'max_shape': ms if isinstance(ms, tuple) else (ms, ms, s, s),
+            'num_classes': found['num_classes'], 'heads': 16 if found['hid'] > 64 else 8, 'layers': layers,
+            'weight_norm': True, 've': True, 'layernorm': found['layernorm'], 'pretrained': found['pretrained']}
+
+
 def from_pretrained(ghn3_name='ghn3xlm16.pt', **kwargs):
     """
     Loads a GHN-3 checkpoint (reference nn.py:31-125): a local file holding {'state_dict', 'config'?} or a bare
@@ -943,7 +1000,11 @@ def from_pretrained(ghn3_name='ghn3xlm16.pt', **kwargs):
             raise FileNotFoundError('cannot load GHN checkpoint %s: not a local file and the hub download failed (%s)'
                                     % (ghn3_name, e))
     else:
-        state_dict = torch.load(ghn3_name, map_location='cpu', weights_only=False)
+        try:
+            state_dict = torch.load(ghn3_name, map_location='cpu', weights_only=False)
+        except Exception:
+            import joblib                    # the released checkpoints are joblib pickles of a state_dict (nn.py:49)
+            state_dict = joblib.load(ghn3_name)
         if 'config' in state_dict:
             ghn_config = state_dict['config']
         if 'state_dict' in state_dict:
@@ -952,40 +1013,19 @@ def from_pretrained(ghn3_name='ghn3xlm16.pt', **kwargs):
         raise NotImplementedError('GHN-2 checkpoints are out of scope of ghn3_b200')
     compute_dtype = kwargs.pop('compute_dtype', 'bf16')
     if ghn_config is None:
-        num_classes = kwargs.pop('num_classes', 10)
-        layers = kwargs.pop('layers', 0)
-        hid = kwargs.pop('hid', 32)
-        layernorm = kwargs.pop('layernorm', False)
-        pretrained = kwargs.pop('pretrained', False)
-        max_shape = kwargs.pop('max_shape', 64)
-        for name, p in state_dict.items():
-            if name.find('class_layer_predictor') >= 0:
-                num_classes = len(p)
-                break
-        s = 16 if num_classes >= 1000 else 11
-        for name, p in state_dict.items():
-            if name.endswith('ln.weight'):
-                layernorm = True
-            elif name.endswith('embed.weight'):
-                hid = p.shape[-1]
-            elif name.endswith('decoder.conv.2.weight'):
-                max_shape = int(len(p) ** 0.5)
-            elif name.endswith('shape_enc.embed_spatial.weight'):
-                s = 11 if len(p) == 9 else 16
-            elif name.endswith('ln1.weight') and name.find('gnn.') >= 0:
-                layers += 1
-            elif name.find('centrality_embed_in') >= 0 > name.find('gnn.'):
-                pretrained = True
-        ghn_config = {'hid': hid,
-                      'max_shape': max_shape if isinstance(max_shape, tuple) else (max_shape, max_shape, s, s),
-                      'num_classes': num_classes, 'heads': 16 if hid > 64 else 8, 'layers': layers,
-                      'weight_norm': True, 've': True, 'layernorm': layernorm, 'pretrained': pretrained}
+        ghn_config = infer_config(state_dict, kwargs)
     else:
         ghn_config = dict(ghn_config)
         ghn_config.pop('is_ghn2', None)
+    cache_compute_copy = kwargs.pop('cache_compute_copy', False)
     ghn = GHN3(**ghn_config, compute_dtype=compute_dtype, **kwargs)
     ghn.load_state_dict(state_dict)
     ghn.fix_embed_layers()
+    if cache_compute_copy and os.path.exists(ghn3_name):
+        # the compute-dtype copy of the GEMM weights (bf16: 1.3 GB instead of 2.6 GB at ghn3xlm16, decoder
+        # fc already repacked position-major) is written beside the checkpoint on first use and read back afterwards
+        ghn._compute_cache_path = '%s.%s.cache' % (ghn3_name, compute_dtype)
+        ghn._compute_cache_key = (os.path.getsize(ghn3_name), int(os.path.getmtime(ghn3_name)))
     return ghn
 
 

@@ -127,6 +127,22 @@ def test_state_dict_contract_and_from_pretrained(tmp_path):
     assert 'gnn.0.centrality_embed_in.weight' in g4.state_dict()
     with pytest.raises(NotImplementedError):
         GHN3(**cfg, is_ghn2=True)
+    # the released checkpoints are bare state_dicts pickled with joblib (reference nn.py:49)
+    import joblib
+    path3 = tmp_path / 'ghn3_joblib.pt'
+    joblib.dump(sd, path3)
+    g5 = from_pretrained(str(path3))
+    assert (g5.hid, g5.layers, g5.layernorm) == (32, 2, True)
+    assert all(torch.equal(a, b) for a, b in zip(g5.state_dict().values(), ghn.state_dict().values()))
+    # config inference over every shipped configuration, including layernorm=False / 11x11 decoder grids
+    from ghn3_b200.nn import infer_config
+    for name, c in CONFIGS.items():
+        got = infer_config(procedural_state_dict(c, 0))
+        assert (got['hid'], got['layers'], got['max_shape'], got['num_classes'], got['layernorm']) == \
+            (c['hid'], c['layers'], tuple(c['max_shape']), c['num_classes'], True), name
+    c10 = dict(hid=32, layers=1, heads=8, max_shape=(32, 32, 11, 11), num_classes=10, layernorm=False)
+    got = infer_config(procedural_state_dict(c10, 0))
+    assert (got['max_shape'], got['num_classes'], got['layernorm'], got['layers']) == ((32, 32, 11, 11), 10, False, 1)
 
 
 def test_no_cpu_fallback():

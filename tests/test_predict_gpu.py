@@ -392,3 +392,35 @@ def test_three_dimensional_shape_group():
         for (n, p), (_, r) in zip(model.named_parameters(), ref.named_parameters()):
             assert float(r.abs().max()) > 0, n
             assert H.max_rel_err(p, r) < TOL[dtype], (dtype, n, H.max_rel_err(p, r))
+
+
+def test_compute_copy_cache_beside_checkpoint(tmp_path):
+    """from_pretrained(..., cache_compute_copy=True): the bf16 copies of the GEMM weights (decoder fc
+    repacked position-major) are written beside the checkpoint once and read back by later loads."""
+    import os
+    from ghn3_b200 import from_pretrained
+    cfg = CONFIGS['ghn3tm8']
+    sd = procedural_state_dict(cfg, 0)
+    path = str(tmp_path / 'ghn.pt')
+    torch.save({'state_dict': sd, 'config': dict(cfg, weight_norm=True, ve=True)}, path)
+    rec = H.graph_records()['resnet50']
+    outs = []
+    for hit in (False, True):
+        ghn = from_pretrained(path, compute_dtype='bf16', cache_compute_copy=True).to(DEV).eval()
+        model = H.build_model('resnet50').to(DEV)
+        with torch.no_grad():
+            ghn(model, Graph.from_record(rec))
+        torch.cuda.synchronize()
+        assert os.path.exists(path + '.bf16.cache')
+        assert ghn._compute_cache_hit is hit
+        outs.append([p.detach().clone() for p in model.parameters()])
+    for a, b in zip(*outs):
+        assert H.max_rel_err(a, b) < 1e-4
+    # a changed checkpoint invalidates the cache
+    sd2 = {k: v * 1.5 for k, v in sd.items()}
+    torch.save({'state_dict': sd2, 'config': dict(cfg, weight_norm=True, ve=True), 'pad': 1}, path)
+    os.utime(path, (1, 1))
+    ghn = from_pretrained(path, compute_dtype='bf16', cache_compute_copy=True).to(DEV).eval()
+    with torch.no_grad():
+        ghn(H.build_model('resnet50').to(DEV), Graph.from_record(rec))
+    assert ghn._compute_cache_hit is False
