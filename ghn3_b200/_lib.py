@@ -256,7 +256,8 @@ assert C.sizeof(ScatterDesc) == 136 and C.sizeof(GemmProblem) == 32
 SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd_bfs', 'ghn3_graph_derive',
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
            'ghn3_graphormer_stack', 'ghn3_graphormer_fused', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence',
-           'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace']
+           'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace',
+           'ghn3_set_programmatic_launch']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
                  'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin', 'ghn3_segnorm']
@@ -304,6 +305,17 @@ def call(name, args, stream):
     """Invokes int ghn3_<name>(const Args*, stream) and raises on a non-zero status."""
     lib = load()
     check(getattr(lib, 'ghn3_' + name)(C.byref(args), C.c_void_p(stream)), 'ghn3_' + name)
+
+
+_pdl_state = [None]
+
+
+def set_programmatic_launch(enabled):
+    """Process-wide programmatic-dependent-launch switch (see include/ghn3_b200.h); no-op if unchanged."""
+    enabled = bool(enabled)
+    if _pdl_state[0] is not enabled:
+        load().ghn3_set_programmatic_launch(C.c_int(int(enabled)))
+        _pdl_state[0] = enabled
 
 
 def launch_count():

@@ -19,6 +19,13 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Programmatic dependent launch is a latency optimisation: a kernel's successor is made resident early and waits in
+// griddepcontrol.wait, so every kernel chain holds the SM resources of TWO kernels. For ONE chain that hides launch and
+// prologue latency (Graphormer stack 1.08 vs 1.49 ms); when several chains run side by side (GHN3.pipeline_depth >= 3)
+// the parked CTAs starve the other chains and throughput drops (1.31 vs 1.11 ms per step). Hence a process-wide switch.
+static std::atomic<int> g_pdl{getenv("GHN3_NO_PDL") == nullptr ? 1 : 0};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -118,7 +125,11 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
 }  // namespace ghn3
 
 extern "C" const char* ghn3_last_error(void) { return ghn3::g_error; }
-extern "C" int ghn3_abi_version(void) { return 1; }
+extern "C" int ghn3_abi_version(void) { return 2; }
+extern "C" int ghn3_set_programmatic_launch(int enabled) {
+  const int old = ghn3::g_pdl.exchange(enabled ? 1 : 0);
+  return old;
+}
 extern "C" int64_t ghn3_launch_count(void) { return ghn3::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream) {

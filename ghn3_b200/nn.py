@@ -539,6 +539,10 @@ class GHN3(GHN):
         # high-priority stream -- take successive calls on the same batch plan in turn, so the latency-bound Graphormer
         # chains of calls k and k+1 run side by side; decoders + scatter of every call stay ordered on ONE side stream
         depth = max(1, int(getattr(self, 'pipeline_depth', 1))) if overlap else 1
+        # programmatic dependent launch: lowest latency for one chain, lower throughput for >= 3 chains side by side
+        # (each chain parks its next kernel's CTAs on the SMs); `programmatic_launch` = True / False overrides
+        pdl = getattr(self, 'programmatic_launch', None)
+        L.set_programmatic_launch(depth < 3 if pdl is None else pdl)
         progs = bp.__dict__.setdefault('programs', [])
         want = bool(return_embeddings)
         if any(p_.w is not w or p_.device != device or p_.want_emb != want for p_ in progs):

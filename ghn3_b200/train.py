@@ -551,6 +551,8 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
     way the reference does (ghn3/nn.py:526-545)."""
     from .nn import _Program
     device = ghn.embed.weight.device
+    pdl = getattr(ghn, 'programmatic_launch', None)       # one chain at a time here: programmatic launch pays
+    L.set_programmatic_launch(True if pdl is None else pdl)
     prog = getattr(bp, 'train_program', None)
     if prog is None or prog.w is not w or prog.device != device or prog.want_emb != bool(return_embeddings):
         prog = _Program(ghn, w, bp, device, bool(return_embeddings), train=True)

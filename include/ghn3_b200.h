@@ -44,6 +44,11 @@ enum ghn3_act { GHN3_ACT_NONE = 0, GHN3_ACT_RELU = 1, GHN3_ACT_GELU = 2 };
 
 const char* ghn3_last_error(void);
 int ghn3_abi_version(void);
+/* Process-wide switch of programmatic dependent launch (default on; GHN3_NO_PDL=1 starts with it off): with it every
+ * kernel of a chain is made resident while its predecessor still runs -- lowest latency for ONE chain, but the parked
+ * CTAs hold SM resources, which costs throughput when several independent chains run side by side. Returns the
+ * previous setting. */
+int ghn3_set_programmatic_launch(int enabled);
 /* Number of kernels this library has launched since load (all streams); backs bench.py's "gpu_launches". */
 int64_t ghn3_launch_count(void);
 
