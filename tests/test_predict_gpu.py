@@ -49,7 +49,7 @@ def run_case(cfg_name, archs, dtype, check_logits=True, fused=False):
         assert e < TOL[dtype], ('embeddings', arch, e)
         off += rec['n']
         ref_params = dict(ref_model.named_parameters())
-        w = 0.0
+        w = w_elem = 0.0
         for name, p in model.named_parameters():
             r = ref_params[name]
             assert p.shape == r.shape
@@ -60,7 +60,12 @@ def run_case(cfg_name, archs, dtype, check_logits=True, fused=False):
             err = H.max_rel_err(p, r)
             w = max(w, err)
             assert err < TOL[dtype], (arch, name, err)
+            # the element-wise figure beside it (floored at 1 % of the tensor's scale): logged and loosely bounded
+            ew = H.elem_rel_err(p, r)
+            w_elem = max(w_elem, ew)
+            assert ew < 100 * TOL[dtype], (arch, name, 'element-wise', ew)
         worst[arch] = w
+        worst[arch + ' (element-wise, floor 1e-2)'] = w_elem
         if check_logits:
             torch.manual_seed(1)
             sz = 299 if arch == 'inception_v3' else 224
@@ -424,3 +429,11 @@ def test_compute_copy_cache_beside_checkpoint(tmp_path):
     with torch.no_grad():
         ghn(H.build_model('resnet50').to(DEV), Graph.from_record(rec))
     assert ghn._compute_cache_hit is False
+
+
+@pytest.mark.parametrize('dtype', ['tf32', 'bf16'])
+@pytest.mark.parametrize('arch', ['efficientnet_b7', 'regnet_y_128gf'])
+def test_xl_config4_models(arch, dtype):
+    """BASELINE.json config 4 at ghn3xlm16: EfficientNet-B7 (653 nodes) and RegNetY-128GF (2.58 GB of parameters written),
+    every predicted tensor against the oracle in both modes."""
+    run_case('ghn3xlm16', [arch], dtype, check_logits=False)

@@ -16,12 +16,13 @@ ORACLE_CHECKED = ['efficientnet_v2_l', 'regnet_y_400mf', 'densenet201', 'incepti
                   'mnasnet1_0', 'shufflenet_v2_x1_0', 'vgg16_bn', 'googlenet', 'wide_resnet50_2', 'vit_l_32']
 
 
-def test_all_torchvision_models_lm8_bf16():
+@pytest.mark.parametrize('dtype,tol,checked', [('bf16', 2e-2, ORACLE_CHECKED), ('tf32', 1e-3, ORACLE_CHECKED[:6])])
+def test_all_torchvision_models_lm8(dtype, tol, checked):
     """ghn3lm8-sized GHN (random-init) predicts all 80 architectures; a subset is compared tensor by tensor with the
-    oracle (<= 2e-2), every model must have all its matched parameters written with finite values."""
+    oracle (<= 2e-2 bf16, <= 1e-3 tf32), every model must have all its matched parameters written with finite values."""
     cfg = CONFIGS['ghn3lm8']
     sd = procedural_state_dict(cfg, 0)
-    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype='bf16')
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
     ghn.load_state_dict(sd)
     ghn = ghn.to(DEV).eval()
     recs = H.graph_records()
@@ -40,7 +41,7 @@ def test_all_torchvision_models_lm8_bf16():
                 failures.append((arch, n, 'non-finite'))
             if id(p) in predicted and torch.equal(p, before[n]):
                 failures.append((arch, n, 'not written'))
-        if arch in ORACLE_CHECKED:
+        if arch in checked:
             ref = H.build_model(arch)
             O.predict(sd, cfg, ref, O.graph_from_record(rec))
             refp = dict(ref.named_parameters())
@@ -49,10 +50,36 @@ def test_all_torchvision_models_lm8_bf16():
                 if n.endswith('pos_embedding'):
                     p, r = p[:, 1:], r[:, 1:]
                 err = H.max_rel_err(p, r)
-                if err > 2e-2:
+                if err > tol:
                     failures.append((arch, n, err))
         del model
     assert not failures, failures[:20]
+
+
+@pytest.mark.parametrize('cfg_name,n,dtype,tol', [('ghn3tm8', 1024, 'bf16', 2e-2), ('ghn3tm8', 3000, 'bf16', 2e-2),
+                                                  ('ghn3tm8', 3000, 'tf32', 1e-3), ('ghn3xlm16', 1024, 'bf16', 2e-2),
+                                                  ('ghn3xlm16', 1024, 'tf32', 1e-3)])
+def test_large_synthetic_graph_stack_runner(cfg_name, n, dtype, tol):
+    """Config 4 as SURVEY 8d specifies it: synthetic DAGs of >= 1024 nodes, also at ghn3xlm16 and in the accurate mode;
+    ghn3_b200.synthetic.StackRunner (node features + SPD + stack + final LayerNorm) vs the oracle."""
+    from ghn3_b200.synthetic import StackRunner, synthetic_dag
+    cfg = CONFIGS[cfg_name]
+    sd = procedural_state_dict(cfg, 0)
+    edges, op = synthetic_dag(n, seed=0)
+    ghn = GHN3(**cfg, weight_norm=True, ve=True, compute_dtype=dtype)
+    ghn.load_state_dict(sd)
+    ghn = ghn.to(DEV).eval()
+    sr = StackRunner(ghn, [n], [edges], [op], DEV)
+    emb = sr.run()
+    torch.cuda.synchronize()
+    adj = np.zeros((n, n), dtype=np.int64)
+    adj[edges[:, 0], edges[:, 1]] = 1
+    A = O.spd_matrix(adj, 50)
+    assert np.array_equal(sr.pack.spd_matrix(0).cpu().numpy(), A.astype(np.uint8))
+    tabs = sr.sidx.cpu().numpy().astype(np.int64)
+    x0 = O.node_features(sd, op, tabs)
+    ref = O.graphormer_stack(sd, cfg, x0, A)
+    assert H.max_rel_err(emb, ref) < tol, H.max_rel_err(emb, ref)
 
 
 @pytest.mark.parametrize('n', [1024, 3000])
