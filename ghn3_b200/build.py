@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libghn3_b200.so')
-SOURCES = ['api.cu', 'graph_kernels.cu', 'dense_kernels.cu', 'gemm_tcgen05.cu', 'graphormer_fused.cu', 'scatter.cu', 'backward_kernels.cu', 'attention_bwd_mma.cu', 'attention_split.cu', 'train.cu']
+SOURCES = ['api.cu', 'graph_kernels.cu', 'dense_kernels.cu', 'gemm_tcgen05.cu', 'graphormer_fused.cu', 'scatter.cu', 'backward_kernels.cu', 'attention_bwd_mma.cu', 'attention_split.cu', 'attention_tcgen05.cu', 'train.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC']
 
 

@@ -3,6 +3,7 @@
 //   ghn3_attention   reference ghn3/graphormer.py:121-140 (QK^T * d^-1/2 + edge bias, softmax, PV), flash-style:
 //                    no (B,H,N,N) logits and no (B,N,N,H) bias tensor are ever materialised
 //   ghn3_gemm_simt   classification heads (ghn3/nn.py:757-758, 294) whose operands are transposed views
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -528,6 +529,9 @@ static int launch_attention(const ghn3_attention_args* a, cudaStream_t stream) {
 }
 
 int attention_split_impl(const ghn3_attention_args* a, cudaStream_t stream);
+int attention_tc_impl(const ghn3_attention_args* a, cudaStream_t stream);
+
+static std::atomic<int> g_attn_tc_min{getenv("GHN3_ATTN_TC_MIN") ? atoi(getenv("GHN3_ATTN_TC_MIN")) : 2048};
 
 int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   GHN3_REQUIRE(a != nullptr, "ghn3_attention: null args");
@@ -536,6 +540,14 @@ int attention_impl(const ghn3_attention_args* a, cudaStream_t stream) {
   if (a->n_graphs <= 0 || a->max_nodes <= 0) return GHN3_OK;
   const int D = a->hid / a->heads;
   const bool bf = a->dtype == GHN3_BF16;
+  if (bf) {
+    // large graphs: the tcgen05 kernel (attention_tcgen05.cu); below the threshold the mma.sync kernel's shorter
+    // prologue and larger CTA count win (measured cross-over between 1024 and 2048 nodes). GHN3_ATTN_TC_MIN overrides the threshold (0 = always, a huge value = never).
+    if (a->max_nodes >= g_attn_tc_min.load(std::memory_order_relaxed)) {
+      const int rc = attention_tc_impl(a, stream);
+      if (rc != GHN3_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (!bf) {
     // fp32 storage: split-bf16 tensor-core kernel (attention_split.cu); the CUDA-core kernel below remains for the
     // head dims it does not cover and as a cross-check (GHN3_NO_SPLIT_ATTN=1)
@@ -703,6 +715,10 @@ using namespace ghn3;
 
 extern "C" int ghn3_layernorm(const ghn3_layernorm_args* a, ghn3_stream_t stream) {
   return layernorm_impl(a, (cudaStream_t)stream);
+}
+
+extern "C" int ghn3_set_attention_tc_min(int min_nodes) {
+  return g_attn_tc_min.exchange(min_nodes);
 }
 
 extern "C" int ghn3_attention(const ghn3_attention_args* a, ghn3_stream_t stream) {

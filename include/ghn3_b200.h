@@ -269,6 +269,10 @@ typedef struct {
 } ghn3_attention_args;
 
 int ghn3_attention(const ghn3_attention_args* args, ghn3_stream_t stream);
+/* bf16 batches whose largest graph has at least `min_nodes` nodes run on the tcgen05 kernel (S and P.V accumulated in
+ * TMEM, csrc/attention_tcgen05.cu), smaller ones on the mma.sync kernel. Default 2048 (GHN3_ATTN_TC_MIN); returns the
+ * previous threshold. */
+int ghn3_set_attention_tc_min(int min_nodes);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * The whole Graphormer stack on packed node features (ghn3/nn.py:258-263, graphormer.py:208-248): per layer

@@ -560,3 +560,43 @@ def test_gemm_fused_layernorm(dtype, x3, splits):
         assert _rel(xx, x_ref) < 2e-5
         assert _rel(ln_out, ln_ref) < (1e-2 if not x3 else 2e-5)
         assert int(counters.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('cfg_name,archs', [('ghn3xlm16', ['efficientnet_v2_l', 'resnet18']), ('ghn3lm8', ['swin_v2_t']),
+                                            ('ghn3tm8', ['resnet50', 'efficientnet_b0', 'alexnet']),
+                                            ('ghn3sm8', ['densenet201'])])
+def test_attention_tcgen05(cfg_name, archs):
+    """The tcgen05 attention kernel (S and P.V in TMEM; large graphs) against the fp32 reference and against the
+    mma.sync kernel, with the softmax statistics it keeps for the backward pass."""
+    cfg = CONFIGS[cfg_name]
+    C_, H_ = cfg['hid'], cfg['heads']
+    D = C_ // H_
+    recs, pack = _pack(archs)
+    torch.manual_seed(7)
+    N = pack.total_nodes
+    qkv = torch.randn(N, 3 * C_, device=DEV).bfloat16()
+    lut = torch.randn(H_, 51 * 51, device=DEV)
+    lib = L.load()
+    old = lib.ghn3_set_attention_tc_min(1 << 30)
+    try:
+        lse_a = torch.zeros(H_, N, device=DEV)
+        ref_kernel = ops.attention(qkv, pack, lut, C_, H_, dtype=ops.BF16, lse2=lse_a)
+        lib.ghn3_set_attention_tc_min(0)
+        lse_b = torch.zeros(H_, N, device=DEV)
+        out = ops.attention(qkv, pack, lut, C_, H_, dtype=ops.BF16, lse2=lse_b)
+        torch.cuda.synchronize()
+    finally:
+        lib.ghn3_set_attention_tc_min(old)
+    assert _rel(out, ref_kernel) < 1e-2
+    assert _rel(lse_b, lse_a) < 1e-3
+    qf = qkv.float().cpu()
+    off = 0
+    for g, rec in enumerate(recs):
+        n = rec['n']
+        A = pack.spd_matrix(g).cpu().long()
+        bias = lut.cpu()[:, (A * 51 + A.t()).reshape(-1)].view(H_, n, n)
+        q, k, v = qf[off:off + n].view(n, 3, H_, D).permute(1, 2, 0, 3)
+        attn = (q @ k.transpose(-2, -1)) * D ** -0.5 + bias
+        ref = (attn.softmax(-1) @ v).transpose(0, 1).reshape(n, C_)
+        assert _rel(out[off:off + n].float().cpu(), ref) < 1e-2, (cfg_name, g)
+        off += n
