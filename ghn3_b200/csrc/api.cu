@@ -125,7 +125,7 @@ int graphormer_impl(const ghn3_graphormer_args* a, cudaStream_t stream) {
 }  // namespace ghn3
 
 extern "C" const char* ghn3_last_error(void) { return ghn3::g_error; }
-extern "C" int ghn3_abi_version(void) { return 2; }
+extern "C" int ghn3_abi_version(void) { return GHN3_ABI_VERSION; }
 extern "C" int ghn3_set_programmatic_launch(int enabled) {
   const int old = ghn3::g_pdl.exchange(enabled ? 1 : 0);
   return old;

@@ -43,7 +43,8 @@ enum ghn3_dtype {
 enum ghn3_act { GHN3_ACT_NONE = 0, GHN3_ACT_RELU = 1, GHN3_ACT_GELU = 2 };
 
 const char* ghn3_last_error(void);
-int ghn3_abi_version(void);
+#define GHN3_ABI_VERSION 2   /* bumped when an argument struct changes layout */
+int ghn3_abi_version(void);  /* == GHN3_ABI_VERSION of the header the library was built from */
 /* Process-wide switch of programmatic dependent launch (default on; GHN3_NO_PDL=1 starts with it off): with it every
  * kernel of a chain is made resident while its predecessor still runs -- lowest latency for ONE chain, but the parked
  * CTAs hold SM resources, which costs throughput when several independent chains run side by side. Returns the
