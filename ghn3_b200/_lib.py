@@ -229,6 +229,10 @@ class MemsetArgs(C.Structure):
     _fields_ = [('ptr', vp), ('bytes', i64)]
 
 
+class MemcpyArgs(C.Structure):
+    _fields_ = [('dst', vp), ('src', vp), ('bytes', i64)]
+
+
 class GraphormerTrainArgs(C.Structure):
     _fields_ = [('fwd', GraphormerArgs), ('xs', vp), ('xm', vp), ('h1', vp), ('qkv', vp), ('ao', vp), ('h2', vp),
                 ('u', vp), ('g', vp), ('lse2', vp)]
@@ -257,7 +261,8 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
            'ghn3_graphormer_stack', 'ghn3_graphormer_fused', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence',
            'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace',
-           'ghn3_set_programmatic_launch', 'ghn3_set_attention_tc_min']
+           'ghn3_set_programmatic_launch', 'ghn3_set_attention_tc_min',
+           'ghn3_sequence_capture', 'ghn3_sequence_launch', 'ghn3_sequence_destroy']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
                  'ghn3_graphormer_bwd', 'ghn3_fc_bwd', 'ghn3_relu_transpose_bwd', 'ghn3_expand_cols', 'ghn3_adamw', 'ghn3_lut_bin', 'ghn3_segnorm']
@@ -289,6 +294,12 @@ def load(build_if_missing=True):
     lib.ghn3_graphormer_fused_sync_ints.argtypes = [C.c_int32]
     lib.ghn3_run_sequence.restype = C.c_int
     lib.ghn3_run_sequence.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ghn3_sequence_capture.restype = C.c_int
+    lib.ghn3_sequence_capture.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.ghn3_sequence_launch.restype = C.c_int
+    lib.ghn3_sequence_launch.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ghn3_sequence_destroy.restype = C.c_int
+    lib.ghn3_sequence_destroy.argtypes = [C.c_void_p]
     lib.ghn3_convert_f32.restype = C.c_int
     lib.ghn3_convert_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     _lib = lib

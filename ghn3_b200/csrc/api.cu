@@ -170,11 +170,94 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
         }
         break;
       }
+      case GHN3_OP_MEMCPY: {
+        const ghn3_memcpy_args* m = (const ghn3_memcpy_args*)ops[i].args;
+        rc = GHN3_OK;
+        if (m->bytes > 0 && cudaMemcpyAsync(m->dst, m->src, (size_t)m->bytes, cudaMemcpyDeviceToDevice,
+                                            (cudaStream_t)stream) != cudaSuccess) {
+          ghn3::set_error("ghn3_run_sequence: cudaMemcpyAsync failed at index %d", i);
+          rc = GHN3_ERR_CUDA;
+        }
+        break;
+      }
       default:
         ghn3::set_error("ghn3_run_sequence: unknown op %d at index %d", ops[i].op, i);
         return GHN3_ERR_BAD_ARG;
     }
     if (rc != GHN3_OK) return rc;
+  }
+  return GHN3_OK;
+}
+
+struct ghn3_sequence {
+  cudaGraphExec_t exec;
+  int64_t launches;
+};
+
+extern "C" int ghn3_sequence_capture(const ghn3_op* ops, int32_t n, int32_t high_priority, ghn3_sequence** out) {
+  if (out == nullptr || (ops == nullptr && n > 0)) {
+    ghn3::set_error("ghn3_sequence_capture: null argument");
+    return GHN3_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  // the caller's stream may be the legacy default stream, which cannot be captured: record on streams of our own
+  // (one per priority class; kernel nodes inherit the capturing stream's priority)
+  static cudaStream_t cap[2] = {nullptr, nullptr};
+  const int pr = high_priority ? 1 : 0;
+  if (cap[pr] == nullptr) {
+    int lo = 0, hi = 0;
+    GHN3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GHN3_CUDA(cudaStreamCreateWithPriority(&cap[pr], cudaStreamNonBlocking, pr ? hi : lo));
+  }
+  const int64_t before = ghn3::g_launches.load(std::memory_order_relaxed);
+  GHN3_CUDA(cudaStreamBeginCapture(cap[pr], cudaStreamCaptureModeRelaxed));
+  const int rc = ghn3_run_sequence(ops, n, (ghn3_stream_t)cap[pr]);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t end = cudaStreamEndCapture(cap[pr], &graph);
+  const int64_t captured = ghn3::g_launches.exchange(before, std::memory_order_relaxed) - before;   // nothing ran
+  if (rc != GHN3_OK) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    return rc;
+  }
+  if (end != cudaSuccess || graph == nullptr) {
+    (void)cudaGetLastError();
+    ghn3::set_error("ghn3_sequence_capture: cudaStreamEndCapture failed: %s", cudaGetErrorString(end));
+    return GHN3_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (inst != cudaSuccess) {
+    (void)cudaGetLastError();
+    ghn3::set_error("ghn3_sequence_capture: cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+    return GHN3_ERR_CUDA;
+  }
+  ghn3_sequence* s = new ghn3_sequence();
+  s->exec = exec;
+  s->launches = captured;
+  *out = s;
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_sequence_launch(ghn3_sequence* seq, ghn3_stream_t stream) {
+  if (seq == nullptr) {
+    ghn3::set_error("ghn3_sequence_launch: null sequence");
+    return GHN3_ERR_BAD_ARG;
+  }
+  GHN3_CUDA(cudaGraphLaunch(seq->exec, (cudaStream_t)stream));
+  ghn3::count_launch((int)seq->launches);
+  return GHN3_OK;
+}
+
+extern "C" int ghn3_sequence_destroy(ghn3_sequence* seq) {
+  if (seq == nullptr) return GHN3_OK;
+  const cudaError_t err = cudaGraphExecDestroy(seq->exec);
+  delete seq;
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    ghn3::set_error("ghn3_sequence_destroy: %s", cudaGetErrorString(err));
+    return GHN3_ERR_CUDA;
   }
   return GHN3_OK;
 }

@@ -45,6 +45,10 @@ FUSE_LN = bool(int(__import__('os').environ.get('GHN3_FUSE_LN', '0')))
 # = True` or GHN3_FUSED=1 turns it on.
 FUSED_DEFAULT = bool(int(__import__('os').environ.get('GHN3_FUSED', '0')))
 FUSED_MAX_NODES = int(__import__('os').environ.get('GHN3_FUSED_MAX_NODES', '1024'))
+# Inference programs replay their kernel sequence as CUDA graphs (ghn3_sequence_capture): one driver call instead of
+# ~180 launches per prediction. `ghn.cuda_graphs = False` or GHN3_CUDA_GRAPHS=0 issues the kernels one by one.
+GRAPHS_DEFAULT = bool(int(__import__('os').environ.get('GHN3_CUDA_GRAPHS', '1')))
+SCATTER_STREAM_DEFAULT = bool(int(__import__('os').environ.get('GHN3_SCATTER_STREAM', '1')))
 
 
 def log(*a, **k):
@@ -566,14 +570,18 @@ class GHN3(GHN):
         st = ov.get(device)
         if st is None:
             st = ov[device] = {'side': torch.cuda.Stream(device=device), 'hi': []}
+            # the write-bound scatter gets its own stream so that it runs beside the NEXT call's read-bound decoder
+            # GEMMs (HBM reads and writes together reach the copy bandwidth; either alone does not);
+            # `ghn.scatter_stream = False` keeps it behind the decoders on one stream
+            st['sc'] = torch.cuda.Stream(device=device) if getattr(self, 'scatter_stream', SCATTER_STREAM_DEFAULT) else st['side']
         while len(st['hi']) <= slot:
             st['hi'].append(torch.cuda.Stream(device=device, priority=-1))
-        return st['hi'][slot], st['side']
+        return st['hi'][slot], st['side'], st['sc']
 
     def flush_all(self):
         """Waits (on the current stream) for every overlapped prediction in flight, whatever program ran it."""
         for st in self.__dict__.get('_ov_streams', {}).values():
-            for strm in [st['side']] + st['hi']:
+            for strm in [st['side'], st['sc']] + st['hi']:
                 torch.cuda.current_stream().wait_stream(strm)
 
     def result_stream(self):
@@ -582,7 +590,7 @@ class GHN3(GHN):
         (e.g. param_norms + a D2H copy) can be enqueued there: `with torch.cuda.stream(ghn.result_stream()): ...`."""
         prog = getattr(self, 'last_program', None)
         if prog is not None and getattr(prog, 'ev_scatter', None) is not None:
-            return prog.side
+            return prog.sc
         return torch.cuda.current_stream()
 
     def flush(self):
@@ -632,6 +640,14 @@ class GHN3(GHN):
         """Device tensor [n_models] (float64): sum of squares of every parameter value written by the last forward
         call, accumulated inside the scatter kernel (no second pass over the parameters, no host sync)."""
         return self.last_program.pred_sumsq
+
+
+def _destroy_sequences(graphs):
+    """Frees the captured kernel sequences (CUDA graph executables) of a program."""
+    lib = L.load()
+    while graphs:
+        _, h = graphs.popitem()
+        lib.ghn3_sequence_destroy(ct.c_void_p(h))
 
 
 class _Program:
@@ -801,6 +817,16 @@ class _Program:
             self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
         self.bound_pack = None
         self.bwd = None
+        # CUDA-graph replay (inference programs): the graph pack's device arrays are mirrored into buffers this
+        # program owns, so that every kernel argument is fixed and the captured sequences stay valid for any pack
+        self.use_graphs = (not train and getattr(self, 'fused', None) is None
+                           and bool(getattr(ghn, 'cuda_graphs', GRAPHS_DEFAULT)))
+        self.mirror = None
+        self.graphs = {}
+        self.graph_key = None
+        self.runs = 0
+        self._finalizer = weakref.finalize(self, _destroy_sequences, self.graphs)
+        self._finalizer.atexit = False            # the CUDA context may already be gone at interpreter exit
 
     def bind_pack(self, pack):
         if pack is self.bound_pack:
@@ -809,15 +835,75 @@ class _Program:
         if getattr(pack, 'op_dev', None) is None:
             raise RuntimeError('internal: graph pack has no op ids')
         nf, ga = self.nf, self.ga
-        nf.op, nf.deg_in, nf.deg_out, nf.dist0 = L.ptr(pack.op_dev), L.ptr(pack.deg_in), L.ptr(pack.deg_out), \
-            L.ptr(pack.dist0)
         lut = self.ghn._lut(self.w, pack.cutoff)
         ga.n_graphs, ga.max_nodes, ga.lut_size = pack.n_graphs, pack.max_nodes, lut.shape[1]
-        ga.node_off, ga.mat_off = L.ptr(pack.d['node_off']), L.ptr(pack.d['mat_off'])
-        ga.pair, ga.lut = L.ptr(pack.pair), L.ptr(lut)
+        ga.lut = L.ptr(lut)
+        if self.use_graphs:
+            blob = pack._blob.dev
+            m = self.mirror
+            if m is None or m['blob'].numel() != blob.numel() or m['layout'] != pack.derived_layout:
+                self.drop_graphs()
+                m = self.mirror = {'blob': torch.empty_like(blob), 'derived': torch.empty_like(pack.derived),
+                                   'layout': pack.derived_layout}
+                off = {name: o for name, o, _ in pack._blob.parts}
+                b0 = m['blob'].data_ptr()
+                deg_in, deg_out, dist0, pair = ops.derived_views(m['derived'], pack.derived_layout)
+                nf.op, nf.deg_in, nf.deg_out, nf.dist0 = b0 + off['op'], L.ptr(deg_in), L.ptr(deg_out), L.ptr(dist0)
+                ga.node_off, ga.mat_off, ga.pair = b0 + off['node_off'], b0 + off['mat_off'], L.ptr(pair)
+                m['copies'] = (L.MemcpyArgs(dst=L.ptr(m['blob']), bytes=blob.numel()),
+                               L.MemcpyArgs(dst=L.ptr(m['derived']), bytes=pack.derived.numel()))
+                m['seq'] = (L.SeqOp * 2)()
+                for i, a in enumerate(m['copies']):
+                    m['seq'][i].op = 23
+                    m['seq'][i].args = ct.cast(ct.pointer(a), ct.c_void_p)
+            m['copies'][0].src, m['copies'][1].src = L.ptr(blob), L.ptr(pack.derived)
+            m['pending'] = True                   # copied by run() on the stream the kernels are launched on
+            self.graph_key = (ga.lut, pack.n_graphs, pack.max_nodes)
+        else:
+            nf.op, nf.deg_in, nf.deg_out, nf.dist0 = L.ptr(pack.op_dev), L.ptr(pack.deg_in), L.ptr(pack.deg_out), \
+                L.ptr(pack.dist0)
+            ga.node_off, ga.mat_off = L.ptr(pack.d['node_off']), L.ptr(pack.d['mat_off'])
+            ga.pair = L.ptr(pack.pair)
         if getattr(self, 'fused', None) is not None:
             self.fused.bind(pack, lut)
         self.bound_pack = pack
+
+    def drop_graphs(self):
+        _destroy_sequences(self.graphs)
+
+    def launch(self, i0, i1, stream_ptr, what, high_priority=False):
+        """Enqueues ops[i0:i1) on the stream: as a captured CUDA graph from the program's second run on (the first run
+        issues the kernels directly -- it also sets their function attributes), kernel by kernel otherwise."""
+        lib = L.load()
+        if i1 <= i0:
+            return
+        m = self.mirror
+        if m is not None and m.get('pending'):    # mirror this call's graph pack first (stream order = data order)
+            L.check(lib.ghn3_run_sequence(m['seq'], 2, ct.c_void_p(stream_ptr)), 'ghn3_run_sequence (pack mirror)')
+            m['pending'] = False
+        at = ct.c_void_p(ct.addressof(self.seq) + i0 * ct.sizeof(L.SeqOp))
+        if self.use_graphs and self.runs > 0:
+            key = (i0, i1, bool(high_priority), L._pdl_state[0]) + tuple(self.graph_key or ())
+            g = self.graphs.get(key)
+            if g is None:
+                h = ct.c_void_p()
+                rc = lib.ghn3_sequence_capture(at, i1 - i0, int(bool(high_priority)), ct.byref(h))
+                if rc != 0:                       # capture not possible here: keep launching kernel by kernel
+                    self.use_graphs = False
+                    self.capture_error = lib.ghn3_last_error().decode(errors='replace')
+                    if self.ghn.debug_level:
+                        log('ghn3_b200: CUDA-graph capture failed (%s); launching kernels one by one' %
+                            self.capture_error)
+                else:
+                    g = self.graphs[key] = h.value
+                    while len(self.graphs) > 16:
+                        old = next(iter(self.graphs))
+                        lib.ghn3_sequence_destroy(ct.c_void_p(self.graphs.pop(old)))
+            if g is not None:
+                L.check(lib.ghn3_sequence_launch(ct.c_void_p(g), ct.c_void_p(stream_ptr)),
+                        'ghn3_sequence_launch (%s)' % what)
+                return
+        L.check(lib.ghn3_run_sequence(at, i1 - i0, ct.c_void_p(stream_ptr)), 'ghn3_run_sequence (%s)' % what)
 
     def refresh_targets(self, weight_norm):
         """Re-reads the addresses of the target parameters; uploads the descriptor table only if one moved."""
@@ -886,7 +972,8 @@ class _Program:
                 self.ev_scatter = None
             if draw_tok:
                 self.tok.normal_(mean=0.0, std=0.02)
-            L.check(lib.ghn3_run_sequence(self.seq, len(self.ops), ct.c_void_p(stream)), 'ghn3_run_sequence')
+            self.launch(0, len(self.ops), stream, 'prediction')
+            self.runs += 1
             return
         if prof is None:
             # Overlapped form: [node features, Graphormer] -> wait for the PREVIOUS call's scatter (it reads the decoder
@@ -897,16 +984,14 @@ class _Program:
                 # the Graphormer stack runs on a HIGH-priority stream (one per program slot), decoders + scatter on a
                 # normal one shared by all programs (their scatters write the same targets: stream order = call order):
                 # when the two compete for SM slots the block scheduler serves the latency-bound chain first
-                self.hi, self.side = self.ghn._overlap_streams(self.device, self.slot)
+                self.hi, self.side, self.sc = self.ghn._overlap_streams(self.device, self.slot)
                 self.i_ln = next(i for i, (_, name_, _) in enumerate(self.ops) if name_ == 'layernorm')
                 self.ev_a = torch.cuda.Event()
                 self.ev_dec = None
-            hi, side = self.hi, self.side
+            hi, side, sc = self.hi, self.side, self.sc
             n_ops, i_ln, i_sc = len(self.ops), self.i_ln, len(self.ops) - 1
             split = self.ghn.__dict__.get('overlap_decoders', True)      # False: only the scatter leaves the main chain
-            at = lambda i: ct.c_void_p(ct.addressof(self.seq) + i * ct.sizeof(L.SeqOp))
-            run = lambda i0, i1, st_, what: L.check(lib.ghn3_run_sequence(at(i0), i1 - i0, ct.c_void_p(st_.cuda_stream)),
-                                                    'ghn3_run_sequence (%s)' % what)
+            run = lambda i0, i1, st_, what: self.launch(i0, i1, st_.cuda_stream, what, high_priority=st_ is hi)
             ev_in = torch.cuda.Event()
             ev_in.record(cur)                    # the graph pack was uploaded / derived on the caller's stream
             hi.wait_event(ev_in)
@@ -923,17 +1008,23 @@ class _Program:
             self.ev_a.record(hi)
             side.wait_event(self.ev_a)
             if split:
-                run(i_ln + 1, i_sc, side, 'decoders')        # ordered after the previous scatter by the stream itself
+                if ev_prev is not None and sc is not side:
+                    side.wait_event(ev_prev)     # this program's previous scatter still reads its decoder outputs
+                run(i_ln + 1, i_sc, side, 'decoders')
             ev_dec = torch.cuda.Event()
             ev_dec.record(side)
             self.ev_dec = ev_dec
+            # scatters of all programs on ONE stream (they write the same targets: stream order = call order)
+            if sc is not side:
+                sc.wait_event(ev_dec)
             if draw_tok:
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(sc):
                     self.tok.normal_(mean=0.0, std=0.02)
-            run(i_sc, n_ops, side, 'scatter')
+            run(i_sc, n_ops, sc, 'scatter')
             ev = torch.cuda.Event()
-            ev.record(side)
+            ev.record(sc)
             self.ev_scatter = ev
+            self.runs += 1
             return
         if ev_prev is not None:
             cur.wait_event(ev_prev)
@@ -945,6 +1036,9 @@ class _Program:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             prof.append((name, ev))
+        if self.mirror is not None and self.mirror.get('pending'):
+            L.check(lib.ghn3_run_sequence(self.mirror['seq'], 2, ct.c_void_p(stream)), 'ghn3_run_sequence (pack mirror)')
+            self.mirror['pending'] = False
         mark('start')
         per_op = getattr(prof, 'per_op', False)       # per-launch events (bench.py's roofline leg)
         for i, (stage, name, args) in enumerate(self.ops):

@@ -50,6 +50,13 @@ class HostBlob:
         return views
 
 
+def derived_views(buf, layout):
+    """(deg_in, deg_out, dist0, pair) views of a GraphPack.derived-style byte buffer."""
+    n_deg, seg, n_pair = layout
+    deg = [buf[i * seg:i * seg + n_deg * 4].view(torch.int32) for i in range(3)]
+    return deg[0], deg[1], deg[2], buf[3 * seg:3 * seg + n_pair * 2].view(torch.int16)
+
+
 class GraphPack:
     """
     Device-resident packed batch of graph structures: 1-hop edge lists (or user-supplied SPD matrices) on the way in;
@@ -109,13 +116,13 @@ class GraphPack:
         self.d = v
         self.spd = v.get('spd')
         self.op_dev = v.get('op')
-        self.pair = self.deg_in = self.deg_out = self.dist0 = None
+        self.pair = self.deg_in = self.deg_out = self.dist0 = self.derived = None
 
     def record_stream(self, stream):
         """Tells the caching allocator that `stream` reads this pack's buffers (they were allocated on another one)."""
         if getattr(self, '_recorded', None) is stream:
             return
-        for t in (self._blob.dev, self.spd, self.pair, self.deg_in, self.deg_out, self.dist0, getattr(self, '_bits', None)):
+        for t in (self._blob.dev, self.spd, getattr(self, 'derived', None), getattr(self, '_bits', None)):
             if isinstance(t, torch.Tensor) and t.is_cuda:
                 t.record_stream(stream)
         self._recorded = stream
@@ -145,10 +152,13 @@ class GraphPack:
                           bits_off=L.ptr(self.d['bits_off']), spd=L.ptr(self.spd))
             L.call('spd_bfs', a, stream)
             self._bits = bits
-        self.pair = torch.empty(max(mat_total, 16), dtype=torch.int16, device=dev)
-        self.deg_in = torch.empty(max(self.total_nodes, 1), dtype=torch.int32, device=dev)
-        self.deg_out = torch.empty_like(self.deg_in)
-        self.dist0 = torch.empty_like(self.deg_in)
+        # one allocation for everything the derive kernel writes ([deg_in | deg_out | dist0 | pair], 256-byte aligned
+        # parts): a program that replays a captured kernel sequence mirrors it with ONE device-to-device copy
+        n_deg = max(self.total_nodes, 1)
+        seg = (n_deg * 4 + 255) // 256 * 256
+        self.derived = torch.empty(3 * seg + max(mat_total, 16) * 2, dtype=torch.uint8, device=dev)
+        self.derived_layout = (n_deg, seg, max(mat_total, 16))
+        self.deg_in, self.deg_out, self.dist0, self.pair = derived_views(self.derived, self.derived_layout)
         a = L.DeriveArgs(n_graphs=self.n_graphs, vmax=self.cutoff, node_off=L.ptr(self.d['node_off']),
                          mat_off=L.ptr(self.d['mat_off']), max_nodes=self.max_nodes, total_nodes=self.total_nodes,
                          spd=L.ptr(self.spd), pair=L.ptr(self.pair), deg_in=L.ptr(self.deg_in),

@@ -700,12 +700,28 @@ enum ghn3_opcode {
   GHN3_OP_GRAPHORMER_TRAIN_FWD = 7, GHN3_OP_GRAPHORMER_BWD = 8, GHN3_OP_TRANSPOSE = 9, GHN3_OP_ELEMENTWISE = 10,
   GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
   GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18,
-  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21, GHN3_OP_GRAPHORMER_FUSED = 22
+  GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21, GHN3_OP_GRAPHORMER_FUSED = 22,
+  GHN3_OP_MEMCPY = 23
 };
 /* GHN3_OP_MEMSET: args points to a ghn3_memset_args; clears `bytes` bytes at `ptr` (cudaMemsetAsync). */
 typedef struct { void* ptr; int64_t bytes; } ghn3_memset_args;
+/* GHN3_OP_MEMCPY: args points to a ghn3_memcpy_args; device-to-device cudaMemcpyAsync of `bytes` bytes. */
+typedef struct { void* dst; const void* src; int64_t bytes; } ghn3_memcpy_args;
 typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
 int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);
+
+/* The same sequence recorded once as a CUDA graph and replayed with ONE driver call per prediction (183 kernel launches
+ * of `ghn(model)` cost 0.4-0.5 ms of host time when issued one by one; inside a graph dependent kernels also start
+ * with less latency). ghn3_sequence_capture records ops[0..n) on an internal capture stream -- nothing executes -- and
+ * instantiates the graph; every pointer and size in the argument structs (and the process-wide switches
+ * ghn3_set_programmatic_launch / ghn3_set_attention_tc_min) is frozen at that moment, so callers keep the buffers the
+ * structs name at fixed addresses and re-capture when anything else changes. high_priority != 0 gives the kernel nodes
+ * the priority of the device's highest-priority streams. Run the sequence once with ghn3_run_sequence before capturing
+ * it (first launches set function attributes). ghn3_launch_count() advances by the captured launch count per replay. */
+typedef struct ghn3_sequence ghn3_sequence;
+int ghn3_sequence_capture(const ghn3_op* ops, int32_t n, int32_t high_priority, ghn3_sequence** out);
+int ghn3_sequence_launch(ghn3_sequence* seq, ghn3_stream_t stream);
+int ghn3_sequence_destroy(ghn3_sequence* seq);
 
 /* dtype conversion helpers used when a checkpoint is prepared for the device (one-time, not on the hot path). */
 int ghn3_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, ghn3_stream_t stream);
