@@ -216,7 +216,8 @@ class AdamWArgs(C.Structure):
     _fields_ = [('params', vp), ('grads', vp), ('exp_avg', vp), ('exp_avg_sq', vp), ('offsets', vp), ('numels', vp),
                 ('chunk0', vp), ('chunk_tensor', vp), ('n_chunks', i64), ('total', i64), ('lr', f32), ('beta1', f32),
                 ('beta2', f32), ('eps', f32), ('weight_decay', f32), ('bias_correction1', f32),
-                ('bias_correction2', f32), ('max_norm', f32), ('sumsq', vp), ('loss', vp), ('skipped', vp)]
+                ('bias_correction2', f32), ('max_norm', f32), ('sumsq', vp), ('loss', vp), ('skipped', vp),
+                ('range_lo', i64), ('range_hi', i64), ('chunk_begin', i64), ('sumsq_ready', i32)]
 
 
 class SegnormArgs(C.Structure):

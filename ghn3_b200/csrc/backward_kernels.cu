@@ -903,11 +903,17 @@ __global__ void __launch_bounds__(256) sumsq_flat_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const ghn3_adamw_args a) {
-  const int t = a.chunk_tensor[blockIdx.x];
+  const int64_t chunk = (int64_t)blockIdx.x + a.chunk_begin;
+  const int t = a.chunk_tensor[chunk];
   const int64_t off = a.offsets[t];
   const int64_t n = a.numels[t];
-  const int64_t c0 = ((int64_t)blockIdx.x - a.chunk0[t]) * GHN3_ADAMW_CHUNK;
-  const int64_t c1 = min(c0 + (int64_t)GHN3_ADAMW_CHUNK, n);
+  int64_t c0 = (chunk - a.chunk0[t]) * GHN3_ADAMW_CHUNK;
+  int64_t c1 = min(c0 + (int64_t)GHN3_ADAMW_CHUNK, n);
+  if (a.range_hi > 0) {                    // this rank's shard of the flat buffers (bounds are multiples of 4)
+    c0 = max(c0, a.range_lo - off);
+    c1 = min(c1, a.range_hi - off);
+    if (c0 >= c1) return;
+  }
   float* __restrict__ p = a.params[t];
   const float* __restrict__ g = a.grads + off;
   float* __restrict__ m = a.exp_avg + off;
@@ -918,7 +924,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const ghn3_adamw_args a) {
     const double ss = *a.sumsq;
     const bool bad = !(ss == ss) || ss > 1e300 || (a.loss != nullptr && !isfinite(*a.loss));
     if (bad) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.skipped, 1);
+      if (blockIdx.x == 0 && threadIdx.x == 0 && a.sumsq_ready != 2) atomicAdd(a.skipped, 1);   // once per step
       return;
     }
   }
@@ -1186,8 +1192,21 @@ extern "C" int ghn3_adamw(const ghn3_adamw_args* a, ghn3_stream_t stream_) {
   GHN3_REQUIRE(a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->offsets && a->numels && a->chunk0 &&
                    a->chunk_tensor, "ghn3_adamw: null pointer");
   GHN3_REQUIRE(a->bias_correction1 > 0.f && a->bias_correction2 > 0.f, "ghn3_adamw: bias corrections must be positive");
-  if (a->max_norm > 0.f || a->skipped != nullptr) {
+  GHN3_REQUIRE(a->range_hi == 0 || (a->range_lo >= 0 && a->range_lo < a->range_hi && a->range_hi <= a->total &&
+                                    a->range_lo % 4 == 0 && a->range_hi % 4 == 0 && a->chunk_begin >= 0),
+               "ghn3_adamw: bad shard range [%lld, %lld)", (long long)a->range_lo, (long long)a->range_hi);
+  if (a->sumsq_ready < 0) {
+    // |g|^2 of this rank's slice only (-1: *sumsq is cleared first, -2: accumulated); the caller sums over the ranks
+    GHN3_REQUIRE(a->sumsq != nullptr && a->range_hi > 0, "ghn3_adamw: the slice norm needs sumsq and a shard range");
+    if (a->sumsq_ready == -1) GHN3_CUDA(cudaMemsetAsync(a->sumsq, 0, sizeof(double), stream));
+    sumsq_flat_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(a->grads + a->range_lo,
+                                                                    a->range_hi - a->range_lo, a->sumsq);
+    GHN3_LAUNCH_CHECK("sumsq_flat_kernel");
+    return GHN3_OK;
+  }
+  if ((a->max_norm > 0.f || a->skipped != nullptr) && !a->sumsq_ready) {
     GHN3_REQUIRE(a->sumsq != nullptr, "ghn3_adamw: clipping / the non-finite guard need the sumsq scratch double");
+    GHN3_REQUIRE(a->range_hi == 0, "ghn3_adamw: a sharded step needs the global |g|^2 from the caller (sumsq_ready)");
     GHN3_CUDA(cudaMemsetAsync(a->sumsq, 0, sizeof(double), stream));
     sumsq_flat_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(a->grads, a->total, a->sumsq);
     GHN3_LAUNCH_CHECK("sumsq_flat_kernel");

@@ -15,7 +15,8 @@ CHUNK = 8192
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, ghn, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
-        params, order, offs, _ = flat_layout(ghn)
+        params, order, offs, early = flat_layout(ghn)
+        self._ghn_ref, self._early = ghn, early
         super().__init__(order, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                      max_grad_norm=max_grad_norm))
         dev = order[0].device
@@ -45,6 +46,58 @@ class FusedAdamW(torch.optim.Optimizer):
         self.loss_for_guard = None
         self._step = 0
         self._checked = False
+        self._sync = None                          # GradSync(shard=True): sharded step, see enable_sharding
+        self._pflat = None
+        # flat start of every chunk (host): the chunks that intersect a shard are found by bisection
+        self._chunk_start = np.repeat(offs[:-1], chunks) + \
+            (np.arange(self._n_chunks, dtype=np.int64) - np.repeat(chunk0, chunks)) * CHUNK
+
+    def enable_sharding(self, sync):
+        """Data parallelism with a reduce-scattered gradient (train.GradSync(shard=True)): this rank updates only its
+        slice of each flat region -- AdamW over 1/N of the 2.6 GB of parameters and moments instead of all of them on
+        every rank -- and the updated parameters are all-gathered. The parameters become views of ONE flat fp32 buffer
+        (same layout as the gradient buffer) so that the all-gather writes them in place; the update itself is
+        arithmetically the same as the replicated one (the global gradient norm is summed over the ranks)."""
+        if sync is None or not getattr(sync, 'shard', False):
+            return False
+        self._sync = sync
+        self._flatten_params()
+        return True
+
+    def _flatten_params(self):
+        pflat = torch.zeros(self._total, dtype=torch.float32, device=self._dev)
+        with torch.no_grad():
+            for p, o in zip(self._order, self._offs[:-1]):
+                v = pflat[int(o):int(o) + p.numel()].view(p.shape)
+                v.copy_(p.detach())
+                p.data = v
+        self._pflat = pflat
+        self._ptrs_host = None
+        ghn = self._ghn_ref
+        ghn._dev = None                            # device weight copies alias the parameters' storage: rebuild
+        ghn.__dict__['_param_list'] = None
+
+    def _params_are_flat(self):
+        base = self._pflat.data_ptr()
+        n = len(self._order)
+        return all(self._order[i].data_ptr() == base + int(self._offs[i]) * 4 for i in (0, n // 2, n - 1))
+
+    def _chunk_range(self, lo, hi):
+        c0 = int(np.searchsorted(self._chunk_start, lo, side='right')) - 1
+        c1 = int(np.searchsorted(self._chunk_start, hi, side='left'))
+        return max(c0, 0), max(c1 - max(c0, 0), 0)
+
+    def gather_state(self):
+        """Sharded mode: all-gathers the moment slices so that every rank holds the full optimizer state (collective;
+        called by Trainer.save on every rank before rank 0 writes the checkpoint)."""
+        sync = self._sync
+        if sync is None:
+            return
+        for lo, hi in ((0, self._early), (self._early, self._total)):
+            if hi > lo:
+                a, b = sync.shard_of(lo, hi)
+                for buf in (self.exp_avg, self.exp_avg_sq):
+                    sync.dist.all_gather_into_tensor(buf[lo:hi], buf[a:b], group=sync.group)
 
     def _param_table(self):
         ptrs = [p.data_ptr() for p in self._order]
@@ -99,12 +152,34 @@ class FusedAdamW(torch.optim.Optimizer):
             a.loss = lg.data_ptr()
             self._loss_keep = lg
             self.loss_for_guard = None
-        L.call('adamw', a, L.current_stream())
+        sync = self._sync
+        if sync is None:
+            L.call('adamw', a, L.current_stream())
+            return loss
+        # ---- sharded step: |g|^2 of this rank's slices -> sum over ranks -> AdamW on the slices -> all-gather ----
+        if not self._params_are_flat():            # .to() / load_state_dict replaced the storages
+            self._flatten_params()
+            a.params = self._param_table().data_ptr()
+        regions = [(lo, hi) for lo, hi in ((0, self._early), (self._early, self._total)) if hi > lo]
+        shards = [sync.shard_of(lo, hi) for lo, hi in regions]
+        for k, (lo, hi) in enumerate(shards):
+            a.range_lo, a.range_hi, a.sumsq_ready = lo, hi, (-1 if k == 0 else -2)
+            L.call('adamw', a, L.current_stream())
+        sync.dist.all_reduce(self._sumsq, group=sync.group)
+        for k, (lo, hi) in enumerate(shards):
+            a.range_lo, a.range_hi = lo, hi
+            a.chunk_begin, a.n_chunks = self._chunk_range(lo, hi)
+            a.sumsq_ready = 1 if k == 0 else 2
+            L.call('adamw', a, L.current_stream())
+        for (lo, hi), (s0, s1) in zip(regions, shards):
+            sync.dist.all_gather_into_tensor(self._pflat[lo:hi], self._pflat[s0:s1], group=sync.group)
         return loss
 
     def state_dict(self):
         """Optimizer state for checkpoints (reference trainer.py:419-426 stores `optimizer.state_dict()`): the two flat
         moment buffers, in the [decoder | rest] layout of ghn3_b200.train.flat_layout, and the step count."""
+        if self._sync is not None:
+            self.gather_state()
         d = super().state_dict()
         d['flat'] = {'exp_avg': self.exp_avg.detach().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().clone(),
                      'step': self._step}

@@ -43,7 +43,7 @@ enum ghn3_dtype {
 enum ghn3_act { GHN3_ACT_NONE = 0, GHN3_ACT_RELU = 1, GHN3_ACT_GELU = 2 };
 
 const char* ghn3_last_error(void);
-#define GHN3_ABI_VERSION 2   /* bumped when an argument struct changes layout */
+#define GHN3_ABI_VERSION 3   /* bumped when an argument struct changes layout */
 int ghn3_abi_version(void);  /* == GHN3_ABI_VERSION of the header the library was built from */
 /* Process-wide switch of programmatic dependent launch (default on; GHN3_NO_PDL=1 starts with it off): with it every
  * kernel of a chain is made resident while its predecessor still runs -- lowest latency for ONE chain, but the parked
@@ -617,6 +617,16 @@ typedef struct {
    * Under data parallelism the gradients are already averaged over ranks, so every rank takes the same decision. */
   const float* loss;
   int32_t* skipped;
+  /* Sharded optimizer step (data parallelism with the gradient reduce-scattered over the ranks): only the elements
+   * with flat index in [range_lo, range_hi) are updated (both multiples of 4; range_hi = 0 means the whole buffer);
+   * chunk_begin = index of the first chunk that intersects the range, n_chunks = how many do. With sumsq_ready != 0
+   * *sumsq already holds |g|^2 of the WHOLE averaged gradient (the caller summed the shards' parts over the ranks)
+   * and is not recomputed (2 = the same, for the second and later ranges of one step: a skipped step is counted
+   * once). sumsq_ready = -1 / -2: no update at all -- |g|^2 of the elements in [range_lo, range_hi) is stored in /
+   * added to *sumsq (the per-rank part of the global norm). */
+  int64_t range_lo, range_hi;
+  int64_t chunk_begin;
+  int32_t sumsq_ready;
 } ghn3_adamw_args;
 int ghn3_adamw(const ghn3_adamw_args* args, ghn3_stream_t stream);
 

@@ -266,6 +266,25 @@ def test_two_rank_gradients_equal_single_rank_mean():
         assert float((g1[k] - g2[k]).abs().max()) / denom < 2e-3, k
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_rank_sharded_optimizer():
+    """Reduce-scattered gradient + sharded fused AdamW + parameter all-gather (GradSync(shard=True),
+    FusedAdamW.enable_sharding) against the replicated step: same parameters, same moments, same training losses."""
+    import os, subprocess, sys, tempfile
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tempfile.mkdtemp()
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
+           '127.0.0.1', '--master-port', '29733', os.path.join(repo, 'tests', 'ddp_shard_worker.py'), out]
+    subprocess.run(cmd, check=True, timeout=900, cwd=repo)
+    res = torch.load(os.path.join(out, 'res.pt'))
+    assert res['rs_err'] < 1e-6, res
+    assert res['opt_err'] < 2e-5 and res['moment_err'] < 1e-5, res
+    assert res['predict_err'] < 1e-4, res
+    assert res['params_equal'], res
+    for a, b in zip(res['losses_sharded'], res['losses_replicated']):
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1.0), res
+
+
 def test_fused_adamw_matches_torch_clip_and_adamw():
     """ghn3_adamw (clip + AdamW, one pass) against nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same grads."""
     from ghn3_b200.optim import FusedAdamW
