@@ -262,7 +262,7 @@ SYMBOLS = ['ghn3_last_error', 'ghn3_abi_version', 'ghn3_launch_count', 'ghn3_spd
            'ghn3_node_features', 'ghn3_edge_lut', 'ghn3_layernorm', 'ghn3_gemm', 'ghn3_gemm_simt', 'ghn3_attention',
            'ghn3_graphormer_stack', 'ghn3_graphormer_fused', 'ghn3_scatter', 'ghn3_sumsq', 'ghn3_relu_transpose', 'ghn3_convert_f32', 'ghn3_debug_gemm_trace', 'ghn3_run_sequence',
            'ghn3_graphormer_fused_sync_ints', 'ghn3_debug_fused_trace',
-           'ghn3_set_programmatic_launch', 'ghn3_set_attention_tc_min',
+           'ghn3_set_programmatic_launch', 'ghn3_set_attention_tc_min', 'ghn3_set_persistent_ctas',
            'ghn3_sequence_capture', 'ghn3_sequence_launch', 'ghn3_sequence_destroy']
 TRAIN_SYMBOLS = ['ghn3_transpose', 'ghn3_elementwise', 'ghn3_colsum', 'ghn3_layernorm_bwd', 'ghn3_attention_bwd',
                  'ghn3_scatter_bwd', 'ghn3_node_features_bwd', 'ghn3_edge_lut_bwd', 'ghn3_graphormer_train_fwd',
@@ -328,6 +328,17 @@ def set_programmatic_launch(enabled):
     if _pdl_state[0] is not enabled:
         load().ghn3_set_programmatic_launch(C.c_int(int(enabled)))
         _pdl_state[0] = enabled
+
+
+_cap_state = [None]
+
+
+def set_persistent_ctas(ctas):
+    """Process-wide grid cap of the persistent GEMM launches (see include/ghn3_b200.h); no-op if unchanged."""
+    ctas = int(ctas or 0)
+    if _cap_state[0] != ctas:
+        load().ghn3_set_persistent_ctas(C.c_int(ctas))
+        _cap_state[0] = ctas
 
 
 def launch_count():

@@ -26,6 +26,13 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_pdl{getenv("GHN3_NO_PDL") == nullptr ? 1 : 0};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
+// Throughput mode (several predictions in flight): the persistent weight-streaming GEMMs of one prediction's decoders
+// take one CTA with ~190 KB of shared memory on EVERY SM, so the Graphormer kernels of the next predictions cannot get
+// an SM until a decoder GEMM ends. Capping their grid at ~2/3 of the SMs costs the decoders ~6-16 % and leaves the rest
+// of the machine to the latency-bound chains: 1.05 -> 1.01 ms per step end to end (measured at 100 of 148).
+static std::atomic<int> g_persistent_cap{0};
+int persistent_cta_cap() { return g_persistent_cap.load(std::memory_order_relaxed); }
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -129,6 +136,9 @@ extern "C" int ghn3_abi_version(void) { return GHN3_ABI_VERSION; }
 extern "C" int ghn3_set_programmatic_launch(int enabled) {
   const int old = ghn3::g_pdl.exchange(enabled ? 1 : 0);
   return old;
+}
+extern "C" int ghn3_set_persistent_ctas(int ctas) {
+  return ghn3::g_persistent_cap.exchange(ctas > 0 ? ctas : 0);
 }
 extern "C" int64_t ghn3_launch_count(void) { return ghn3::g_launches.load(std::memory_order_relaxed); }
 

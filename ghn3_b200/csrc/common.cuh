@@ -92,6 +92,7 @@ int num_sms();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+int persistent_cta_cap();   // api.cu: ghn3_set_persistent_ctas
 bool pdl_enabled();     // api.cu: GHN3_NO_PDL=1 launches every kernel fully serialised (experiments)
 
 template <typename... KArgs, typename... Args>

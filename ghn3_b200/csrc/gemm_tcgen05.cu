@@ -41,6 +41,7 @@ struct GemmKernelArgs {
   int32_t b_dynamic;     // B is produced by an earlier kernel of the step: do not fetch it before pdl_wait()
   const int32_t* rowmap; // optional: output row of problem row m is rowmap[p.d_off + m] (d_off is then a table offset)
   int32_t n_tiles;       // grouped launches: length of `tiles` (the persistent kernel strides over it)
+  int32_t implicit_nt;   // persistent kernel on ONE problem (tiles == NULL): tile t = (M tile t / implicit_nt, N tile t % implicit_nt)
   // fused LayerNorm of the finished rows (residual GEMMs of the Graphormer stack): the CTA that completes the last
   // tile / K-split of a 128-row block normalises those rows of D (= the residual stream) into ln_out
   void* ln_out;
@@ -182,13 +183,19 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmKernelArgs& args, 
   const float* bias_s = (const float*)(rowoff_s + 32);
   const int tile_n = args.b_group > 0 ? args.b_group * args.b_outer : BN;   // valid columns of a full tile
   const int n_end = min(p.n, (nt + 1) * tile_n);
+  // the accumulator chunk after the current one is already on its way from TMEM while this one is converted and stored
+  uint32_t rn[32];
+  if (nt * tile_n < n_end) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), rn);
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     const int n0 = nt * tile_n + c0;
     if (n0 >= n_end) break;                    // warp-uniform
     uint32_t r[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
     tmem_ld_wait();
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) r[jj] = rn[jj];
+    if (c0 + 32 < BN && n0 + 32 < n_end)
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), rn);
     if (rows_valid <= 0) continue;             // warp-uniform
     auto row_off = [&](int row) -> int64_t { return rowoff_s[row]; };
     const bool bf16_out = args.out_dtype == GHN3_BF16;
@@ -198,12 +205,25 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmKernelArgs& args, 
     const bool vec_ok = (n0 + 32 <= n_end) && (((p.ldd * eb_out) & 15) == 0) &&
                         (((((args.rowmap ? 0 : p.d_off) + n0) * eb_out + (int64_t)(uintptr_t)args.d) & 15) == 0);
     // phase 1 (thread = accumulator row): bias + activation, convert, write the row into the staging block
-    const float b_lane = bias_s[c0 + lane];
-    const float b_row = (use_bias && args.bias_rows && lane < rows_valid)
-                            ? __ldg(args.bias + p.bias_off + m_base + lane) : 0.f;
+    // (the epilogue is instruction-latency bound -- ~1100 dependent warp instructions per 128 x 128 tile, ncu -- so the
+    // bias is only touched when there is one: column biases as 8 broadcast 16-byte shared-memory loads)
     float v[32];
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]) + __shfl_sync(0xffffffffu, b_lane, jj) + b_row;
+    for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(r[jj]);
+    if (use_bias) {                            // warp-uniform
+      if (args.bias_rows) {
+        const float b_row = lane < rows_valid ? __ldg(args.bias + p.bias_off + m_base + lane) : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] += b_row;
+      } else {
+        const float4* b4 = (const float4*)(bias_s + c0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 b = b4[c];
+          v[4 * c] += b.x; v[4 * c + 1] += b.y; v[4 * c + 2] += b.z; v[4 * c + 3] += b.w;
+        }
+      }
+    }
     // the activation is selected ONCE per chunk (a per-element runtime test gets if-converted and the erf
     // polynomial would issue, predicated off, for every element of every GEMM)
     if (!args.accumulate) {
@@ -604,6 +624,18 @@ __device__ __forceinline__ void epilogue_prepare_swapped(const GemmKernelArgs& a
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStagingBytes = 4 * (kStageBlock + kMetaBlock);
 
+// tile t of a persistent launch: from the tile list (grouped launches), or enumerated over the single problem with the
+// N tiles of one M tile adjacent (CTAs running side by side then share the activation rows in L2)
+__device__ __forceinline__ void fetch_tile(const GemmKernelArgs& args, int t, int4& tile, ghn3_gemm_problem& p) {
+  if (args.tiles != nullptr) {
+    tile = args.tiles[t];
+    p = args.problems[tile.x];
+  } else {
+    tile = make_int4(0, t / args.implicit_nt, t % args.implicit_nt, 0);
+    p = args.single;
+  }
+}
+
 template <int BN, int kStages, bool kX3>
 constexpr int gemm_persistent_smem_bytes() {
   return kStages * (kBlockM + BN) * kRowBytes * (kX3 ? 2 : 1) + kStagingBytes + 1024 + 256;
@@ -675,17 +707,11 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
       uint32_t it = 0;
       int4 tile_next = make_int4(0, 0, 0, 0);
       ghn3_gemm_problem p_next = {};
-      if ((int)blockIdx.x < n_tiles) {
-        tile_next = args.tiles[blockIdx.x];
-        p_next = args.problems[tile_next.x];
-      }
+      if ((int)blockIdx.x < n_tiles) fetch_tile(args, blockIdx.x, tile_next, p_next);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int4 tile = tile_next;
         const ghn3_gemm_problem p = p_next;
-        if (t + (int)gridDim.x < n_tiles) {
-          tile_next = args.tiles[t + gridDim.x];
-          p_next = args.problems[tile_next.x];
-        }
+        if (t + (int)gridDim.x < n_tiles) fetch_tile(args, t + gridDim.x, tile_next, p_next);
         // normal: activations (tma_a) fill the 128-row UMMA-A slot, weights (tma_b) the BN-row UMMA-B slot;
         // swapped: weights fill the 128-row slot, activations the BN-row slot
         const int act_row = p.a_row0 + tile.y * (kSwap ? BN : kBlockM);
@@ -748,17 +774,12 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tma_a, const 
     int j = 0;
     int4 tile_next = make_int4(0, 0, 0, 0);
     ghn3_gemm_problem p_next = {};
-    if ((int)blockIdx.x < n_tiles) {
-      tile_next = args.tiles[blockIdx.x];
-      p_next = args.problems[tile_next.x];
-    }
+    if ((int)blockIdx.x < n_tiles) fetch_tile(args, blockIdx.x, tile_next, p_next);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
       const int4 tile = tile_next;
       const ghn3_gemm_problem p = p_next;
-      if (t + (int)gridDim.x < n_tiles) {                 // descriptor of the next tile: latency hidden by this tile
-        tile_next = args.tiles[t + gridDim.x];
-        p_next = args.problems[tile_next.x];
-      }
+      // descriptor of the next tile: latency hidden by this tile
+      if (t + (int)gridDim.x < n_tiles) fetch_tile(args, t + gridDim.x, tile_next, p_next);
       const int ab = j & 1;
       if constexpr (kSwap) epilogue_prepare_swapped<BN>(args, p, tile.y, meta, lane);
       else epilogue_prepare<BN>(args, p, tile.y, tile.z, meta, q, lane, p.bias_off >= 0);
@@ -922,7 +943,9 @@ static int launch_gemm_persistent(const CUtensorMap& ma, const CUtensorMap& mb, 
   }
   // GHN3_PERSISTENT_CTAS < #SMs leaves SMs free for a latency-bound kernel chain running concurrently on another
   // stream (the weight-streaming GEMMs stay HBM-bound with ~2/3 of the SMs)
-  static const int cap = getenv("GHN3_PERSISTENT_CTAS") ? std::max(1, atoi(getenv("GHN3_PERSISTENT_CTAS"))) : 1 << 30;
+  static const int env_cap = getenv("GHN3_PERSISTENT_CTAS") ? std::max(1, atoi(getenv("GHN3_PERSISTENT_CTAS"))) : 0;
+  const int set_cap = persistent_cta_cap();                  // ghn3_set_persistent_ctas (0 = one CTA per SM)
+  const int cap = env_cap > 0 ? env_cap : (set_cap > 0 ? set_cap : 1 << 30);
   const dim3 grid((unsigned)std::min(std::min(n_tiles, num_sms()), cap));
   GHN3_CUDA(launch_pdl(gemm_tcgen05_persistent_kernel<kTf32, BN, kStages, kSwap, kX3>, grid, dim3(gemm_threads<kX3>()), (size_t)smem, stream, ma, mb,
                        ka));
@@ -1018,6 +1041,7 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
   ka.b_dynamic = a->b_dynamic;
   ka.rowmap = a->rowmap;
   ka.n_tiles = a->n_tiles;
+  ka.implicit_nt = 0;
   ka.ln_out = a->ln_out;
   ka.ln_gamma = a->ln_gamma;
   ka.ln_beta = a->ln_beta;
@@ -1039,6 +1063,19 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
     if (x3) return launch_gemm_persistent<true, 128, 3, false, true>(ma, mb, ka, a->n_tiles, stream);
     if (tf32) return launch_gemm_persistent<true, 128, 5, false, false>(ma, mb, ka, a->n_tiles, stream);
     return launch_gemm_persistent<false, 128, 5, false, false>(ma, mb, ka, a->n_tiles, stream);
+  }
+
+  // one large problem (all-architecture batches: M = 18 666 rows, K = C): per-tile launch / prologue / TMEM-allocation
+  // cost and the un-overlapped epilogue dominate a 6-block K loop, so run it on the persistent kernel too
+  static const bool no_persistent_single = getenv("GHN3_NO_PERSISTENT_SINGLE") != nullptr;
+  if (a->problems == nullptr && bn == 128 && splits == 1 && a->kb_list == nullptr && a->ln_out == nullptr &&
+      !no_persistent && !no_persistent_single && (int64_t)grid.x * grid.y >= 2 * num_sms()) {
+    ka.implicit_nt = (int)grid.x;
+    const int n_tiles = (int)(grid.x * grid.y);
+    ka.n_tiles = n_tiles;
+    if (x3) return launch_gemm_persistent<true, 128, 3, false, true>(ma, mb, ka, n_tiles, stream);
+    if (tf32) return launch_gemm_persistent<true, 128, 5, false, false>(ma, mb, ka, n_tiles, stream);
+    return launch_gemm_persistent<false, 128, 5, false, false>(ma, mb, ka, n_tiles, stream);
   }
 
   if (x3) {

@@ -547,6 +547,12 @@ class GHN3(GHN):
         # (each chain parks its next kernel's CTAs on the SMs); `programmatic_launch` = True / False overrides
         pdl = getattr(self, 'programmatic_launch', None)
         L.set_programmatic_launch(depth < 3 if pdl is None else pdl)
+        # throughput mode: the persistent decoder GEMMs leave ~1/3 of the SMs to the other predictions' Graphormer chains
+        # (`persistent_ctas` overrides; 0 = one CTA per SM)
+        cap = getattr(self, 'persistent_ctas', None)
+        if cap is None:
+            cap = (2 * torch.cuda.get_device_properties(device).multi_processor_count + 2) // 3 if depth >= 3 else 0
+        L.set_persistent_ctas(cap)
         progs = bp.__dict__.setdefault('programs', [])
         want = bool(return_embeddings)
         if any(p_.w is not w or p_.device != device or p_.want_emb != want for p_ in progs):
@@ -883,7 +889,7 @@ class _Program:
             m['pending'] = False
         at = ct.c_void_p(ct.addressof(self.seq) + i0 * ct.sizeof(L.SeqOp))
         if self.use_graphs and self.runs > 0:
-            key = (i0, i1, bool(high_priority), L._pdl_state[0]) + tuple(self.graph_key or ())
+            key = (i0, i1, bool(high_priority), L._pdl_state[0], L._cap_state[0]) + tuple(self.graph_key or ())
             g = self.graphs.get(key)
             if g is None:
                 h = ct.c_void_p()

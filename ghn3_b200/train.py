@@ -583,6 +583,7 @@ def forward_keep_grads(ghn, nets, graphs, w, bp, return_embeddings):
     device = ghn.embed.weight.device
     pdl = getattr(ghn, 'programmatic_launch', None)       # one chain at a time here: programmatic launch pays
     L.set_programmatic_launch(True if pdl is None else pdl)
+    L.set_persistent_ctas(getattr(ghn, 'persistent_ctas', None) or 0)      # one chain at a time: every SM
     prog = getattr(bp, 'train_program', None)
     if prog is None or prog.w is not w or prog.device != device or prog.want_emb != bool(return_embeddings):
         prog = _Program(ghn, w, bp, device, bool(return_embeddings), train=True)

@@ -50,6 +50,10 @@ int ghn3_abi_version(void);  /* == GHN3_ABI_VERSION of the header the library wa
  * CTAs hold SM resources, which costs throughput when several independent chains run side by side. Returns the
  * previous setting. */
 int ghn3_set_programmatic_launch(int enabled);
+/* Process-wide cap on the grid of the persistent (weight-streaming) GEMM launches: `ctas` > 0 leaves the other SMs to
+ * kernels of other streams (throughput mode, several predictions in flight); 0 = one CTA per SM (default; best for one
+ * prediction at a time). GHN3_PERSISTENT_CTAS in the environment overrides it. Returns the previous setting. */
+int ghn3_set_persistent_ctas(int ctas);
 /* Number of kernels this library has launched since load (all streams); backs bench.py's "gpu_launches". */
 int64_t ghn3_launch_count(void);
 
