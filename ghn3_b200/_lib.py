@@ -131,7 +131,7 @@ class ReluTransposeArgs(C.Structure):
 
 
 class SeqOp(C.Structure):
-    _fields_ = [('op', i32), ('reserved', i32), ('args', vp)]
+    _fields_ = [('op', i32), ('lane', i32), ('args', vp)]
 
 
 class SumsqArgs(C.Structure):

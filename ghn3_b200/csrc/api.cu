@@ -147,8 +147,31 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
     ghn3::set_error("ghn3_run_sequence: null op table");
     return GHN3_ERR_BAD_ARG;
   }
+  // auxiliary lane (ops[i].lane == 1): one library-owned stream + two events, shared by all sequences of the process
+  // (every use is bracketed by FORK / JOIN on the caller's stream, so sequences cannot interleave on it)
+  static cudaStream_t aux = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const ghn3_stream_t main_stream = stream;
   for (int i = 0; i < n; ++i) {
     int rc;
+    if (ops[i].op == GHN3_OP_FORK || ops[i].op == GHN3_OP_JOIN || ops[i].lane == 1) {
+      if (aux == nullptr) {
+        GHN3_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        GHN3_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        GHN3_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      }
+    }
+    if (ops[i].op == GHN3_OP_FORK) {
+      GHN3_CUDA(cudaEventRecord(ev_fork, (cudaStream_t)main_stream));
+      GHN3_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
+      continue;
+    }
+    if (ops[i].op == GHN3_OP_JOIN) {
+      GHN3_CUDA(cudaEventRecord(ev_join, aux));
+      GHN3_CUDA(cudaStreamWaitEvent((cudaStream_t)main_stream, ev_join, 0));
+      continue;
+    }
+    stream = ops[i].lane == 1 ? (ghn3_stream_t)aux : main_stream;
     switch (ops[i].op) {
       case GHN3_OP_NODE_FEATURES: rc = ghn3_node_features((const ghn3_node_features_args*)ops[i].args, stream); break;
       case GHN3_OP_GRAPHORMER: rc = ghn3_graphormer_stack((const ghn3_graphormer_args*)ops[i].args, stream); break;

@@ -48,6 +48,9 @@ FUSED_MAX_NODES = int(__import__('os').environ.get('GHN3_FUSED_MAX_NODES', '1024
 # Inference programs replay their kernel sequence as CUDA graphs (ghn3_sequence_capture): one driver call instead of
 # ~180 launches per prediction. `ghn.cuda_graphs = False` or GHN3_CUDA_GRAPHS=0 issues the kernels one by one.
 GRAPHS_DEFAULT = bool(int(__import__('os').environ.get('GHN3_CUDA_GRAPHS', '1')))
+# Two-lane decoder sequences: the 1-D decoder and the conv.2 column classes with few tiles run beside the large
+# weight-streaming launches (GHN3_OP_FORK / JOIN); `ghn.decoder_lanes = False` or GHN3_LANES=0 keeps one lane.
+LANES_DEFAULT = bool(int(__import__('os').environ.get('GHN3_LANES', '1')))
 SCATTER_STREAM_DEFAULT = bool(int(__import__('os').environ.get('GHN3_SCATTER_STREAM', '1')))
 
 
@@ -787,6 +790,7 @@ class _Program:
             self.ops.append(('heads_1d', 'gemm', gemm_args(d_in, w['d1_w0'], w['d1_b0'], ops.ACT_RELU, self.hid1, act)))
             self.ops.append(('heads_1d', 'gemm', gemm_args(self.hid1, w['d1_w1'], w['d1_b1'], ops.ACT_NONE, self.d1,
                                                            ops.F32)))
+            self._d1_ops = [self.ops[-2][2], self.ops[-1][2]]      # depend on the decoder input rows only
             bufs[SRC_D1] = self.d1
             if bp.n_clsb:
                 self.clsb = E(2 * bp.n_clsb, ncls, dtype=torch.float32)
@@ -795,6 +799,7 @@ class _Program:
                                     sdm=ncls, sdn=1, m=2 * bp.n_clsb, n=ncls, k=mc, relu_a=1, act=ops.ACT_NONE,
                                     batch=1)
                 self.ops.append(('heads_1d', 'gemm_simt', sa))
+                self._d1_ops.append(sa)
                 bufs[SRC_CLSB] = self.clsb
         self.tok = E(max(bp.n_tok_elems, 1), dtype=torch.float32)
         bufs[SRC_TOK] = self.tok
@@ -816,11 +821,48 @@ class _Program:
                                     chunk_desc=L.ptr(st['chunk_desc']), norm_out=L.ptr(self.pred_sumsq),
                                     n_norm_slots=len(bp.plans))
             self.ops.append(('scatter', 'scatter', self.sc))
-        # flat op table for ghn3_run_sequence
-        self.seq = (L.SeqOp * len(self.ops))()
-        for i, (_, name, args) in enumerate(self.ops):
-            self.seq[i].op = self.OP[name]
-            self.seq[i].args = ct.cast(ct.pointer(args), ct.c_void_p)
+        # flat op table for ghn3_run_sequence. `self.ops` stays in dependency order on one lane (the profiled path runs
+        # it op by op); the table may reorder the decoder ops onto two lanes:
+        #   main: fc -> conv.0 -> large conv.2 launches ........ JOIN -> class heads
+        #   aux:  FORK -> 1-D decoder      FORK(after conv.0) -> conv.2 column classes with few tiles
+        # The small launches are latency-bound (a K = 8C loop on a handful of tiles): next to the HBM-bound launches
+        # they are free, in front of them they cost ~0.1 ms per prediction.
+        names = [name for _, name, _ in self.ops]
+        i_ln0 = names.index('layernorm') if 'layernorm' in names else None
+        stage_of = [st_ for st_, _, _ in self.ops]
+        order = [(i, 0) for i in range(len(self.ops))]
+        lanes = (not train and i_ln0 is not None and R > 0 and bool(getattr(ghn, 'decoder_lanes', LANES_DEFAULT)))
+        if lanes:
+            n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+            pre = [i for i in range(len(self.ops)) if i <= i_ln0]
+            i_fc = [i for i, st_ in enumerate(stage_of) if st_ in ('dec_fc', 'dec_conv0')]
+            c2 = [i for i, st_ in enumerate(stage_of) if st_ == 'dec_conv2']
+            c2_small = [i for i, (g_, _, tl) in zip(c2, bp.c2_launches) if tl.shape[0] < 2 * n_sm]
+            c2_big = [i for i in c2 if i not in c2_small]
+            d1 = [i for i in range(len(self.ops)) if self.ops[i][2] in getattr(self, '_d1_ops', [])]
+            cls = [i for i, st_ in enumerate(stage_of) if st_ == 'heads_1d' and i not in d1]
+            tail = [i for i, st_ in enumerate(stage_of) if st_ == 'scatter']
+            if c2_big and (d1 or c2_small):
+                order = [(i, 0) for i in pre]
+                if d1:
+                    order += [('fork', 0)] + [(i, 1) for i in d1]
+                order += [(i, 0) for i in i_fc]
+                if c2_small:
+                    order += [('fork', 0)] + [(i, 1) for i in c2_small]
+                order += [(i, 0) for i in c2_big] + [('join', 0)] + [(i, 0) for i in cls] + [(i, 0) for i in tail]
+                assert sorted(i for i, _ in order if not isinstance(i, str)) == list(range(len(self.ops)))
+        self.seq = (L.SeqOp * len(order))()
+        self.seq_len = len(order)
+        for k, (i, lane) in enumerate(order):
+            if isinstance(i, str):
+                self.seq[k].op = 24 if i == 'fork' else 25
+                self.seq[k].args = None
+            else:
+                self.seq[k].op = self.OP[self.ops[i][1]]
+                self.seq[k].args = ct.cast(ct.pointer(self.ops[i][2]), ct.c_void_p)
+            self.seq[k].lane = lane
+        pos = {i: k for k, (i, _) in enumerate(order) if not isinstance(i, str)}
+        self.seq_ln = pos[i_ln0] if i_ln0 is not None else None          # table position of the final LayerNorm
         self.bound_pack = None
         self.bwd = None
         # CUDA-graph replay (inference programs): the graph pack's device arrays are mirrored into buffers this
@@ -978,7 +1020,7 @@ class _Program:
                 self.ev_scatter = None
             if draw_tok:
                 self.tok.normal_(mean=0.0, std=0.02)
-            self.launch(0, len(self.ops), stream, 'prediction')
+            self.launch(0, self.seq_len, stream, 'prediction')
             self.runs += 1
             return
         if prof is None:
@@ -991,11 +1033,11 @@ class _Program:
                 # normal one shared by all programs (their scatters write the same targets: stream order = call order):
                 # when the two compete for SM slots the block scheduler serves the latency-bound chain first
                 self.hi, self.side, self.sc = self.ghn._overlap_streams(self.device, self.slot)
-                self.i_ln = next(i for i, (_, name_, _) in enumerate(self.ops) if name_ == 'layernorm')
+                self.i_ln = self.seq_ln
                 self.ev_a = torch.cuda.Event()
                 self.ev_dec = None
             hi, side, sc = self.hi, self.side, self.sc
-            n_ops, i_ln, i_sc = len(self.ops), self.i_ln, len(self.ops) - 1
+            n_ops, i_ln, i_sc = self.seq_len, self.i_ln, self.seq_len - 1
             split = self.ghn.__dict__.get('overlap_decoders', True)      # False: only the scatter leaves the main chain
             run = lambda i0, i1, st_, what: self.launch(i0, i1, st_.cuda_stream, what, high_priority=st_ is hi)
             ev_in = torch.cuda.Event()

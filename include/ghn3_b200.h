@@ -715,13 +715,18 @@ enum ghn3_opcode {
   GHN3_OP_COLSUM = 11, GHN3_OP_LAYERNORM_BWD = 12, GHN3_OP_ATTENTION_BWD = 13, GHN3_OP_SCATTER_BWD = 14,
   GHN3_OP_NODE_FEATURES_BWD = 15, GHN3_OP_EDGE_LUT_BWD = 16, GHN3_OP_FC_BWD = 17, GHN3_OP_RELU_TRANSPOSE_BWD = 18,
   GHN3_OP_EXPAND_COLS = 19, GHN3_OP_MEMSET = 20, GHN3_OP_LAYERNORM = 21, GHN3_OP_GRAPHORMER_FUSED = 22,
-  GHN3_OP_MEMCPY = 23
+  GHN3_OP_MEMCPY = 23, GHN3_OP_FORK = 24, GHN3_OP_JOIN = 25
 };
 /* GHN3_OP_MEMSET: args points to a ghn3_memset_args; clears `bytes` bytes at `ptr` (cudaMemsetAsync). */
 typedef struct { void* ptr; int64_t bytes; } ghn3_memset_args;
 /* GHN3_OP_MEMCPY: args points to a ghn3_memcpy_args; device-to-device cudaMemcpyAsync of `bytes` bytes. */
 typedef struct { void* dst; const void* src; int64_t bytes; } ghn3_memcpy_args;
-typedef struct { int32_t op; int32_t reserved; const void* args; } ghn3_op;
+/* Two-lane sequences: an op with lane = 1 is issued on an auxiliary stream owned by the library, so that independent
+ * small launches (the 1-D decoder, column classes of conv.2 with few tiles) run beside the large ones instead of in
+ * front of them. GHN3_OP_FORK (args ignored) makes the auxiliary lane wait for everything issued on the main lane so
+ * far; GHN3_OP_JOIN makes the main lane wait for the auxiliary one -- a sequence that used lane 1 must end joined.
+ * Captured (ghn3_sequence_capture) the lanes become parallel branches of the graph. */
+typedef struct { int32_t op; int32_t lane; const void* args; } ghn3_op;
 int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t stream);
 
 /* The same sequence recorded once as a CUDA graph and replayed with ONE driver call per prediction (183 kernel launches
