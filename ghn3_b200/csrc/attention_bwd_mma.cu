@@ -39,6 +39,7 @@ __device__ __forceinline__ void bm_stage(__nv_bfloat16* dst, __nv_bfloat16* dstT
   using X = BmDims<D>;
   constexpr int HP = X::DK / 2;                   // bf16 pairs per row, padded
   const int rows64 = (rows + 63) & ~63;
+#pragma unroll 4                                   // four independent global loads in flight per thread
   for (int idx = threadIdx.x; idx < rows64 * HP; idx += blockDim.x) {
     const int j = idx / HP, d = (idx - j * HP) * 2;
     float v0 = 0.f, v1 = 0.f;
@@ -182,6 +183,21 @@ __global__ void __launch_bounds__(kBmWarps * 32, 2) attention_bwd_mma_dq_kernel(
 #pragma unroll
       for (int nt = 0; nt < kBmNT; ++nt) { pw0[nt] = nw0[nt]; pw1[nt] = nw1[nt]; }
       if (k0 + c0 + kBmChunk < n) load_pairs(k0 + c0 + kBmChunk);   // next chunk's indices: in flight during this chunk's MMAs
+      // running dS sums of this chunk: all loads are issued here, ahead of the MMAs (issued one by one at their
+      // read-modify-write site they serialise -- a store may alias the next load -- into 8 L2 round trips per chunk)
+      float2 acc0[kBmNT], acc1[kBmNT];
+      if (dsp != nullptr) {
+#pragma unroll
+        for (int nt = 0; nt < kBmNT; ++nt) {
+          const int col = k0 + c0 + nt * 8 + 2 * tq;
+          acc0[nt] = make_float2(0.f, 0.f);
+          acc1[nt] = make_float2(0.f, 0.f);
+          if (col < n) {
+            if (ok0) acc0[nt] = __ldcg((const float2*)(dsp + (int64_t)r0 * ld + col));
+            if (ok1) acc1[nt] = __ldcg((const float2*)(dsp + (int64_t)r1 * ld + col));
+          }
+        }
+      }
       float s[kBmNT][4], dp[kBmNT][4];
 #pragma unroll
       for (int nt = 0; nt < kBmNT; ++nt) {
@@ -211,18 +227,12 @@ __global__ void __launch_bounds__(kBmWarps * 32, 2) attention_bwd_mma_dq_kernel(
         s[nt][2] = p10 * (dp[nt][2] - dl1);
         s[nt][3] = p11 * (dp[nt][3] - dl1);
         if (dsp != nullptr && v0) {                      // running sum of dS over the layers (one owner per element)
-          if (ok0) {
-            float2* t = (float2*)(dsp + (int64_t)r0 * ld + col);      // col even, ld multiple of 16: 8-byte aligned
-            float2 cur = *t;
-            cur.x += s[nt][0]; cur.y += s[nt][1];                     // s[nt][1] is 0 for an invalid column
-            *t = cur;
-          }
-          if (ok1) {
-            float2* t = (float2*)(dsp + (int64_t)r1 * ld + col);
-            float2 cur = *t;
-            cur.x += s[nt][2]; cur.y += s[nt][3];
-            *t = cur;
-          }
+          if (ok0)                                       // col even, ld multiple of 16: 8-byte aligned;
+            __stcg((float2*)(dsp + (int64_t)r0 * ld + col),                  // s[nt][1] is 0 for an invalid column
+                   make_float2(acc0[nt].x + s[nt][0], acc0[nt].y + s[nt][1]));
+          if (ok1)
+            __stcg((float2*)(dsp + (int64_t)r1 * ld + col),
+                   make_float2(acc1[nt].x + s[nt][2], acc1[nt].y + s[nt][3]));
         }
       }
 #pragma unroll
