@@ -55,7 +55,7 @@ class GemmArgs(C.Structure):
                 ('single', GemmProblem), ('problems', vp), ('tiles', vp), ('n_tiles', i32), ('block_n', i32),
                 ('k_splits', i32), ('tf32_x3', i32), ('b_group', i32), ('b_group_stride', i32), ('bias_rows', i32), ('b_dynamic', i32), ('rowmap', vp), ('swap_ab', i32), ('ln_out', vp),
                 ('ln_gamma', vp), ('ln_beta', vp), ('ln_counters', vp), ('ln_out_dtype', i32), ('kb_list', vp),
-                ('kb_off', vp)]
+                ('kb_off', vp), ('persistent_single', i32)]
 
 
 class GemmSimtArgs(C.Structure):

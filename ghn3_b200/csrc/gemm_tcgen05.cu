@@ -1065,11 +1065,11 @@ int gemm_impl(const ghn3_gemm_args* a, cudaStream_t stream) {
     return launch_gemm_persistent<false, 128, 5, false, false>(ma, mb, ka, a->n_tiles, stream);
   }
 
-  // one large problem (all-architecture batches: M = 18 666 rows, K = C): per-tile launch / prologue / TMEM-allocation
-  // cost and the un-overlapped epilogue dominate a 6-block K loop, so run it on the persistent kernel too
-  static const bool no_persistent_single = getenv("GHN3_NO_PERSISTENT_SINGLE") != nullptr;
+  // one large problem on the persistent kernel (opt-in: measured equal to two one-tile CTAs per SM, see the header)
+  static const bool env_persistent_single = getenv("GHN3_PERSISTENT_SINGLE") != nullptr;
   if (a->problems == nullptr && bn == 128 && splits == 1 && a->kb_list == nullptr && a->ln_out == nullptr &&
-      !no_persistent && !no_persistent_single && (int64_t)grid.x * grid.y >= 2 * num_sms()) {
+      !no_persistent && (a->persistent_single || env_persistent_single) &&
+      (int64_t)grid.x * grid.y >= 2 * num_sms()) {
     ka.implicit_nt = (int)grid.x;
     const int n_tiles = (int)(grid.x * grid.y);
     ka.n_tiles = n_tiles;

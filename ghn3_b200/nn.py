@@ -558,6 +558,15 @@ class GHN3(GHN):
         L.set_persistent_ctas(cap)
         progs = bp.__dict__.setdefault('programs', [])
         want = bool(return_embeddings)
+        if not progs and not self.__dict__.get('_pool_reserved'):
+            # Every new program allocates ~20 workspace buffers that stay alive with its plan; served one cudaMalloc at
+            # a time that is 2-3 ms per cold prediction. One block handed to torch's caching allocator up front (it
+            # splits cached blocks) covers a whole model zoo. `ghn.reserve_bytes = 0` switches it off.
+            self.__dict__['_pool_reserved'] = True
+            nbytes = int(getattr(self, 'reserve_bytes', 1 << 29))
+            if nbytes > 0 and torch.cuda.mem_get_info(device)[0] > 8 * nbytes:
+                del_me = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                del del_me
         if any(p_.w is not w or p_.device != device or p_.want_emb != want for p_ in progs):
             self.flush_all()
             del progs[:]

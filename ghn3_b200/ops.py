@@ -212,7 +212,7 @@ def layernorm(x, gamma, beta, out_dtype=BF16, dst_row=None, out_rows=None, out_f
 
 
 def gemm(a, b, bias=None, act=ACT_NONE, in_dtype=BF16, out=None, out_dtype=F32, accumulate=False, problems=None,
-         tiles=None, block_n=0, single=None, k_splits=0, x3=False, b_group=0, b_group_stride=0, bias_rows=False, b_dynamic=True, rowmap=None, swap_ab=False):
+         tiles=None, block_n=0, single=None, k_splits=0, x3=False, b_group=0, b_group_stride=0, bias_rows=False, b_dynamic=True, rowmap=None, swap_ab=False, persistent_single=False):
     """
     D = act(A @ B^T + bias). A [a_rows, K], B [b_rows, K] row-major CUDA tensors of the in_dtype storage type.
     Either a single problem covering all of A and B (default, or `single` = dict) or a grouped launch
@@ -228,7 +228,8 @@ def gemm(a, b, bias=None, act=ACT_NONE, in_dtype=BF16, out=None, out_dtype=F32, 
                    k=K, in_dtype=in_dtype, d=L.ptr(out), out_dtype=out_dtype, bias=L.ptr(bias), act=act,
                    accumulate=int(accumulate), block_n=block_n, k_splits=k_splits, tf32_x3=int(x3),
                    b_group=b_group, b_group_stride=b_group_stride, bias_rows=int(bias_rows),
-                   b_dynamic=int(b_dynamic), rowmap=L.ptr(rowmap), swap_ab=int(swap_ab))
+                   b_dynamic=int(b_dynamic), rowmap=L.ptr(rowmap), swap_ab=int(swap_ab),
+                   persistent_single=int(persistent_single))
     if problems is not None:
         g.problems = L.ptr(problems)
         g.tiles = L.ptr(tiles)

@@ -12,6 +12,8 @@ Nothing in this file touches the GPU or does floating-point work on parameters.
 """
 from collections import OrderedDict
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -24,6 +26,7 @@ try:
 except Exception:  # pragma: no cover
     _VitEncoder = ()
 
+_ATTR_NAMES = frozenset(('weight', 'bias', 'in_proj_weight', 'in_proj_bias', 'pos_embedding'))
 _PARAM_ATTRS = (('weight', '.weight', True), ('bias', '.bias', False), ('in_proj_weight', '.in_proj_weight', True),
                 ('in_proj_bias', '.in_proj_bias', False), ('pos_embedding', '.pos_embedding.weight', True))
 
@@ -50,8 +53,18 @@ def layered_modules(model):
     cells = [OrderedDict() for _ in range(n_cells)]
     for name, mod in model.named_modules():
         hits = []
+        md = mod.__dict__
+        pd = md.get('_parameters', {})
+        if not pd and _ATTR_NAMES.isdisjoint(md) and _ATTR_NAMES.isdisjoint(type(mod).__dict__):
+            continue                       # containers, activations, ...: nothing to predict
         for attr, suffix, is_w in _PARAM_ATTRS:
-            p = getattr(mod, attr, None)
+            # registered parameter, then plain attribute (the shape lists of parameter-free modules, tensors set by a
+            # keep_grads prediction); nn.Module.__getattr__ for a missing name costs ~2 us x 8 names x every module
+            p = pd.get(attr)
+            if p is None:
+                p = md.get(attr)
+                if p is None and hasattr(type(mod), attr):
+                    p = getattr(mod, attr, None)
             if p is None or isinstance(p, bool) or not isinstance(p, (torch.Tensor, list, tuple)):
                 continue
             hits.append((name + suffix, p, is_w))
@@ -195,7 +208,7 @@ class ModelPlan:
                 n_t = 2 if (len(tsz) == 1 and entry['is_w'] and getattr(entry['module'], 'bias', None) is not None) \
                     else 1
                 self.n_tensors += n_t
-                self.n_params += int(np.prod(tsz)) * n_t
+                self.n_params += math.prod(int(v) for v in tsz) * n_t
 
     def prune_unmatched(self):
         """reduce_graph=True (nn.py:684-690): parameters of modules that no graph node refers to are set to None."""
@@ -246,7 +259,7 @@ def scale_for(sz):
         return 1.0
     no_relu = len(sz) > 2 and (sz[1] == 1 or sz[2] < sz[3])
     beta = 1.0 if no_relu else 2.0
-    return float(np.float32((beta / float(np.prod(sz[1:]))) ** 0.5))
+    return float(np.float32((beta / float(math.prod(int(v) for v in sz[1:]))) ** 0.5))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -267,15 +280,34 @@ C2_DENSE_BLOCK_N = int(_os.environ.get('GHN3_C2_BLOCK_N', '128'))    # N tile of
 
 
 def tiles_for(problems, block_m=128, block_n=128):
-    out = []
-    for p, prob in enumerate(problems):
-        mt, nt = -(-int(prob['m']) // block_m), -(-int(prob['n']) // block_n)
-        grid = np.stack(np.meshgrid(np.arange(mt), np.arange(nt), indexing='ij'), -1).reshape(-1, 2)
-        t = np.zeros((len(grid), 4), dtype=np.int32)
-        t[:, 0] = p
-        t[:, 1:3] = grid
-        out.append(t)
-    return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.int32)
+    """(problem, M tile, N tile, 0) rows for every tile of every problem, N tiles of one M tile adjacent."""
+    if len(problems) == 0:
+        return np.zeros((0, 4), dtype=np.int32)
+    mt = -(-problems['m'].astype(np.int64) // block_m)
+    nt = -(-problems['n'].astype(np.int64) // block_n)
+    cnt = mt * nt
+    total = int(cnt.sum())
+    p = np.repeat(np.arange(len(problems), dtype=np.int64), cnt)
+    local = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    ntp = nt[p]
+    t = np.zeros((total, 4), dtype=np.int32)
+    t[:, 0] = p
+    t[:, 1] = local // np.maximum(ntp, 1)
+    t[:, 2] = local % np.maximum(ntp, 1)
+    return t
+
+
+def fastdiv_array(d):
+    """Vectorised _lib.fastdiv: (mul, shift) arrays with n // d == (n * mul >> 32) >> shift, mul == 0 for d <= 1."""
+    d = np.asarray(d, dtype=np.int64)
+    big = d > 1
+    dd = np.where(big, d, 2)
+    s = np.ceil(np.log2(dd.astype(np.float64))).astype(np.int64)
+    s += (1 << s) < dd                         # guard against rounding of log2 just below a power of two
+    s -= ((1 << (s - 1)) >= dd) & (s > 1)
+    mul = -((-(np.int64(1) << (31 + s))) // dd)
+    assert bool((mul[big] < (1 << 32)).all())
+    return np.where(big, mul, 0).astype(np.uint32), np.where(big, s - 1, 0).astype(np.uint32)
 
 
 class BatchPlan:
@@ -369,23 +401,26 @@ class BatchPlan:
             b, t = conv[q]
             dst_row[offs[b] + t.node] = r
         wins = np.array([conv[q][1].win for q in fc_order], dtype=np.int64).reshape(-1, 4)
-        rowmap = []
-        for py in range(S):
-            for px in range(S):
-                if len(wins) == 0:
-                    break
-                need = np.nonzero((wins[:, 0] <= py) & (py < wins[:, 1]) & (wins[:, 2] <= px) & (px < wins[:, 3]))[0]
-                if len(need) == 0:
-                    continue
-                pos = py * S + px
-                breaks = np.nonzero(np.diff(need) != 1)[0] + 1
-                for run in np.split(need, breaks):
-                    fc_probs.append((int(run[0]), pos * 4 * C, len(run), 4 * C, len(rowmap), 4 * C, pos * 4 * C))
-                    for r in run:
-                        q = fc_order[r]
-                        row0, P, kwp, khp = self.conv_rows[q]
-                        y0, _, x0, _ = conv[q][1].win
-                        rowmap.append(row0 + (py - y0) * kwp + (px - x0))
+        rowmap = np.zeros(0, dtype=np.int64)
+        if len(wins):
+            # need[pos, r]: decoder-grid position pos = py * S + px lies inside the window of the r-th node (fc order);
+            # one fc problem per run of consecutive r at a position, (node, position) rows through the row map
+            py, px = np.divmod(np.arange(S * S, dtype=np.int64), S)
+            need = ((wins[None, :, 0] <= py[:, None]) & (py[:, None] < wins[None, :, 1]) &
+                    (wins[None, :, 2] <= px[:, None]) & (px[:, None] < wins[None, :, 3]))
+            pos_i, r_i = np.nonzero(need)                              # position-major, r ascending
+            first = np.ones(len(pos_i), dtype=bool)
+            first[1:] = (pos_i[1:] != pos_i[:-1]) | (r_i[1:] != r_i[:-1] + 1)
+            starts = np.nonzero(first)[0]
+            lens = np.diff(np.append(starts, len(pos_i)))
+            order_arr = np.asarray(fc_order, dtype=np.int64)
+            rows_arr = np.asarray(self.conv_rows, dtype=np.int64).reshape(-1, 4)     # (row0, P, kwp, khp) per conv node
+            q_i = order_arr[r_i]
+            wq = wins[r_i]
+            rowmap = rows_arr[q_i, 0] + (py[pos_i] - wq[:, 0]) * rows_arr[q_i, 2] + (px[pos_i] - wq[:, 2])
+            for st_, ln_ in zip(starts.tolist(), lens.tolist()):
+                pos = int(pos_i[st_])
+                fc_probs.append((int(r_i[st_]), pos * 4 * C, ln_, 4 * C, st_, 4 * C, pos * 4 * C))
         self.fc_rowmap = np.asarray(rowmap, dtype=np.int32)
         self.clsw_elems = clsw_elems
         self.fc_problems = np.array(fc_probs, dtype=PROBLEM_DT) if fc_probs else np.zeros(0, PROBLEM_DT)
@@ -432,19 +467,17 @@ class BatchPlan:
 
         cur_model = [0]
 
+        FIELDS = ('t1', 't2', 't3', 'so', 'si', 'ld', 'ca', 'ra', 'kh_src', 'kw_src', 'cy', 'cx', 'scale', 'mode')
+        DEFAULTS = (1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1.0, 0)
+
         def add(module, attr, shape, src_buf, src_off, **f):
-            numel = int(np.prod(shape))
-            d = np.zeros((), dtype=DESC_DT)
-            d['numel'] = numel
-            d['norm_slot'] = cur_model[0]
-            for k_, v in dict(t1=1, t2=1, t3=1, so=1, si=1, ld=0, ca=0, ra=0, kh_src=1, kw_src=1, cy=0, cx=0,
-                              scale=1.0, mode=0).items():
-                d[k_] = f.get(k_, v)
-            for f_ in ('t1', 't2', 't3', 'so', 'si'):
-                d['m_' + f_], d['s_' + f_] = fastdiv(int(d[f_]))
+            # plain tuples here, ONE structured array at the end (a numpy record per call costs ~40 us)
+            numel = 1
+            for v in shape:
+                numel *= int(v)
             if numel >= (1 << 31):
                 raise NotImplementedError('target tensors with 2^31 or more elements are not supported')
-            recs.append(d)
+            recs.append((numel, cur_model[0]) + tuple(f.get(k_, v) for k_, v in zip(FIELDS, DEFAULTS)))
             # view: 'full' = the whole parameter; 'tok' / 'body' = row 0 / rows 1.. of a ViT pos_embedding
             targets.append((module, attr, tuple(shape), f.get('view', 'full')))
             srcs.append((src_buf, int(src_off)))
@@ -510,7 +543,14 @@ class BatchPlan:
             else:
                 add(mod, param_attr(mod, False), tsz, SRC_D1, row_off + max_ch, so=max_ch, ca=1, mode=2)
 
-        self.desc_static = np.array(recs, dtype=DESC_DT) if recs else np.zeros(0, DESC_DT)
+        self.desc_static = np.zeros(len(recs), dtype=DESC_DT)
+        if recs:
+            cols = list(zip(*recs))
+            self.desc_static['numel'], self.desc_static['norm_slot'] = cols[0], cols[1]
+            for k_, col in zip(FIELDS, cols[2:]):
+                self.desc_static[k_] = col
+            for f_ in ('t1', 't2', 't3', 'so', 'si'):
+                self.desc_static['m_' + f_], self.desc_static['s_' + f_] = fastdiv_array(self.desc_static[f_])
         self.desc_targets = targets
         self.desc_src_buf = np.array([s_[0] for s_ in srcs], dtype=np.int64)
         self.desc_src_off = np.array([s_[1] for s_ in srcs], dtype=np.uint64)

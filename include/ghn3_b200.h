@@ -229,6 +229,10 @@ typedef struct {
    * skipped and leaves D untouched (the caller pre-zeroes D). Device arrays; NULL = dense. */
   const int32_t* kb_list;
   const int32_t* kb_off;
+  /* single-problem launches: 1 = run on the persistent kernel (one CTA per SM walks tiles enumerated in the kernel,
+   * epilogue of tile j under the main loop of tile j + 1). Measured equal to two one-tile CTAs per SM on the K = C GEMMs
+   * of an 18 666-row batch (the epilogue warps are the limit either way), so 0 (off) is the default. */
+  int32_t persistent_single;
 } ghn3_gemm_args;
 
 int ghn3_gemm(const ghn3_gemm_args* args, ghn3_stream_t stream);

@@ -86,8 +86,8 @@ def test_gemm_block_n(block_n):
 
 @pytest.mark.parametrize('mode', ['bf16', 'tf32', 'x3'])
 def test_gemm_large_single_problem_persistent(mode):
-    """One problem with >= 2 x #SMs tiles runs on the persistent kernel with enumerated tiles (the Graphormer GEMMs of an
-    all-architecture batch: M = 18 666, K = C): bias + GELU into the activation dtype, residual accumulation, ragged
+    """One problem with >= 2 x #SMs tiles on the persistent kernel with enumerated tiles (ghn3_gemm_args.persistent_single;
+    the Graphormer GEMMs of an all-architecture batch: M = 18 666, K = C): bias + GELU into the activation dtype, residual accumulation, ragged
     M / N edges."""
     torch.manual_seed(5)
     m, n, k = 128 * 40 + 37, 128 * 9 + 72, 384            # 41 x 10 = 410 tiles
@@ -101,16 +101,18 @@ def test_gemm_large_single_problem_persistent(mode):
     else:
         a_in, b_in, dt, x3, tol = a, b, ops.TF32, True, 3e-5
     lin = a_in.double() @ b_in.double().t() + bias.double()
-    out = ops.gemm(a_in, b_in, bias=bias, in_dtype=dt, out_dtype=ops.F32, x3=x3, block_n=128)
+    out = ops.gemm(a_in, b_in, bias=bias, in_dtype=dt, out_dtype=ops.F32, x3=x3, block_n=128, persistent_single=True)
     torch.cuda.synchronize()
     assert _rel(out, lin.float()) < tol
     act_dt = ops.BF16 if mode == 'bf16' else ops.F32
-    out = ops.gemm(a_in, b_in, bias=bias, act=ops.ACT_GELU, in_dtype=dt, out_dtype=act_dt, x3=x3, block_n=128)
+    out = ops.gemm(a_in, b_in, bias=bias, act=ops.ACT_GELU, in_dtype=dt, out_dtype=act_dt, x3=x3, block_n=128,
+                   persistent_single=True)
     torch.cuda.synchronize()
     assert _rel(out, torch.nn.functional.gelu(lin).float()) < (1e-2 if mode == 'bf16' else 1e-4)
     x = torch.randn(m, n, device=DEV)
     ref = (x.double() + lin).float()
-    ops.gemm(a_in, b_in, bias=bias, in_dtype=dt, out=x, out_dtype=ops.F32, accumulate=True, x3=x3, block_n=128)
+    ops.gemm(a_in, b_in, bias=bias, in_dtype=dt, out=x, out_dtype=ops.F32, accumulate=True, x3=x3, block_n=128,
+             persistent_single=True)
     torch.cuda.synchronize()
     assert _rel(x, ref) < tol
 

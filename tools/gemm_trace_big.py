@@ -3,7 +3,6 @@ import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from ghn3_b200 import ops, _lib as L
-os.environ.setdefault('GHN3_NO_PERSISTENT_SINGLE', '1')     # the traced kernel is the one-tile-per-CTA kernel
 dev = 'cuda'
 lib = L.load()
 buf = torch.zeros(4096, 8, dtype=torch.int64, device=dev)
