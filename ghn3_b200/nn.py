@@ -504,9 +504,10 @@ class GHN3(GHN):
                 _, old = self._plan_cache.popitem(last=False)
                 # drop the programs' buffers explicitly: program -> pred_flat -> grad_fn -> ctx -> program is a cycle
                 # through C++ autograd nodes that the garbage collector does not see
-                progs = list(old.__dict__.get('programs', [])) + [old.__dict__.get('program'),
+                progs = list(old.__dict__.get('programs', [])) + list(old.__dict__.get('programs_shared', [])) + \
+                    [old.__dict__.get('program'),
                                                                    old.__dict__.get('train_program')]
-                for attr in ('program', 'programs', 'train_program', 'dev', 'out_meta'):
+                for attr in ('program', 'programs', 'programs_shared', 'train_program', 'dev', 'out_meta'):
                     old.__dict__.pop(attr, None)
                 for prog in progs:
                     if prog is not None and prog is not self.__dict__.get('last_program'):
@@ -556,23 +557,15 @@ class GHN3(GHN):
         if cap is None:
             cap = (2 * torch.cuda.get_device_properties(device).multi_processor_count + 2) // 3 if depth >= 3 else 0
         L.set_persistent_ctas(cap)
-        progs = bp.__dict__.setdefault('programs', [])
+        share = not overlap and prof is None and bool(getattr(self, 'share_workspaces', True))
+        progs = bp.__dict__.setdefault('programs_shared' if share else 'programs', [])
         want = bool(return_embeddings)
-        if not progs and not self.__dict__.get('_pool_reserved'):
-            # Every new program allocates ~20 workspace buffers that stay alive with its plan; served one cudaMalloc at
-            # a time that is 2-3 ms per cold prediction. One block handed to torch's caching allocator up front (it
-            # splits cached blocks) covers a whole model zoo. `ghn.reserve_bytes = 0` switches it off.
-            self.__dict__['_pool_reserved'] = True
-            nbytes = int(getattr(self, 'reserve_bytes', 1 << 29))
-            if nbytes > 0 and torch.cuda.mem_get_info(device)[0] > 8 * nbytes:
-                del_me = torch.empty(nbytes, dtype=torch.uint8, device=device)
-                del del_me
         if any(p_.w is not w or p_.device != device or p_.want_emb != want for p_ in progs):
             self.flush_all()
             del progs[:]
         slot = bp.__dict__.get('next_slot', 0) % depth
         while len(progs) <= slot:
-            progs.append(_Program(self, w, bp, device, want, slot=len(progs)))
+            progs.append(_Program(self, w, bp, device, want, slot=len(progs), shared=share))
         prog = progs[slot]
         bp.next_slot = slot + 1
         bp.program = prog
@@ -660,6 +653,43 @@ class GHN3(GHN):
         return self.last_program.pred_sumsq
 
 
+class _SharedWorkspace:
+    """Grow-only temporaries shared by the serial-mode programs of one (GHN, device, stream): the k-th buffer a program
+    asks for is a typed view of the k-th shared block; a block that is too small is replaced by a larger one (programs
+    built earlier keep their views of the old block alive)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.blocks = []
+        self.k = 0
+
+    @classmethod
+    def of(cls, ghn, device):
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        table = ghn.__dict__.setdefault('_shared_ws', {})
+        ws = table.get(key)
+        if ws is None:
+            ws = table[key] = cls(device)
+        ws.k = 0                               # a new program starts at the first block
+        return ws
+
+    def empty(self, shape, dtype):
+        numel = 1
+        for v in shape:
+            numel *= int(v)
+        nbytes = max(numel * dtype.itemsize, 1)
+        k = self.k
+        self.k += 1
+        if k == len(self.blocks):
+            self.blocks.append(None)
+        blk = self.blocks[k]
+        if blk is None or blk.numel() < nbytes:
+            # grow with some head-room so that a zoo of similar models settles after a few allocations
+            blk = self.blocks[k] = torch.empty((nbytes * 5 // 4 + 255) // 256 * 256, dtype=torch.uint8,
+                                               device=self.device)
+        return blk[:numel * dtype.itemsize].view(dtype).view(*[int(v) for v in shape])
+
+
 def _destroy_sequences(graphs):
     """Frees the captured kernel sequences (CUDA graph executables) of a program."""
     lib = L.load()
@@ -676,7 +706,7 @@ class _Program:
     OP = {'node_features': 1, 'graphormer_stack': 2, 'gemm': 3, 'gemm_simt': 4, 'scatter': 5, 'relu_transpose': 6,
           'graphormer_train_fwd': 7, 'layernorm': 21, 'graphormer_fused': 22}
 
-    def __init__(self, ghn, w, bp, device, want_emb, train=False, slot=0):
+    def __init__(self, ghn, w, bp, device, want_emb, train=False, slot=0, shared=False):
         self.w, self.bp, self.device, self.want_emb = w, bp, device, want_emb
         self.train = train
         self.slot = slot
@@ -688,7 +718,15 @@ class _Program:
         st = ghn._static_device(bp, device)
         self.st = st
         N = bp.total_nodes
-        E = lambda *shape, dtype=tdt: torch.empty(*shape, dtype=dtype, device=device)
+        # `shared` (programs of the one-prediction-at-a-time mode): the per-call temporaries are views of grow-only
+        # buffers owned by the GHN and shared by the programs of ALL batch plans -- they run one after the other on one
+        # stream. A model zoo then needs the workspace of its largest model once instead of one set per architecture
+        # (hundreds of MB each at XL, kept alive with the plan), and a cold prediction skips ~20 cudaMallocs (~3 ms).
+        # Programs of the overlapped mode run side by side and keep private buffers.
+        self.shared = bool(shared) and not train
+        ws = _SharedWorkspace.of(ghn, device) if self.shared else None
+        E = (lambda *shape, dtype=tdt: ws.empty(shape, dtype)) if ws is not None else \
+            (lambda *shape, dtype=tdt: torch.empty(*shape, dtype=dtype, device=device))
         self.keep = []
         self.ops = []            # (stage label, op code, ctypes args struct)
         # ---- node features ----
@@ -706,7 +744,7 @@ class _Program:
         # ---- Graphormer stack + final LN scattered into the decoder input rows ----
         n_dec = bp.n_conv + bp.n_1d
         self.dec_in = E(max(n_dec, 1), C)
-        self.emb = E(N, C, dtype=torch.float32) if want_emb else None
+        self.emb = torch.empty(N, C, dtype=torch.float32, device=device) if want_emb else None   # returned to the caller
         self.h, self.qkv, self.ff = E(N, C), E(N, 3 * C), E(N, 4 * C)
         self.h2 = E(N, C)
         self.ln_counters = torch.zeros((N + 127) // 128 + 1, dtype=torch.int32, device=device)
