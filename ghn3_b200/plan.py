@@ -101,6 +101,7 @@ class ShapeIndexer:
         self.ch_table = self._table(ch, {c: 8 for c in range(4, 8)})
         self.sp_table = self._table(sp, {2: 3})
         self.dummy = np.array([self.n_ch, self.n_ch, self.n_sp, self.n_sp], dtype=np.int32)
+        self._memo = {}
 
     @staticmethod
     def _table(bins, alias):
@@ -125,7 +126,14 @@ class ShapeIndexer:
         return cls._cache[key]
 
     def lookup(self, sz):
+        """int32[4] index row of a tensor shape (memoised: a model zoo repeats a few hundred shapes)."""
         sz = tuple(int(v) for v in sz)
+        hit = self._memo.get(sz)
+        if hit is None:
+            hit = self._memo[sz] = self._lookup(sz)
+        return hit
+
+    def _lookup(self, sz):
         if len(sz) == 1:
             sz = (sz[0], 1)
         if len(sz) == 2:
@@ -247,14 +255,25 @@ class ModelPlan:
     def _window(t, kh, kw, S):
         """Centred crop of the S x S decoder grid (nn.py:742-747) -> (y0, y1, x0, x1); bilinear flag (nn.py:751)."""
         off = S // 2
-        y0, y1 = max(0, off - kh // 2), min(S, off + int(np.ceil(kh / 2)))
-        x0, x1 = max(0, off - kw // 2), min(S, off + int(np.ceil(kw / 2)))
+        y0, y1 = max(0, off - kh // 2), min(S, off + (kh + 1) // 2)
+        x0, x1 = max(0, off - kw // 2), min(S, off + (kw + 1) // 2)
         t.win = (y0, y1, x0, x1)
         t.interp = min(kh, kw) > min(min(S, kh), min(S, kw))
 
 
+_scale_memo = {}
+
+
 def scale_for(sz):
     """Fan-in normalisation factor of nn.py:562-583 for a tensor of shape sz (>1-D); rounded once to fp32."""
+    key = tuple(int(v) for v in sz)
+    hit = _scale_memo.get(key)
+    if hit is None:
+        hit = _scale_memo[key] = _scale_for(key)
+    return hit
+
+
+def _scale_for(sz):
     if len(sz) > 2 and sz[2] >= 11 and sz[0] == 1:
         return 1.0
     no_relu = len(sz) > 2 and (sz[1] == 1 or sz[2] < sz[3])

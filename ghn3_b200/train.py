@@ -413,6 +413,11 @@ class _Backward:
         self.d_lut.zero_()
         live = []
         if self.n_desc:
+            # the pinned table is read by an asynchronous H2D copy: the previous step's copy must have run before the
+            # host rewrites it (the Trainer step has no other host synchronisation)
+            ev_ptrs = getattr(self, 'ev_ptrs', None)
+            if ev_ptrs is not None:
+                ev_ptrs.synchronize()
             host = self.grad_ptrs_np
             flat_ptr = 0
             if flat_grad is not None:
@@ -443,6 +448,8 @@ class _Backward:
                 else:
                     host[i] = 0
             self.grad_ptrs.copy_(self.grad_ptrs_host, non_blocking=True)
+            self.ev_ptrs = torch.cuda.Event()
+            self.ev_ptrs.record()
         stream = L.current_stream()
         lib = L.load()
         nd = self.n_decoder_ops
