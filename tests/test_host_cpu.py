@@ -288,6 +288,60 @@ def test_flat_gradient_layout_and_conv2_block_lists():
         assert len(dl) < (-(-R // 128)) * (KF // bk)                  # and they do skip something
 
 
+def test_flat_layout_regions_split_into_equal_aligned_shards():
+    """Sharded optimizer step: both regions of the flat gradient / parameter layout are multiples of FLAT_PAD elements,
+    so every world size dividing FLAT_PAD / 4 gets equal 16-byte aligned slices; the chunk range of a slice found by
+    bisection covers exactly the chunks that intersect it."""
+    from ghn3_b200.nn import GHN3
+    from ghn3_b200.train import FLAT_PAD, flat_layout
+    ghn = GHN3(**CONFIGS['ghn3tiny'], weight_norm=True, ve=True)
+    params, order, offs, early = flat_layout(ghn)
+    total = int(offs[-1])
+    assert early % FLAT_PAD == 0 and total % FLAT_PAD == 0 and 0 < early < total
+    assert all(int(offs[i]) + order[i].numel() <= int(offs[i + 1]) for i in range(len(order)))
+    CH = 8192
+    numels = np.array([p.numel() for p in order], dtype=np.int64)
+    chunks = (numels + CH - 1) // CH
+    chunk0 = np.concatenate([[0], np.cumsum(chunks)[:-1]])
+    start = np.repeat(offs[:-1], chunks) + (np.arange(int(chunks.sum())) - np.repeat(chunk0, chunks)) * CH
+    end = np.minimum(start + CH, np.repeat(offs[:-1] + numels, chunks))
+    for world in (2, 4, 8):
+        for lo_r, hi_r in ((0, early), (early, total)):
+            n = (hi_r - lo_r) // world
+            assert n % 4 == 0
+            for r in range(world):
+                lo, hi = lo_r + r * n, lo_r + (r + 1) * n
+                c0 = max(int(np.searchsorted(start, lo, side='right')) - 1, 0)
+                c1 = int(np.searchsorted(start, hi, side='left'))
+                hit = np.nonzero((end > lo) & (start < hi))[0]
+                assert len(hit) == 0 or (c0 <= hit[0] and hit[-1] < c1)
+
+
+def test_vectorised_plan_helpers_match_their_scalar_definitions():
+    """tiles_for (one vectorised pass over all problems) against the per-problem enumeration; fastdiv_array against the
+    scalar magic-number routine the scatter descriptors were defined with."""
+    from ghn3_b200._lib import fastdiv
+    from ghn3_b200.plan import PROBLEM_DT, fastdiv_array, tiles_for
+    rs = np.random.RandomState(0)
+    probs = np.zeros(37, dtype=PROBLEM_DT)
+    probs['m'] = rs.randint(0, 700, 37)
+    probs['n'] = rs.randint(0, 1500, 37)
+    for bm, bn in ((128, 128), (64, 128), (128, 120)):
+        want = [(p, i, j, 0) for p in range(37) for i in range(-(-int(probs['m'][p]) // bm))
+                for j in range(-(-int(probs['n'][p]) // bn))]
+        got = tiles_for(probs, block_m=bm, block_n=bn)
+        assert got.dtype == np.int32 and got.tolist() == [list(t) for t in want]
+    assert tiles_for(probs[:0]).shape == (0, 4)
+    ds = np.concatenate([np.arange(0, 3000), 2 ** np.arange(1, 31), 2 ** np.arange(1, 31) - 1, 2 ** np.arange(1, 31) + 1,
+                         rs.randint(1, 2 ** 31 - 1, 5000)])
+    mul, sh = fastdiv_array(ds)
+    assert all((int(a), int(b)) == fastdiv(int(d)) for a, b, d in zip(mul, sh, ds))
+    n = rs.randint(0, 2 ** 31 - 1, 2000).astype(np.uint64)
+    for d in (3, 7, 24, 384, 1000, 65537):
+        m_, s_ = fastdiv(d)
+        assert np.array_equal((n * np.uint64(m_) >> np.uint64(32)) >> np.uint64(s_), n // np.uint64(d))
+
+
 def test_net_generator_is_deterministic_and_within_the_design_space():
     from ghn3_b200.deepnets import NetGenerator, CHANNELS, OPS
     a, b = NetGenerator(seed=3), NetGenerator(seed=3)
