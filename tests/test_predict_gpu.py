@@ -163,7 +163,7 @@ def test_fused_graphormer_end_to_end(cfg_name, archs):
 
 def test_trace_on_the_fly_graphs_none():
     """The drop-in call of the reference README: model = ghn(model) with no prebuilt graph (host tracer + CUDA SPD)."""
-    ghn, cfg = make_ghn('ghn3tiny', 'bf16')
+    ghn, cfg = make_ghn('ghn3tiny', 'tf32')      # two runs are compared at 1e-4: bf16 run-to-run noise can exceed that
     m1, m2 = H.build_model('resnet18').to(DEV), H.build_model('resnet18').to(DEV)
     with torch.no_grad():
         out = ghn(m1)                                                  # traced here
@@ -409,7 +409,7 @@ def test_compute_copy_cache_beside_checkpoint(tmp_path):
     path = str(tmp_path / 'ghn.pt')
     torch.save({'state_dict': sd, 'config': dict(cfg, weight_norm=True, ve=True)}, path)
     rec = H.graph_records()['resnet50']
-    outs = []
+    outs, copies = [], []
     for hit in (False, True):
         ghn = from_pretrained(path, compute_dtype='bf16', cache_compute_copy=True).to(DEV).eval()
         model = H.build_model('resnet50').to(DEV)
@@ -419,8 +419,12 @@ def test_compute_copy_cache_beside_checkpoint(tmp_path):
         assert os.path.exists(path + '.bf16.cache')
         assert ghn._compute_cache_hit is hit
         outs.append([p.detach().clone() for p in model.parameters()])
+        copies.append({k: ghn._dev[k].detach().clone() for k in ghn._CACHED})
+    for k in copies[0]:                                  # the cached copies ARE the converted weights, bit for bit
+        assert torch.equal(copies[0][k], copies[1][k]), k
     for a, b in zip(*outs):
-        assert H.max_rel_err(a, b) < 1e-4
+        # two bf16 predictions differ by their own run-to-run noise (fp32 atomics order -> bf16 rounding flips)
+        assert H.max_rel_err(a, b) < 5e-3
     # a changed checkpoint invalidates the cache
     sd2 = {k: v * 1.5 for k, v in sd.items()}
     torch.save({'state_dict': sd2, 'config': dict(cfg, weight_norm=True, ve=True), 'pad': 1}, path)
