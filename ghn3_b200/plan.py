@@ -45,6 +45,17 @@ def cell_index(name, n_cells):
     return None
 
 
+_cls_attr_memo = {}
+
+
+def _class_level_attrs(cls):
+    """Names of _ATTR_NAMES defined on the class (or a base) rather than per instance: properties, class defaults."""
+    hit = _cls_attr_memo.get(cls)
+    if hit is None:
+        hit = _cls_attr_memo[cls] = frozenset(a for a in _ATTR_NAMES if hasattr(cls, a))
+    return hit
+
+
 def layered_modules(model):
     """[{param_name: entry}] per cell; entry = dict(param_name, module, is_w, sz)."""
     if hasattr(model, 'module'):
@@ -55,7 +66,8 @@ def layered_modules(model):
         hits = []
         md = mod.__dict__
         pd = md.get('_parameters', {})
-        if not pd and _ATTR_NAMES.isdisjoint(md) and _ATTR_NAMES.isdisjoint(type(mod).__dict__):
+        cls_attrs = _class_level_attrs(type(mod))
+        if not pd and not cls_attrs and _ATTR_NAMES.isdisjoint(md):
             continue                       # containers, activations, ...: nothing to predict
         for attr, suffix, is_w in _PARAM_ATTRS:
             # registered parameter, then plain attribute (the shape lists of parameter-free modules, tensors set by a
@@ -63,7 +75,7 @@ def layered_modules(model):
             p = pd.get(attr)
             if p is None:
                 p = md.get(attr)
-                if p is None and hasattr(type(mod), attr):
+                if p is None and attr in cls_attrs:
                     p = getattr(mod, attr, None)
             if p is None or isinstance(p, bool) or not isinstance(p, (torch.Tensor, list, tuple)):
                 continue
@@ -487,18 +499,18 @@ class BatchPlan:
         cur_model = [0]
 
         FIELDS = ('t1', 't2', 't3', 'so', 'si', 'ld', 'ca', 'ra', 'kh_src', 'kw_src', 'cy', 'cx', 'scale', 'mode')
-        DEFAULTS = (1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1.0, 0)
 
-        def add(module, attr, shape, src_buf, src_off, **f):
+        def add(module, attr, shape, src_buf, src_off, t1=1, t2=1, t3=1, so=1, si=1, ld=0, ca=0, ra=0, kh_src=1,
+                kw_src=1, cy=0, cx=0, scale=1.0, mode=0, view='full'):
             # plain tuples here, ONE structured array at the end (a numpy record per call costs ~40 us)
             numel = 1
             for v in shape:
                 numel *= int(v)
             if numel >= (1 << 31):
                 raise NotImplementedError('target tensors with 2^31 or more elements are not supported')
-            recs.append((numel, cur_model[0]) + tuple(f.get(k_, v) for k_, v in zip(FIELDS, DEFAULTS)))
+            recs.append((numel, cur_model[0], t1, t2, t3, so, si, ld, ca, ra, kh_src, kw_src, cy, cx, scale, mode))
             # view: 'full' = the whole parameter; 'tok' / 'body' = row 0 / rows 1.. of a ViT pos_embedding
-            targets.append((module, attr, tuple(shape), f.get('view', 'full')))
+            targets.append((module, attr, tuple(shape), view))
             srcs.append((src_buf, int(src_off)))
 
         for q, (b, t) in enumerate(self.conv):
