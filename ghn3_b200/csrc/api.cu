@@ -149,17 +149,28 @@ extern "C" int ghn3_run_sequence(const ghn3_op* ops, int32_t n, ghn3_stream_t st
   }
   // auxiliary lane (ops[i].lane == 1): one library-owned stream + two events, shared by all sequences of the process
   // (every use is bracketed by FORK / JOIN on the caller's stream, so sequences cannot interleave on it)
-  static cudaStream_t aux = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // (one set per device: streams and events belong to the device that was current when they were created)
+  constexpr int kMaxDev = 64;
+  static cudaStream_t aux_of[kMaxDev] = {};
+  static cudaEvent_t ev_fork_of[kMaxDev] = {}, ev_join_of[kMaxDev] = {};
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   const ghn3_stream_t main_stream = stream;
   for (int i = 0; i < n; ++i) {
     int rc;
-    if (ops[i].op == GHN3_OP_FORK || ops[i].op == GHN3_OP_JOIN || ops[i].lane == 1) {
-      if (aux == nullptr) {
-        GHN3_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-        GHN3_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        GHN3_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    if (aux == nullptr && (ops[i].op == GHN3_OP_FORK || ops[i].op == GHN3_OP_JOIN || ops[i].lane == 1)) {
+      int dev = 0;
+      GHN3_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= kMaxDev) {
+        ghn3::set_error("ghn3_run_sequence: device ordinal %d out of range for the auxiliary lane", dev);
+        return GHN3_ERR_BAD_ARG;
       }
+      if (aux_of[dev] == nullptr) {
+        GHN3_CUDA(cudaStreamCreateWithFlags(&aux_of[dev], cudaStreamNonBlocking));
+        GHN3_CUDA(cudaEventCreateWithFlags(&ev_fork_of[dev], cudaEventDisableTiming));
+        GHN3_CUDA(cudaEventCreateWithFlags(&ev_join_of[dev], cudaEventDisableTiming));
+      }
+      aux = aux_of[dev]; ev_fork = ev_fork_of[dev]; ev_join = ev_join_of[dev];
     }
     if (ops[i].op == GHN3_OP_FORK) {
       GHN3_CUDA(cudaEventRecord(ev_fork, (cudaStream_t)main_stream));
@@ -235,8 +246,16 @@ extern "C" int ghn3_sequence_capture(const ghn3_op* ops, int32_t n, int32_t high
   *out = nullptr;
   // the caller's stream may be the legacy default stream, which cannot be captured: record on streams of our own
   // (one per priority class; kernel nodes inherit the capturing stream's priority)
-  static cudaStream_t cap[2] = {nullptr, nullptr};
+  constexpr int kMaxDev = 64;
+  static cudaStream_t cap_of[kMaxDev][2] = {};
   const int pr = high_priority ? 1 : 0;
+  int dev = 0;
+  GHN3_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) {
+    ghn3::set_error("ghn3_sequence_capture: device ordinal %d out of range", dev);
+    return GHN3_ERR_BAD_ARG;
+  }
+  cudaStream_t* cap = cap_of[dev];
   if (cap[pr] == nullptr) {
     int lo = 0, hi = 0;
     GHN3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
